@@ -1,0 +1,142 @@
+/* mtgseg_b200 — C ABI of the B200 (sm_100a) implementation of the card-segmentation hot path.
+ *
+ * Drop-in boundary for the network the reference builds in train/model.py:18-48 (torchvision LR-ASPP on a
+ * dilated MobileNetV3-Large with the reference's 3x3 head, train/model.py:92-142) as driven by
+ * train/train.py:67-153 and train/evaluate.py:41-100.  The reference has no FFI of its own (it is pure
+ * Python on top of torch/torchvision); each entry point below names the Python call it stands in for.
+ * The Python binding a maintainer adds is shown in INTEGRATION.md (ctypes, ~40 lines).
+ *
+ * Conventions
+ *   - plain C: ints, sizes, raw DEVICE pointers; `stream` is a cudaStream_t passed as void*.
+ *   - every call is asynchronous on `stream`, allocates nothing, and never synchronises the device.
+ *   - the caller owns all memory (weights, packed arena, workspace, outputs).
+ *   - return 0 on success, <0 on error (MTGSEG_ERR_*); mtgseg_last_error() gives the thread-local message.
+ *     Unsupported shapes / dtypes are errors: there is no fallback path of any kind.
+ */
+#ifndef MTGSEG_B200_H
+#define MTGSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTGSEG_ABI_VERSION 1
+
+#define MTGSEG_OK 0
+#define MTGSEG_ERR_ARG (-1)
+#define MTGSEG_ERR_CUDA (-2)
+#define MTGSEG_ERR_UNSUPPORTED (-3)
+#define MTGSEG_ERR_WORKSPACE (-4)
+
+/* logits element types (output of the network; input of the metric kernel) */
+#define MTGSEG_LOGITS_NONE 0
+#define MTGSEG_LOGITS_F32 1
+#define MTGSEG_LOGITS_BF16 2
+#define MTGSEG_LOGITS_F16 3
+
+/* activation codes of the per-op entry points */
+#define MTGSEG_ACT_NONE 0
+#define MTGSEG_ACT_RELU 1
+#define MTGSEG_ACT_HSWISH 2
+#define MTGSEG_ACT_HSIGMOID 3
+#define MTGSEG_ACT_SIGMOID 4
+
+/* The architecture is fixed by the reference (create_model, train/model.py:145-156); only the input size
+ * (train/config.py:21-22), the class count (config.py:20) and the head width (model.py:47) vary. */
+typedef struct mtgseg_net_desc {
+  int32_t in_h;           /* Config.INPUT_HEIGHT, 320 */
+  int32_t in_w;           /* Config.INPUT_WIDTH, 240  */
+  int32_t num_classes;    /* Config.NUM_CLASSES, 2    */
+  int32_t inter_channels; /* LRASPPHead inter_channels, 128 */
+} mtgseg_net_desc;
+
+int mtgseg_version(void);
+const char* mtgseg_last_error(void);
+
+/* Number of state_dict entries expected by mtgseg_pack_weights (319). */
+int mtgseg_param_count(void);
+/* Bytes of the packed-weight arena / of the activation workspace for `batch` images. */
+size_t mtgseg_packed_bytes(const mtgseg_net_desc* desc);
+size_t mtgseg_workspace_bytes(const mtgseg_net_desc* desc, int batch);
+
+/* model.load_state_dict / optimizer.step aftermath: convert the reference-layout parameters (device
+ * pointers in state_dict order: fp32 OIHW convs, BN weight/bias/running_mean/running_var, int64
+ * num_batches_tracked (ignored)) into the kernel layouts (bf16 K-major weights, folded BN scale/shift). */
+int mtgseg_pack_weights(const mtgseg_net_desc* desc, const void* const* params, int n_params, void* packed, void* stream);
+
+/* CardSegmentationModel.forward in eval mode (train/model.py:79-89; train/evaluate.py:66, train/train.py:142)
+ * plus, optionally, what evaluate.py does with the logits: argmax mask (evaluate.py:74) and the 2x2
+ * confusion counts against `targets` (utils.py:94-164, evaluate.py:88).
+ *   x        float32 [batch,3,in_h,in_w]   (train/dataset.py:84-88)
+ *   logits   [batch,num_classes,in_h,in_w] of `logits_dtype`, or NULL
+ *   mask     uint8 [batch,in_h,in_w] argmax (ties -> lowest class), or NULL
+ *   counts4  uint64[4] {n00,n01,n10,n11} (index = target*2 + prediction), ACCUMULATED; needs targets; or NULL
+ *   targets  int64 [batch,in_h,in_w] or NULL */
+int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits, int logits_dtype,
+                         uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
+                         int batch, void* stream);
+
+/* Measurement aids (bench.py): kernels launched by this library so far in this process, and one forward with
+ * CUDA events around every kernel launch (synchronises `stream`; algorithmic bytes/flops per launch as in
+ * each input read once, each output written once). */
+typedef struct mtgseg_layer_prof {
+  char name[48];   /* e.g. "b2.expand 160x120 16->64" */
+  char kernel[24]; /* kernel family, e.g. "conv_gemm_1x1" */
+  float ms;
+  double bytes;
+  double flops;
+} mtgseg_layer_prof;
+unsigned long long mtgseg_launch_count(void);
+int mtgseg_forward_infer_profiled(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits,
+                                  int logits_dtype, uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace,
+                                  size_t workspace_bytes, int batch, void* stream, mtgseg_layer_prof* out, int max_layers,
+                                  int* n_layers);
+
+/* calculate_iou / calculate_dice_coefficient / calculate_pixel_accuracy (train/utils.py:94-164) and
+ * sklearn confusion_matrix (train/evaluate.py:88) reduced to their integer core: accumulates the 2x2
+ * counts of argmax(logits[batch,2,hw]) vs targets[batch,hw] into counts4 (uint64[4]). */
+int mtgseg_metric_counts(const void* logits, int logits_dtype, const int64_t* targets, uint64_t* counts4, int64_t batch,
+                         int64_t hw, void* stream);
+
+/* CombinedLoss.forward + backward (train/utils.py:58-92, train/train.py:96-101) in one pass:
+ *   loss3[0] = dice_weight*(1 - dice) + ce_weight*CE, loss3[1] = dice loss, loss3[2] = CE
+ *   dlogits (same dtype/layout as logits, may be NULL) = d loss3[0] / d logits
+ * logits [batch,num_classes,hw]; targets int64 [batch,hw]; scratch = mtgseg_loss_scratch_bytes() bytes. */
+size_t mtgseg_loss_scratch_bytes(void);
+int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, float* scratch,
+                        float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight, float ce_weight,
+                        float smooth, void* stream);
+
+/* ---- per-operator entry points (unit tests, profiling) ------------------------------------------------ */
+/* nn.Conv2d 1x1 (+ folded BN, activation, residual, squeeze-excite input scale) on NHWC bf16:
+ * out[M,N] = act((a[M,K] . w[N,K]^T) * scale + shift) + residual ; a rows of image b scaled by a_scale[b,K] */
+int mtgseg_conv1x1(const void* a, const void* w, void* out, int M, int N, int K, const float* scale, const float* shift,
+                   int act, const void* residual, const float* a_scale, int hw, void* stream);
+/* nn.Conv2d 3x3 pad 1 (train/model.py:110) on NHWC bf16 [B,H,W,K], weights [N,9,K] */
+int mtgseg_conv3x3(const void* a, const void* w, void* out, int B, int H, int W, int N, int K, const float* scale,
+                   const float* shift, int act, void* stream);
+/* depthwise k x k conv + folded BN + act on NHWC bf16; weights bf16 [k*k,C]; optional per-chunk channel sums
+ * gap_partial float[B,chunks,C] with chunks = mtgseg_dwconv_chunks(...) */
+int mtgseg_dwconv_chunks(int H, int W, int C, int k, int stride, int dil, int need_gap);
+int mtgseg_dwconv(const void* in, const void* w, void* out, int B, int H, int W, int C, int k, int stride, int dil,
+                  const float* scale, const float* shift, int act, float* gap_partial, int chunks, void* stream);
+/* stem 3x3/s2 conv 3->16 + BN + Hardswish: x fp32 NCHW -> out bf16 NHWC; w fp32 [27,16] */
+int mtgseg_stem(const float* x, const float* w, const float* scale, const float* shift, void* out, int B, int H, int W,
+                void* stream);
+/* pooled MLP: mean = sum(sums[B,chunks,C])/HW ; h = act1(w1 mean + b1) ; out = act2(w2 h + b2) (out = h if w2 NULL) */
+int mtgseg_se_mlp(const float* sums, int chunks, int B, int C, int SQ, int HW, const void* w1, const float* b1, int act1,
+                  const void* w2, const float* b2, int act2, float* out, void* stream);
+int mtgseg_gap(const void* in, float* out, int B, int HW, int C, void* stream);
+int mtgseg_head_mix(const void* cbr, const float* s, const void* low, const float* w_high, const float* b_high,
+                    const float* w_low, const float* b_low, float* out, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC,
+                    int NC, void* stream);
+int mtgseg_upsample_out(const float* lowres, void* logits, int logits_dtype, uint8_t* mask, const int64_t* targets,
+                        uint64_t* counts4, int B, int Hl, int Wl, int H, int W, int NC, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTGSEG_B200_H */

@@ -1,0 +1,199 @@
+// extern "C" surface declared in include/mtgseg_b200.h.
+#include "net.h"
+
+using namespace mtgseg;
+
+namespace {
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+int plan_for(const mtgseg_net_desc* d, NetPlan& P) {
+  MTG_REQUIRE(d != nullptr, MTG_ERR_ARG, "net desc is NULL");
+  return build_plan(*d, P);
+}
+}  // namespace
+
+extern "C" {
+
+int mtgseg_version(void) { return MTGSEG_ABI_VERSION; }
+const char* mtgseg_last_error(void) { return get_error(); }
+
+int mtgseg_param_count(void) {
+  NetPlan P;
+  mtgseg_net_desc d{320, 240, 2, 128};
+  return build_plan(d, P) == MTG_OK ? P.n_params : -1;
+}
+
+size_t mtgseg_packed_bytes(const mtgseg_net_desc* desc) {
+  NetPlan P;
+  return plan_for(desc, P) == MTG_OK ? P.packed_bytes : 0;
+}
+
+size_t mtgseg_workspace_bytes(const mtgseg_net_desc* desc, int batch) {
+  NetPlan P;
+  if (plan_for(desc, P) != MTG_OK || batch <= 0) return 0;
+  InferIO io;
+  io.batch = batch;
+  size_t need = 0;
+  if (run_infer(P, io, nullptr, 0, &need, nullptr) != MTG_OK) return 0;
+  return need;
+}
+
+int mtgseg_pack_weights(const mtgseg_net_desc* desc, const void* const* params, int n_params, void* packed, void* stream) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(params && packed, MTG_ERR_ARG, "pack_weights: null pointer");
+  MTG_REQUIRE(n_params == P.n_params, MTG_ERR_ARG, "pack_weights: expected %d state_dict entries, got %d", P.n_params, n_params);
+  for (int i = 0; i < n_params; ++i) MTG_REQUIRE(params[i] != nullptr, MTG_ERR_ARG, "pack_weights: params[%d] is NULL", i);
+  return pack_weights(P, params, packed, S(stream));
+}
+
+int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits, int logits_dtype,
+                         uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
+                         int batch, void* stream) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(x && packed && workspace, MTG_ERR_ARG, "forward_infer: null pointer");
+  MTG_REQUIRE(batch > 0, MTG_ERR_ARG, "forward_infer: batch must be positive");
+  MTG_REQUIRE(logits || mask || counts4, MTG_ERR_ARG, "forward_infer: no output requested");
+  MTG_REQUIRE(!logits || (logits_dtype >= LOGITS_F32 && logits_dtype <= LOGITS_F16), MTG_ERR_ARG, "forward_infer: bad logits dtype %d", logits_dtype);
+  MTG_REQUIRE(!counts4 || targets, MTG_ERR_ARG, "forward_infer: counts4 needs targets");
+  MTG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MTG_ERR_ARG, "forward_infer: workspace must be 256-byte aligned");
+  InferIO io;
+  io.x = x; io.packed = packed; io.logits = logits; io.logits_dtype = logits_dtype; io.mask = mask;
+  io.counts4 = counts4; io.targets = targets; io.batch = batch;
+  size_t need = 0;
+  rc = run_infer(P, io, nullptr, 0, &need, nullptr);
+  if (rc) return rc;
+  MTG_REQUIRE(need <= workspace_bytes, MTG_ERR_WORKSPACE, "forward_infer: workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  return run_infer(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, nullptr, S(stream));
+}
+
+unsigned long long mtgseg_launch_count(void) { return launch_count(); }
+
+int mtgseg_forward_infer_profiled(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits,
+                                  int logits_dtype, uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace,
+                                  size_t workspace_bytes, int batch, void* stream, mtgseg_layer_prof* out, int max_layers,
+                                  int* n_layers) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(x && packed && workspace && out && n_layers, MTG_ERR_ARG, "forward_infer_profiled: null pointer");
+  MTG_REQUIRE(batch > 0 && (logits || mask || counts4), MTG_ERR_ARG, "forward_infer_profiled: bad arguments");
+  InferIO io;
+  io.x = x; io.packed = packed; io.logits = logits; io.logits_dtype = logits_dtype; io.mask = mask;
+  io.counts4 = counts4; io.targets = targets; io.batch = batch;
+  size_t need = 0;
+  rc = run_infer(P, io, nullptr, 0, &need, nullptr);
+  if (rc) return rc;
+  MTG_REQUIRE(need <= workspace_bytes, MTG_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  LayerProfiler prof;
+  prof.st = S(stream);
+  rc = run_infer(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, nullptr, S(stream), &prof);
+  cudaError_t e = cudaStreamSynchronize(S(stream));
+  int n = 0;
+  for (auto& r : prof.recs) {
+    if (n < max_layers && e == cudaSuccess && rc == MTG_OK) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      snprintf(out[n].name, sizeof(out[n].name), "%s", r.name);
+      snprintf(out[n].kernel, sizeof(out[n].kernel), "%s", r.kernel);
+      out[n].ms = ms; out[n].bytes = r.bytes; out[n].flops = r.flops;
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  *n_layers = n;
+  if (rc) return rc;
+  MTG_REQUIRE(e == cudaSuccess, MTG_ERR_CUDA, "forward_infer_profiled: %s", cudaGetErrorString(e));
+  return MTG_OK;
+}
+
+int mtgseg_metric_counts(const void* logits, int logits_dtype, const int64_t* targets, uint64_t* counts4, int64_t batch,
+                         int64_t hw, void* stream) {
+  return launch_metric_counts(logits, logits_dtype, targets, reinterpret_cast<unsigned long long*>(counts4), batch, hw, S(stream));
+}
+
+size_t mtgseg_loss_scratch_bytes(void) { return loss_scratch_bytes(); }
+
+int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, float* scratch,
+                        float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight, float ce_weight,
+                        float smooth, void* stream) {
+  return launch_loss(logits, logits_dtype, targets, dlogits, scratch, loss3, batch, hw, num_classes, dice_weight, ce_weight,
+                     smooth, S(stream));
+}
+
+int mtgseg_conv1x1(const void* a, const void* w, void* out, int M, int N, int K, const float* scale, const float* shift,
+                   int act, const void* residual, const float* a_scale, int hw, void* stream) {
+  ConvGemmArgs g;
+  g.a = static_cast<const bf16*>(a); g.w = static_cast<const bf16*>(w); g.out = static_cast<bf16*>(out);
+  g.M = M; g.N = N; g.K = K; g.scale = scale; g.shift = shift; g.act = act;
+  g.residual = static_cast<const bf16*>(residual); g.a_scale = a_scale; g.hw = hw;
+  return launch_conv_gemm(g, S(stream));
+}
+
+int mtgseg_conv3x3(const void* a, const void* w, void* out, int B, int H, int W, int N, int K, const float* scale,
+                   const float* shift, int act, void* stream) {
+  ConvGemmArgs g;
+  g.a = static_cast<const bf16*>(a); g.w = static_cast<const bf16*>(w); g.out = static_cast<bf16*>(out);
+  g.M = B * H * W; g.N = N; g.K = K; g.scale = scale; g.shift = shift; g.act = act;
+  g.conv3x3 = 1; g.B = B; g.H = H; g.W = W;
+  return launch_conv_gemm(g, S(stream));
+}
+
+int mtgseg_dwconv_chunks(int H, int W, int C, int k, int stride, int dil, int need_gap) {
+  const int pad = (k - 1) / 2 * dil;
+  const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  return dwconv_chunks(Ho, Wo, C, need_gap != 0);
+}
+
+int mtgseg_dwconv(const void* in, const void* w, void* out, int B, int H, int W, int C, int k, int stride, int dil,
+                  const float* scale, const float* shift, int act, float* gap_partial, int chunks, void* stream) {
+  DwConvArgs a;
+  a.in = static_cast<const bf16*>(in); a.w = static_cast<const bf16*>(w); a.out = static_cast<bf16*>(out);
+  a.scale = scale; a.shift = shift; a.act = act; a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride; a.dil = dil;
+  a.gap_partial = gap_partial; a.chunks = chunks;
+  return launch_dwconv(a, S(stream));
+}
+
+int mtgseg_stem(const float* x, const float* w, const float* scale, const float* shift, void* out, int B, int H, int W,
+                void* stream) {
+  StemArgs a;
+  a.x = x; a.w = w; a.scale = scale; a.shift = shift; a.out = static_cast<bf16*>(out); a.B = B; a.H = H; a.W = W;
+  return launch_stem(a, S(stream));
+}
+
+int mtgseg_se_mlp(const float* sums, int chunks, int B, int C, int SQ, int HW, const void* w1, const float* b1, int act1,
+                  const void* w2, const float* b2, int act2, float* out, void* stream) {
+  SeMlpArgs a;
+  a.sums = sums; a.chunks = chunks; a.B = B; a.C = C; a.SQ = SQ; a.HW = HW;
+  a.w1 = static_cast<const bf16*>(w1); a.b1 = b1; a.act1 = act1; a.w2 = static_cast<const bf16*>(w2); a.b2 = b2; a.act2 = act2;
+  a.out = out;
+  return launch_se_mlp(a, S(stream));
+}
+
+int mtgseg_gap(const void* in, float* out, int B, int HW, int C, void* stream) {
+  return launch_gap(static_cast<const bf16*>(in), out, B, HW, C, S(stream));
+}
+
+int mtgseg_head_mix(const void* cbr, const float* s, const void* low, const float* w_high, const float* b_high,
+                    const float* w_low, const float* b_low, float* out, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC,
+                    int NC, void* stream) {
+  HeadMixArgs a;
+  a.cbr = static_cast<const bf16*>(cbr); a.s = s; a.low = static_cast<const bf16*>(low);
+  a.w_high = w_high; a.b_high = b_high; a.w_low = w_low; a.b_low = b_low; a.out = out;
+  a.B = B; a.Hh = Hh; a.Wh = Wh; a.Hl = Hl; a.Wl = Wl; a.IC = IC; a.LC = LC; a.NC = NC;
+  return launch_head_mix(a, S(stream));
+}
+
+int mtgseg_upsample_out(const float* lowres, void* logits, int logits_dtype, uint8_t* mask, const int64_t* targets,
+                        uint64_t* counts4, int B, int Hl, int Wl, int H, int W, int NC, void* stream) {
+  UpsampleOutArgs a;
+  a.lowres = lowres; a.logits = logits; a.logits_dtype = logits_dtype; a.mask = mask; a.targets = targets;
+  a.counts = reinterpret_cast<unsigned long long*>(counts4);
+  a.B = B; a.Hl = Hl; a.Wl = Wl; a.H = H; a.W = W; a.NC = NC;
+  return launch_upsample_out(a, S(stream));
+}
+
+}  // extern "C"

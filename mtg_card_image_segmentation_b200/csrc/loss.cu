@@ -1,0 +1,133 @@
+// CombinedLoss = dice_w * DiceLoss + ce_w * CrossEntropy (train/utils.py:15-92) and its gradient, fused.
+//
+//   p = softmax(z) over classes;  S = sum_pixels p[target];  N = #pixels
+//   dice = 1 - (2S + eps) / (2N + eps)      (ONE global scalar: sum p == N, sum one_hot == N)
+//   ce   = -(1/N) sum log p[target]
+//   dL/dz_c = ce_w (p_c - y_c)/N - dice_w * 2/(2N+eps) * p_t (y_c - p_c)
+//
+// The gradient needs no global quantity, so loss partial sums and dlogits come out of ONE pass over the
+// logits (the reference runs ~12 elementwise/reduction kernels and materialises a one-hot tensor).
+// Partial sums are written per block and reduced in fixed order by a one-block kernel: deterministic.
+#include <cuda_fp16.h>
+
+#include "ops.h"
+
+namespace mtgseg {
+namespace {
+
+constexpr int MAX_NC = 8;
+constexpr int LOSS_BLOCKS = 148 * 4;
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16(v); }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) loss_kernel(const T* __restrict__ logits, const int64_t* __restrict__ targets,
+                                                   T* __restrict__ dlogits, float* __restrict__ partials, long long batch,
+                                                   long long hw, int nc, float g_ce, float g_dice) {
+  __shared__ float red[2][8];
+  float s_pt = 0.f, s_log = 0.f;
+  const long long total = batch * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / hw, px = i - n * hw;
+    const T* zp = logits + n * nc * hw + px;
+    float z[MAX_NC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c)
+      if (c < nc) { z[c] = ldf(zp + c * hw); m = fmaxf(m, z[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c)
+      if (c < nc) { z[c] = expf(z[c] - m); sum += z[c]; }
+    const float inv = 1.f / sum;
+    const int t = static_cast<int>(targets[i]);
+    float pt = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c)
+      if (c < nc) { z[c] *= inv; if (c == t) pt = z[c]; }
+    s_pt += pt;
+    s_log += logf(pt);
+    if (dlogits) {
+      T* gp = dlogits + n * nc * hw + px;
+#pragma unroll
+      for (int c = 0; c < MAX_NC; ++c)
+        if (c < nc) {
+          const float y = (c == t) ? 1.f : 0.f;
+          stf(gp + c * hw, g_ce * (z[c] - y) - g_dice * pt * (y - z[c]));
+        }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_pt += __shfl_xor_sync(0xffffffffu, s_pt, o);
+    s_log += __shfl_xor_sync(0xffffffffu, s_log, o);
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][warp] = s_pt; red[1][warp] = s_log; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = b;
+  }
+}
+
+__global__ void loss_finalize_kernel(const float* __restrict__ partials, int blocks, double n, float dice_w, float ce_w,
+                                     float smooth, float* __restrict__ out) {
+  __shared__ double sa[256], sb[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < blocks; i += 256) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double dice = 1.0 - (2.0 * sa[0] + smooth) / (2.0 * n + smooth);
+    const double ce = -sb[0] / n;
+    out[0] = static_cast<float>(dice_w * dice + ce_w * ce);
+    out[1] = static_cast<float>(dice);
+    out[2] = static_cast<float>(ce);
+  }
+}
+
+}  // namespace
+
+size_t loss_scratch_bytes() { return sizeof(float) * 2 * LOSS_BLOCKS; }
+
+int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, float* scratch, float* loss3,
+                long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st) {
+  MTG_REQUIRE(logits && targets && scratch && loss3, MTG_ERR_ARG, "loss: null pointer");
+  MTG_REQUIRE(nc >= 2 && nc <= MAX_NC, MTG_ERR_UNSUPPORTED, "loss: num_classes %d not in [2,%d]", nc, MAX_NC);
+  MTG_REQUIRE(batch > 0 && hw > 0, MTG_ERR_ARG, "loss: empty batch");
+  const double n = static_cast<double>(batch) * static_cast<double>(hw);
+  const float g_ce = static_cast<float>(ce_w / n);
+  const float g_dice = static_cast<float>(dice_w * 2.0 / (2.0 * n + smooth));
+  long long blocks = (batch * hw + 256 * 4 - 1) / (256 * 4);
+  if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+  const int g = static_cast<int>(blocks);
+  if (dtype == LOGITS_F32)
+    loss_kernel<float><<<g, 256, 0, st>>>(static_cast<const float*>(logits), targets, static_cast<float*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice);
+  else if (dtype == LOGITS_BF16)
+    loss_kernel<bf16><<<g, 256, 0, st>>>(static_cast<const bf16*>(logits), targets, static_cast<bf16*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice);
+  else if (dtype == LOGITS_F16)
+    loss_kernel<__half><<<g, 256, 0, st>>>(static_cast<const __half*>(logits), targets, static_cast<__half*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice);
+  else
+    MTG_REQUIRE(false, MTG_ERR_ARG, "loss: unknown logits dtype %d", dtype);
+  MTG_LAUNCH_CHECK();
+  loss_finalize_kernel<<<1, 256, 0, st>>>(scratch, g, n, dice_w, ce_w, smooth, loss3);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+}  // namespace mtgseg

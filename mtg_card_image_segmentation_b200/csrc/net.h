@@ -1,0 +1,64 @@
+#pragma once
+#include "../../include/mtgseg_b200.h"
+#include <vector>
+
+#include "ops.h"
+
+namespace mtgseg {
+
+constexpr int kNumBlocks = 15;
+
+struct BlockCfg { int cin, k, cexp, cout; bool se; int act; int stride, dil; };
+
+struct ConvBnPlan {
+  int w_idx = -1, gamma = -1, beta = -1, mean = -1, var = -1;  // indices into the state_dict-ordered parameter list
+  int cout = 0;
+  float eps = 1e-3f;
+  size_t w_off = 0, scale_off = 0, shift_off = 0;  // offsets into the packed arena
+};
+
+struct BlockPlan {
+  BlockCfg cfg;
+  bool has_expand = false;
+  ConvBnPlan expand, dw, project;
+  int sq = 0, fc1_w = -1, fc1_b = -1, fc2_w = -1, fc2_b = -1;
+  size_t fc1_w_off = 0, fc1_b_off = 0, fc2_w_off = 0, fc2_b_off = 0;
+};
+
+struct NetPlan {
+  mtgseg_net_desc desc;
+  ConvBnPlan stem, last, cbr;
+  BlockPlan blocks[kNumBlocks];
+  int scale_w = -1, low_w = -1, low_b = -1, high_w = -1, high_b = -1;
+  size_t scale_w_off = 0, low_w_off = 0, low_b_off = 0, high_w_off = 0, high_b_off = 0;
+  int n_params = 0;
+  size_t packed_bytes = 0;
+};
+
+struct InferIO {
+  const float* x = nullptr;
+  const void* packed = nullptr;
+  void* logits = nullptr;
+  int logits_dtype = LOGITS_F32;
+  uint8_t* mask = nullptr;
+  uint64_t* counts4 = nullptr;
+  const int64_t* targets = nullptr;
+  int batch = 0;
+};
+
+// optional per-launch profile of one forward (bench.py roofline): CUDA events around every kernel launch
+struct LayerProfiler {
+  struct Rec { char name[48]; char kernel[24]; double bytes, flops; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  cudaStream_t st = nullptr;
+  void begin(const char* name, const char* kernel, double bytes, double flops);
+  void end();
+};
+
+const BlockCfg* block_table();
+int build_plan(const mtgseg_net_desc& d, NetPlan& P);
+int pack_weights(const NetPlan& P, const void* const* params, void* packed, cudaStream_t st);
+int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes, size_t* ws_needed, cudaStream_t st,
+              LayerProfiler* prof = nullptr);
+
+}  // namespace mtgseg

@@ -1,0 +1,117 @@
+// Internal launcher interface between the network plan (net.cu), the C-ABI (api.cu) and the kernels.
+// All activations are NHWC bf16 ("pixels x channels" matrices); all launchers are asynchronous on `st`.
+#pragma once
+#include "common.cuh"
+
+namespace mtgseg {
+
+// ---- tcgen05 implicit-GEMM convolution (gemm_tc.cu) ---------------------------------------------
+struct ConvGemmArgs {
+  const bf16* a = nullptr;     // 1x1: [M][K]; 3x3: NHWC [B][H][W][K]
+  const bf16* w = nullptr;     // 1x1: [N][K]; 3x3: [N][9][K]   (K contiguous)
+  bf16* out = nullptr;         // [M][N]
+  int M = 0, N = 0, K = 0;
+  const float* scale = nullptr;  // [N] folded BatchNorm scale (nullptr -> 1)
+  const float* shift = nullptr;  // [N] folded BatchNorm shift (nullptr -> 0)
+  int act = ACT_NONE;
+  const bf16* residual = nullptr;  // [M][N] added after the activation-less projection
+  const float* a_scale = nullptr;  // squeeze-excite: [B][K] multiplier applied to A rows of image b
+  int hw = 0;                      // rows per image (needed with a_scale)
+  int conv3x3 = 0;                 // 3x3, stride 1, pad 1, dilation 1
+  int B = 0, H = 0, W = 0;         // geometry for conv3x3 (M == B*H*W)
+};
+int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st);
+
+// ---- bandwidth-bound kernels (dwconv.cu, stem.cu, se.cu, tail.cu, metrics.cu) -------------------
+struct DwConvArgs {
+  const bf16* in = nullptr;   // [B][H][W][C]
+  const bf16* w = nullptr;    // [k*k][C] bf16, tap-major
+  bf16* out = nullptr;        // [B][Ho][Wo][C]
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int act = ACT_NONE;
+  int B = 0, H = 0, W = 0, C = 0, k = 3, stride = 1, dil = 1;
+  float* gap_partial = nullptr;  // optional [B][chunks][C] per-chunk channel sums of the output
+  int chunks = 1;                // pixel chunks per image (grid.x); see dwconv_chunks()
+};
+int dwconv_chunks(int Ho, int Wo, int C, bool need_gap);
+int launch_dwconv(const DwConvArgs& a, cudaStream_t st);
+
+struct StemArgs {
+  const float* x = nullptr;  // [B][3][H][W] fp32 NCHW (the reference's data contract)
+  const float* w = nullptr;  // [27][16] fp32, index (ci*9 + ky*3 + kx)
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  bf16* out = nullptr;  // [B][Ho][Wo][16]
+  int B = 0, H = 0, W = 0;
+};
+int launch_stem(const StemArgs& a, cudaStream_t st);
+
+// channel sums over pixels: in [B][HW][C] bf16 -> out [B][C] fp32 (sums, not means)
+int launch_gap(const bf16* in, float* out, int B, int HW, int C, cudaStream_t st);
+
+// Two-layer (or one-layer when w2 == nullptr) per-image MLP on pooled features:
+//   mean = sum(partials)/HW ; h = act1(W1 mean + b1) ; out = act2(W2 h + b2)   (out = h if no W2)
+struct SeMlpArgs {
+  const float* sums = nullptr;  // [B][chunks][C]
+  int chunks = 1;
+  int B = 0, C = 0, SQ = 0, HW = 0;
+  const bf16* w1 = nullptr;   // [SQ][C]
+  const float* b1 = nullptr;  // [SQ] or nullptr
+  int act1 = ACT_RELU;
+  const bf16* w2 = nullptr;   // [C][SQ] or nullptr
+  const float* b2 = nullptr;
+  int act2 = ACT_HSIGMOID;
+  float* out = nullptr;  // [B][C] (or [B][SQ] when single layer)
+};
+int launch_se_mlp(const SeMlpArgs& a, cudaStream_t st);
+
+struct HeadMixArgs {
+  const bf16* cbr = nullptr;    // [B][Hh][Wh][IC]  relu(bn(conv3x3(high)))
+  const float* s = nullptr;     // [B][IC]          sigmoid branch
+  const bf16* low = nullptr;    // [B][Hl][Wl][LC]
+  const float* w_high = nullptr;  // [NC][IC]
+  const float* b_high = nullptr;  // [NC]
+  const float* w_low = nullptr;   // [NC][LC]
+  const float* b_low = nullptr;   // [NC]
+  float* out = nullptr;           // [B][Hl][Wl][NC] fp32 low-resolution logits
+  int B = 0, Hh = 0, Wh = 0, Hl = 0, Wl = 0, IC = 0, LC = 0, NC = 0;
+};
+int launch_head_mix(const HeadMixArgs& a, cudaStream_t st);
+
+enum LogitsDtype : int { LOGITS_NONE = 0, LOGITS_F32 = 1, LOGITS_BF16 = 2, LOGITS_F16 = 3 };
+struct UpsampleOutArgs {
+  const float* lowres = nullptr;  // [B][Hl][Wl][NC]
+  void* logits = nullptr;         // [B][NC][H][W] (dtype below) or nullptr
+  int logits_dtype = LOGITS_F32;
+  uint8_t* mask = nullptr;            // [B][H][W] argmax (ties -> lowest class) or nullptr
+  const int64_t* targets = nullptr;   // [B][H][W] for counts
+  unsigned long long* counts = nullptr;  // [4] n00,n01,n10,n11 (accumulated with atomics), NC == 2 only
+  int B = 0, Hl = 0, Wl = 0, H = 0, W = 0, NC = 0;
+};
+int launch_upsample_out(const UpsampleOutArgs& a, cudaStream_t st);
+
+// 2x2 confusion counts from full-resolution logits [B][2][H][W] and int64 targets.
+int launch_metric_counts(const void* logits, int logits_dtype, const int64_t* targets, unsigned long long* counts4,
+                         long long batch, long long hw, cudaStream_t st);
+
+// ---- fused CombinedLoss forward + gradient (loss.cu) ---------------------------------------------
+size_t loss_scratch_bytes();
+// loss3 = {total, dice_loss, ce_loss}; dlogits (same dtype/layout as logits, nullable) = dLoss/dlogits
+int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, float* scratch, float* loss3,
+                long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st);
+
+// ---- weight packing (pack.cu) --------------------------------------------------------------------
+int launch_cast_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);
+int launch_copy_f32(const float* in, float* out, size_t n, cudaStream_t st);
+// [O][I][kh][kw] fp32 -> [O][kh*kw][I] bf16
+int launch_pack_oihw_to_otapi(const float* in, bf16* out, int O, int I, int taps, cudaStream_t st);
+// depthwise [C][1][k][k] fp32 -> [k*k][C] bf16
+int launch_pack_dw(const float* in, bf16* out, int C, int taps, cudaStream_t st);
+// stem [16][3][3][3] fp32 -> [27][16] fp32
+int launch_pack_stem(const float* in, float* out, cudaStream_t st);
+// scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+int launch_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                   float* shift, int C, cudaStream_t st);
+
+}  // namespace mtgseg

@@ -1,0 +1,91 @@
+// Weight packing: reference state_dict tensors (fp32, OIHW) -> the layouts the kernels read.
+// Runs once per weight update; bandwidth is irrelevant (16 MB), so these are plain grid-stride kernels.
+#include "ops.h"
+
+namespace mtgseg {
+namespace {
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+__global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = in[i];
+}
+// in [O][I][T] -> out [O][T][I]
+__global__ void oihw_to_otapi_kernel(const float* __restrict__ in, bf16* __restrict__ out, int O, int I, int T) {
+  const size_t n = static_cast<size_t>(O) * I * T;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % I);
+    const size_t r = i / I;
+    const int t = static_cast<int>(r % T);
+    const size_t o = r / T;
+    out[i] = __float2bfloat16(in[(o * I + ci) * T + t]);
+  }
+}
+// in [C][T] -> out [T][C]
+__global__ void pack_dw_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int T) {
+  const int n = C * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i % C, t = i / C;
+    out[i] = __float2bfloat16(in[c * T + t]);
+  }
+}
+// in [16][27] -> out [27][16]
+__global__ void pack_stem_kernel(const float* __restrict__ in, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 27 * 16) out[i] = in[(i % 16) * 27 + i / 16];
+}
+__global__ void fold_bn_kernel(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ m,
+                               const float* __restrict__ v, float eps, float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    const float s = g[i] / sqrtf(v[i] + eps);
+    scale[i] = s;
+    shift[i] = b[i] - m[i] * s;
+  }
+}
+
+inline int blocks_for(size_t n) {
+  size_t b = (n + 255) / 256;
+  if (b > 1024) b = 1024;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+int launch_cast_bf16(const float* in, bf16* out, size_t n, cudaStream_t st) {
+  cast_bf16_kernel<<<blocks_for(n), 256, 0, st>>>(in, out, n);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_copy_f32(const float* in, float* out, size_t n, cudaStream_t st) {
+  copy_f32_kernel<<<blocks_for(n), 256, 0, st>>>(in, out, n);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_pack_oihw_to_otapi(const float* in, bf16* out, int O, int I, int taps, cudaStream_t st) {
+  oihw_to_otapi_kernel<<<blocks_for(static_cast<size_t>(O) * I * taps), 256, 0, st>>>(in, out, O, I, taps);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_pack_dw(const float* in, bf16* out, int C, int taps, cudaStream_t st) {
+  pack_dw_kernel<<<blocks_for(static_cast<size_t>(C) * taps), 256, 0, st>>>(in, out, C, taps);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_pack_stem(const float* in, float* out, cudaStream_t st) {
+  pack_stem_kernel<<<2, 256, 0, st>>>(in, out);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                   float* shift, int C, cudaStream_t st) {
+  fold_bn_kernel<<<ceil_div(C, 256), 256, 0, st>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+}  // namespace mtgseg

@@ -1,0 +1,79 @@
+// Stem: dense 3x3 stride-2 convolution 3 -> 16 channels + folded BatchNorm + Hardswish, reading the
+// reference's fp32 NCHW batch (train/dataset.py:84-88 contract) and writing NHWC bf16.
+// K = 27 is far too small for the tensor cores to matter; the layer is bound by reading the image
+// (12 B/pixel) and writing 32 B per output pixel, so it is a direct convolution: one thread per output
+// pixel, all 16 output channels in registers, weights broadcast from shared memory.
+// Replaces features[0] of tv:models/mobilenetv3.py:160-170.
+#include "ops.h"
+
+namespace mtgseg {
+namespace {
+
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                   bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo) {
+  __shared__ float4 sw[27 * 4];
+  __shared__ float ssc[16], ssh[16];
+  for (int i = threadIdx.x; i < 27 * 4; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
+  if (threadIdx.x < 16) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
+  __syncthreads();
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % Wo);
+    const long long t = idx / Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * 2 - 1 + kx;
+          if (ix < 0 || ix >= W) continue;
+          const float xv = __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix);
+          const float4* wp = &sw[(ci * 9 + ky * 3 + kx) * 4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = wp[q];
+            acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+    float o0[8], o1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o0[j] = apply_act(fmaf(acc[j], ssc[j], ssh[j]), ACT_HSWISH);
+      o1[j] = apply_act(fmaf(acc[8 + j], ssc[8 + j], ssh[8 + j]), ACT_HSWISH);
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + idx * 16);
+    op[0] = pack8(o0);
+    op[1] = pack8(o1);
+  }
+}
+
+}  // namespace
+
+int launch_stem(const StemArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.x && a.w && a.scale && a.shift && a.out, MTG_ERR_ARG, "stem: null pointer");
+  const int Ho = (a.H + 2 - 3) / 2 + 1, Wo = (a.W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(a.B) * Ho * Wo;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stem_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(a.x, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+}  // namespace mtgseg

@@ -1,0 +1,143 @@
+"""Host-side driver of the inference path: owns the packed-weight arena and the activation workspace (torch
+tensors, so PyTorch's caching allocator owns the memory) and calls the C ABI on torch's current stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+_TORCH_TO_LOGITS = {torch.float32: N.LOGITS_F32, torch.bfloat16: N.LOGITS_BF16, torch.float16: N.LOGITS_F16}
+
+
+class SegEngine:
+    def __init__(self, num_classes: int = 2, inter_channels: int = 128):
+        self.lib = N.load()
+        self.num_classes = num_classes
+        self.inter_channels = inter_channels
+        self._packed = None
+        self._packed_sig = None
+        self._ws = None
+        self._desc_cache = {}
+
+    def desc(self, h: int, w: int) -> N.NetDesc:
+        key = (h, w)
+        if key not in self._desc_cache:
+            self._desc_cache[key] = N.NetDesc(h, w, self.num_classes, self.inter_channels)
+        return self._desc_cache[key]
+
+    # -- weights -----------------------------------------------------------------------------
+    def pack(self, tensors, device) -> torch.Tensor:
+        """(Re)pack the reference-layout state tensors when any of them changed (version counters)."""
+        sig = (str(device), tuple((t.data_ptr(), t._version) for t in tensors))
+        if self._packed is not None and sig == self._packed_sig:
+            return self._packed
+        n = self.lib.mtgseg_param_count()
+        if len(tensors) != n:
+            raise RuntimeError(f"expected {n} state_dict entries, got {len(tensors)}")
+        for t in tensors:
+            if t.device != device:
+                raise RuntimeError("model parameters/buffers and the input batch must be on the same CUDA device")
+            if not t.is_contiguous():
+                raise RuntimeError("state tensors must be contiguous")
+        d = self.desc(320, 240)  # packing does not depend on the input size
+        nbytes = self.lib.mtgseg_packed_bytes(C.byref(d))
+        if self._packed is None or self._packed.numel() != nbytes or self._packed.device != device:
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        arr = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        N.check(self.lib.mtgseg_pack_weights(C.byref(d), arr, n, self._packed.data_ptr(), N.stream_ptr()), "mtgseg_pack_weights")
+        self._packed_sig = sig
+        return self._packed
+
+    def workspace(self, d: N.NetDesc, batch: int, device) -> torch.Tensor:
+        need = self.lib.mtgseg_workspace_bytes(C.byref(d), batch)
+        if need == 0:
+            raise RuntimeError(f"mtgseg_workspace_bytes failed: {self.lib.mtgseg_last_error().decode()}")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    # -- inference ---------------------------------------------------------------------------
+    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"expected a (B,3,H,W) batch, got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            packed = self.pack(tensors, dev)
+            d = self.desc(H, W)
+            ws = self.workspace(d, B, dev)
+            logits = None
+            if logits_dtype is not None:
+                logits = torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
+            mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+            counts = None
+            if targets is not None:
+                if targets.dtype != torch.int64 or tuple(targets.shape) != (B, H, W) or targets.device != dev:
+                    raise RuntimeError("targets must be an int64 (B,H,W) tensor on the input's device")
+                targets = targets.contiguous()
+                counts = torch.zeros(4, dtype=torch.int64, device=dev)
+            rc = self.lib.mtgseg_forward_infer(
+                C.byref(d), x.data_ptr(), packed.data_ptr(), N.ptr(logits),
+                _TORCH_TO_LOGITS.get(logits_dtype, N.LOGITS_NONE), N.ptr(mask), N.ptr(counts), N.ptr(targets),
+                ws.data_ptr(), ws.numel(), B, N.stream_ptr())
+            N.check(rc, "mtgseg_forward_infer")
+        if want_mask or targets is not None:
+            return {"logits": logits, "mask": mask, "counts": counts}
+        return logits
+
+
+    def profile(self, tensors, x, logits_dtype=torch.bfloat16):
+        """One forward with CUDA events around every kernel launch -> list of dicts (bench.py roofline)."""
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            packed = self.pack(tensors, dev)
+            d = self.desc(H, W)
+            ws = self.workspace(d, B, dev)
+            logits = torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
+            recs = (N.LayerProf * 128)()
+            n = C.c_int(0)
+            rc = self.lib.mtgseg_forward_infer_profiled(
+                C.byref(d), x.data_ptr(), packed.data_ptr(), logits.data_ptr(), _TORCH_TO_LOGITS[logits_dtype], None, None,
+                None, ws.data_ptr(), ws.numel(), B, N.stream_ptr(), recs, 128, C.byref(n))
+            N.check(rc, "mtgseg_forward_infer_profiled")
+        return [{"name": recs[i].name.decode(), "kernel": recs[i].kernel.decode(), "ms": recs[i].ms,
+                 "bytes": recs[i].bytes, "flops": recs[i].flops} for i in range(n.value)]
+
+
+class GraphedInference:
+    """CUDA-graph replay of one fixed-shape inference call (launch-bound regimes: ~60 kernels per forward).
+
+    ``run(x)`` copies ``x`` into the captured input buffer and replays; outputs are the captured tensors."""
+
+    def __init__(self, model, example, logits_dtype=torch.bfloat16, want_mask=False):
+        self.model = model
+        self.x = example.clone()
+        eng, tensors = model.engine(), model._state_tensors()
+        kw = dict(logits_dtype=logits_dtype, want_mask=want_mask)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture: packs weights, sizes the workspace, sets func attributes
+            eng.infer(tensors, self.x, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = eng.lib.mtgseg_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = eng.infer(tensors, self.x, **kw)
+        self.launches_per_replay = int(eng.lib.mtgseg_launch_count() - before)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def run(self, x):
+        self.x.copy_(x, non_blocking=True)
+        return self.replay()

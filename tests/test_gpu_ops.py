@@ -1,0 +1,161 @@
+"""Per-operator parity of the CUDA kernels (through the C ABI) against plain PyTorch fp32 maths on the
+same bf16-rounded inputs.  Tolerances: outputs are bf16 (8 mantissa bits) -> max error <= 1e-2 of the
+output range and rel-L2 <= 4e-3 (half an ulp RMS)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import devops as D  # noqa: E402
+
+DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False  # the references below must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+ACTS = {0: lambda x: x, 1: F.relu, 2: F.hardswish, 3: F.hardsigmoid, 4: torch.sigmoid}
+
+
+def _rand(*shape, gen, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale)
+
+
+def _check(name, got, ref, tol_max=1e-2, tol_l2=4e-3):
+    emax, el2 = D.report(name, got, ref)
+    assert not torch.isnan(got.float()).any(), name
+    assert emax <= tol_max and el2 <= tol_l2, f"{name}: max-rel {emax:.3g} l2 {el2:.3g}"
+
+
+@pytest.mark.parametrize("M,N,K,act,res,se", [
+    (128, 64, 64, 0, False, False),      # one full tile, one k-block
+    (300, 960, 160, 2, False, False),    # block-16 conv: 4 N tiles, partial M tile, K=160 (2.5 k-blocks)
+    (4800, 160, 960, 0, True, True),     # block 14/15 project: K=960 (15 k-blocks), SE scale, residual
+    (2 * 160 * 120, 64, 16, 1, False, False),  # block 2 expand: K=16 (one 16-wide k-step)
+    (2 * 80 * 60, 24, 64, 0, False, False),    # N=24 -> padded MMA N=32
+    (1200 * 3, 40, 72, 0, False, True),  # block 4 project with SE, K=72
+    (777, 200, 80, 2, False, False),     # ragged M, N=200 -> 208
+    (600, 184, 80, 2, False, False),
+    (1, 16, 16, 0, False, False),        # smallest
+    (148 * 128 * 9 + 5, 72, 24, 1, False, False),  # many tiles per persistent CTA
+])
+def test_conv1x1(M, N, K, act, res, se):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = _rand(M, K, gen=g).bfloat16().to(DEV)
+    w = _rand(N, K, gen=g, scale=K ** -0.5).bfloat16().to(DEV)
+    scale = (torch.rand(N, generator=g) + 0.5).to(DEV)
+    shift = _rand(N, gen=g, scale=0.2).to(DEV)
+    residual = _rand(M, N, gen=g).bfloat16().to(DEV) if res else None
+    hw = 300 if M % 300 == 0 else (1200 if M % 1200 == 0 else M)
+    a_scale = torch.rand(M // hw, K, generator=g).to(DEV) if se else None
+    got = D.conv1x1(a, w, scale, shift, act, residual, a_scale, hw)
+    af = a.float()
+    if se:
+        af = (af.view(M // hw, hw, K) * a_scale[:, None, :]).bfloat16().float().view(M, K)
+    ref = ACTS[act]((af @ w.float().t()) * scale + shift)
+    if res:
+        ref = ref + residual.float()
+    _check(f"conv1x1 M{M} N{N} K{K}", got, ref)
+
+
+@pytest.mark.parametrize("B,H,W,N,K", [(2, 20, 15, 128, 960), (3, 4, 3, 128, 960), (5, 20, 15, 128, 64), (1, 9, 7, 32, 72)])
+def test_conv3x3(B, H, W, N, K):
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = _rand(B, H, W, K, gen=g).bfloat16().to(DEV)
+    w = _rand(N, K, 3, 3, gen=g, scale=(9 * K) ** -0.5).bfloat16()
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9, K).contiguous().to(DEV)
+    scale = (torch.rand(N, generator=g) + 0.5).to(DEV)
+    shift = _rand(N, gen=g, scale=0.2).to(DEV)
+    got = D.conv3x3(x, wp, scale, shift, 1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().to(DEV), None, 1, 1)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None]).permute(0, 2, 3, 1)
+    _check(f"conv3x3 B{B} {H}x{W} N{N} K{K}", got, ref)
+
+
+@pytest.mark.parametrize("B,H,W,C,k,stride,dil,act,gap", [
+    (2, 160, 120, 16, 3, 1, 1, 1, False), (2, 160, 120, 64, 3, 2, 1, 1, False), (2, 80, 60, 72, 5, 2, 1, 1, True),
+    (3, 40, 30, 120, 5, 1, 1, 1, True), (2, 40, 30, 240, 3, 2, 1, 2, False), (2, 20, 15, 184, 3, 1, 1, 2, False),
+    (2, 20, 15, 672, 5, 1, 2, 2, True), (3, 20, 15, 960, 5, 1, 2, 2, True), (1, 7, 5, 200, 3, 1, 1, 2, False),
+])
+def test_dwconv(B, H, W, C, k, stride, dil, act, gap):
+    g = torch.Generator().manual_seed(C + k)
+    x = _rand(B, H, W, C, gen=g).bfloat16().to(DEV)
+    w = _rand(C, 1, k, k, gen=g, scale=1.0 / k).bfloat16()
+    wp = w.reshape(C, k * k).t().contiguous().to(DEV)
+    scale = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    shift = _rand(C, gen=g, scale=0.2).to(DEV)
+    got, gp = D.dwconv(x, wp, scale, shift, act, k, stride, dil, gap)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().to(DEV), None, stride, (k - 1) // 2 * dil, dil, C)
+    ref = ACTS[act](ref * scale[None, :, None, None] + shift[None, :, None, None]).permute(0, 2, 3, 1)
+    _check(f"dwconv C{C} k{k} s{stride} d{dil}", got, ref)
+    if gap:
+        sums = gp.sum(1)
+        ref_s = got.float().sum((1, 2))
+        _check(f"dwconv gap C{C}", sums, ref_s, tol_max=1e-4, tol_l2=1e-5)
+
+
+def test_stem():
+    g = torch.Generator().manual_seed(1)
+    x = _rand(3, 3, 64, 48, gen=g).to(DEV)
+    w = _rand(16, 3, 3, 3, gen=g, scale=0.3)
+    wp = w.reshape(16, 27).t().contiguous().to(DEV)
+    scale = (torch.rand(16, generator=g) + 0.5).to(DEV)
+    shift = _rand(16, gen=g, scale=0.2).to(DEV)
+    got = D.stem(x, wp, scale, shift)
+    ref = F.conv2d(x, w.to(DEV), None, 2, 1)
+    ref = F.hardswish(ref * scale[None, :, None, None] + shift[None, :, None, None]).permute(0, 2, 3, 1)
+    _check("stem", got, ref)
+
+
+@pytest.mark.parametrize("B,C,SQ,two", [(5, 960, 240, True), (3, 72, 24, True), (4, 960, 128, False), (2, 120, 32, True)])
+def test_se_mlp(B, C, SQ, two):
+    g = torch.Generator().manual_seed(C)
+    hw = 300
+    sums = (_rand(B, 3, C, gen=g) * 50).to(DEV)
+    w1 = _rand(SQ, C, gen=g, scale=C ** -0.5).bfloat16().to(DEV)
+    b1 = _rand(SQ, gen=g, scale=0.1).to(DEV) if two else None
+    w2 = _rand(C, SQ, gen=g, scale=SQ ** -0.5).bfloat16().to(DEV) if two else None
+    b2 = _rand(C, gen=g, scale=0.1).to(DEV) if two else None
+    got = D.se_mlp(sums, hw, w1, b1, 1 if two else 4, w2, b2, 3)
+    mean = sums.sum(1) / hw
+    h = mean @ w1.float().t()
+    if two:
+        ref = F.hardsigmoid(F.relu(h + b1) @ w2.float().t() + b2)
+    else:
+        ref = torch.sigmoid(h)
+    _check(f"se_mlp C{C}", got, ref, tol_max=1e-4, tol_l2=1e-5)
+
+
+def test_gap():
+    g = torch.Generator().manual_seed(3)
+    x = _rand(3, 300, 960, gen=g).bfloat16().to(DEV)
+    _check("gap", D.gap(x), x.float().sum(1), tol_max=1e-5, tol_l2=1e-6)
+
+
+@pytest.mark.parametrize("NC,H,W", [(2, 320, 240), (3, 64, 48), (2, 70, 50)])
+def test_head_tail(NC, H, W):
+    g = torch.Generator().manual_seed(NC)
+    B, IC, LC = 3, 128, 40
+    Hl, Wl = (H + 7) // 8, (W + 7) // 8
+    Hh, Wh = (Hl + 1) // 2, (Wl + 1) // 2
+    cbr = F.relu(_rand(B, Hh, Wh, IC, gen=g)).bfloat16().to(DEV)
+    s = torch.rand(B, IC, generator=g).to(DEV)
+    low = _rand(B, Hl, Wl, LC, gen=g).bfloat16().to(DEV)
+    wh, bh = _rand(NC, IC, gen=g, scale=0.1).to(DEV), _rand(NC, gen=g, scale=0.1).to(DEV)
+    wl, bl = _rand(NC, LC, gen=g, scale=0.1).to(DEV), _rand(NC, gen=g, scale=0.1).to(DEV)
+    lowres = D.head_mix(cbr, s, low, wh, bh, wl, bl)
+    x = (cbr.float() * s[:, None, None, :]).permute(0, 3, 1, 2)
+    x = F.interpolate(x, size=(Hl, Wl), mode="bilinear", align_corners=False)
+    ref_low = F.conv2d(low.float().permute(0, 3, 1, 2), wl[:, :, None, None], bl) + F.conv2d(x, wh[:, :, None, None], bh)
+    _check("head_mix", lowres.permute(0, 3, 1, 2), ref_low, tol_max=1e-4, tol_l2=1e-5)
+    t = torch.randint(0, 2, (B, H, W), generator=g).to(DEV)
+    logits, mask, counts = D.upsample_out(lowres, H, W, torch.float32, True, True, t if NC == 2 else None)
+    ref = F.interpolate(lowres.permute(0, 3, 1, 2).contiguous(), size=(H, W), mode="bilinear", align_corners=False)
+    _check("upsample_out f32", logits, ref, tol_max=1e-5, tol_l2=1e-6)
+    assert torch.equal(mask.long(), torch.argmax(logits, 1))
+    if NC == 2:
+        p = mask.long()
+        exp = torch.bincount((t * 2 + p).reshape(-1), minlength=4)
+        assert torch.equal(counts, exp)
+    lb, _, _ = D.upsample_out(lowres, H, W, torch.bfloat16)
+    _check("upsample_out bf16", lb, ref, tol_max=1e-2, tol_l2=4e-3)
+    lh, _, _ = D.upsample_out(lowres, H, W, torch.float16)
+    _check("upsample_out f16", lh, ref, tol_max=2e-3, tol_l2=1e-3)
