@@ -1,0 +1,121 @@
+"""Host-side drop-in surface (no GPU): module tree / state_dict layout, checkpoint round trip, loud failure
+without CUDA, the exporter-only composite forward, repo layout rules."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, has_reference
+from oracle import lraspp_oracle as O
+
+import mtg_card_image_segmentation_b200 as M
+
+
+def test_state_dict_layout_matches_reference_contract():
+    m = M.create_model(num_classes=2, pretrained=False)
+    sd = m.state_dict()
+    spec = O.state_dict_spec()
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for (k, shape, _), v in zip(spec, sd.values()):
+        assert tuple(v.shape) == tuple(shape), k
+    assert M.count_parameters(m) == (4_201_348, 4_201_348)
+    assert abs(M.get_model_size(m) - 16.12) < 0.01
+    assert len(list(m.parameters())) == 178  # AdamW param order contract
+    # module tree the reference's tools walk (train/prune.py:52-58 iterates nn.Conv2d children)
+    assert isinstance(m.model.backbone["0"][0], torch.nn.Conv2d)
+    assert isinstance(m.model.classifier.cbr[0], torch.nn.Conv2d) and m.model.classifier.cbr[0].kernel_size == (3, 3)
+    assert m.model.backbone["4"].block[2].fc1.bias is not None
+    assert m.model.classifier.cbr[1].eps == 1e-5 and m.model.backbone["3"].block[0][1].eps == 1e-3
+    assert m.model.backbone["3"].block[0][1].momentum == 0.01 and m.model.classifier.cbr[1].momentum == 0.1
+
+
+def test_constructor_contract():
+    with pytest.raises(RuntimeError, match="pretrained"):
+        M.create_model(2, pretrained=True)
+    m = M.CardSegmentationModel(num_classes=3, pretrained=False)
+    assert m.model.classifier.low_classifier.out_channels == 3
+
+
+def test_cpu_forward_fails_loudly():
+    m = M.create_model(2, False).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        m(torch.zeros(1, 3, 64, 48))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.CombinedLoss()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.calculate_iou(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
+
+
+def test_checkpoint_round_trip(tmp_path):
+    m = M.create_model(2, False)
+    m.load_state_dict(O.make_weights(4), strict=True)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=100, eta_min=1e-5)
+    M.save_checkpoint(m, opt, sched, 7, 0.875, str(tmp_path), "ck.pth")
+    ck = torch.load(tmp_path / "ck.pth", map_location="cpu", weights_only=True)  # tensors/primitives only
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_metric"}
+    assert list(ck["model_state_dict"].keys()) == [k for k, _, _ in O.state_dict_spec()]
+    m2 = M.create_model(2, False)
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-3)
+    epoch, best = M.load_checkpoint(m2, opt2, None, str(tmp_path / "ck.pth"))
+    assert (epoch, best) == (7, 0.875)
+    for a, b in zip(m.state_dict().values(), m2.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference only exists in the build container")
+def test_checkpoint_interchange_with_reference(tmp_path):
+    """A checkpoint written by our save_checkpoint loads into the reference model and vice versa."""
+    import functools
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_model2", "/root/reference/train/model.py")
+    ref_model = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_model)
+    ref_model.lraspp_mobilenet_v3_large = functools.partial(ref_model.lraspp_mobilenet_v3_large, weights_backbone=None)
+    ref = ref_model.create_model(2, pretrained=False)
+    ours = M.create_model(2, False)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in ours.named_parameters()]
+    o1 = torch.optim.AdamW(ref.parameters(), lr=1e-3)
+    o2 = torch.optim.AdamW(ours.parameters(), lr=1e-3)
+    o2.load_state_dict(o1.state_dict())
+
+
+def test_export_composite_forward_matches_oracle():
+    """torch.jit.trace (what train/export.py:177-182 does) goes through the ATen composite and reproduces the
+    oracle; the trace contains the 66 convolutions of the reference's exported graph."""
+    m = M.create_model(2, False)
+    x, _ = O.synthetic_cards(1, seed=2, height=64, width=48)
+    sd = O.calibrate_running_stats(O.make_weights(8), x)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    traced = torch.jit.trace(m, x, check_trace=False)
+    with torch.no_grad():
+        torch.testing.assert_close(traced(x), O.forward(sd, x), rtol=1e-4, atol=1e-5)
+    assert str(traced.inlined_graph).count("aten::_convolution") == 66
+
+
+def test_repo_layout_rules():
+    """Only tests/, bench.py and __graft_entry__.py may touch oracle/; the product never does."""
+    pkg = os.path.join(ROOT, "mtg_card_image_segmentation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in src, f
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_arch_table_in_sync_with_cuda_plan():
+    from mtg_card_image_segmentation_b200 import arch
+    src = open(os.path.join(ROOT, "mtg_card_image_segmentation_b200", "csrc", "net.cu")).read()
+    rows = re.findall(r"\{(\d+), (\d+), (\d+), (\d+), (true|false), ACT_(RELU|HSWISH),\s*(\d+), (\d+)\}", src)
+    assert len(rows) == 15
+    for r, b in zip(rows, arch.BLOCKS):
+        assert (int(r[0]), int(r[1]), int(r[2]), int(r[3]), r[4] == "true", {"RELU": "RE", "HSWISH": "HS"}[r[5]],
+                int(r[6]), int(r[7])) == tuple(b)
+    assert [tuple(b) for b in arch.BLOCKS] == [tuple(b) for b in O.BLOCKS]
