@@ -79,6 +79,27 @@ int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void
                          uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
                          int batch, void* stream);
 
+/* One training step = mtgseg_forward_train -> (loss, mtgseg_loss_fwd_bwd) -> mtgseg_backward -> mtgseg_adamw_step ->
+ * mtgseg_pack_weights, all on one stream with one workspace of mtgseg_train_workspace_bytes().
+ *
+ * mtgseg_forward_train: model.train(); model(images) (train/train.py:82,96-97): batch-statistics BatchNorm; the
+ *   running_mean / running_var / num_batches_tracked entries of `params` are UPDATED in place (momentum 0.01 backbone,
+ *   0.1 head; unbiased variance); everything backward needs stays in `workspace`.
+ * mtgseg_backward: loss.backward() (train/train.py:101,105) for the forward that last used `workspace`.
+ *   dlogits [batch,num_classes,in_h,in_w]; grads[i] = fp32 gradient buffer of state_dict entry i in the reference's
+ *   layout (OIHW), NULL for buffers; the caller ZEROES them first (several are accumulated with atomics).
+ * mtgseg_adamw_step: torch.optim.AdamW.step (train/train.py:167-171) over all tensors in one launch. chunk_table is a
+ *   DEVICE array of n_chunks records {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int32 n;}
+ *   (one CTA each; split big tensors into several records). inv_scale / found_inf: GradScaler hooks, may be NULL. */
+size_t mtgseg_train_workspace_bytes(const mtgseg_net_desc* desc, int batch);
+int mtgseg_forward_train(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, int n_params,
+                         void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, int batch, void* stream);
+int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, float* const* grads,
+                    int n_params, const void* dlogits, int dlogits_dtype, void* workspace, size_t workspace_bytes, int batch,
+                    void* stream);
+int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, const float* inv_scale, const float* found_inf, void* stream);
+
 /* Measurement aids (bench.py): kernels launched by this library so far in this process, and one forward with
  * CUDA events around every kernel launch (synchronises `stream`; algorithmic bytes/flops per launch as in
  * each input read once, each output written once). */
@@ -126,9 +147,10 @@ int mtgseg_dwconv(const void* in, const void* w, void* out, int B, int H, int W,
 /* stem 3x3/s2 conv 3->16 + BN + Hardswish: x fp32 NCHW -> out bf16 NHWC; w fp32 [27,16] */
 int mtgseg_stem(const float* x, const float* w, const float* scale, const float* shift, void* out, int B, int H, int W,
                 void* stream);
-/* pooled MLP: mean = sum(sums[B,chunks,C])/HW ; h = act1(w1 mean + b1) ; out = act2(w2 h + b2) (out = h if w2 NULL) */
+/* pooled MLP: mean = sum(sums[B,chunks,C])/HW ; h = act1(w1 mean + b1) ; out = act2(w2 h + b2) (out = h if w2 NULL);
+ * hidden = float[B,SQ] scratch for the two-layer form */
 int mtgseg_se_mlp(const float* sums, int chunks, int B, int C, int SQ, int HW, const void* w1, const float* b1, int act1,
-                  const void* w2, const float* b2, int act2, float* out, void* stream);
+                  const void* w2, const float* b2, int act2, float* out, float* hidden, void* stream);
 int mtgseg_gap(const void* in, float* out, int B, int HW, int C, void* stream);
 int mtgseg_head_mix(const void* cbr, const float* s, const void* low, const float* w_high, const float* b_high,
                     const float* w_low, const float* b_low, float* out, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC,

@@ -37,6 +37,10 @@ SIGNATURES = {
     "mtgseg_workspace_bytes": (_sz, [_ND, _i]),
     "mtgseg_pack_weights": (_i, [_ND, C.POINTER(_vp), _i, _vp, _vp]),
     "mtgseg_forward_infer": (_i, [_ND, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "mtgseg_train_workspace_bytes": (_sz, [_ND, _i]),
+    "mtgseg_forward_train": (_i, [_ND, _vp, _vp, C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
+    "mtgseg_backward": (_i, [_ND, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
+    "mtgseg_adamw_step": (_i, [_vp, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _vp, _vp]),
     "mtgseg_launch_count": (C.c_ulonglong, []),
     "mtgseg_forward_infer_profiled": (_i, [_ND, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp, C.POINTER(LayerProf), _i,
                                            C.POINTER(_i)]),
@@ -48,7 +52,7 @@ SIGNATURES = {
     "mtgseg_dwconv_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "mtgseg_dwconv": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "mtgseg_stem": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "mtgseg_se_mlp": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "mtgseg_se_mlp": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mtgseg_gap": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mtgseg_head_mix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mtgseg_upsample_out": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -69,6 +69,49 @@ int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void
   return run_infer(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, nullptr, S(stream));
 }
 
+size_t mtgseg_train_workspace_bytes(const mtgseg_net_desc* desc, int batch) {
+  NetPlan P;
+  if (plan_for(desc, P) != MTG_OK || batch <= 0) return 0;
+  return train_workspace_bytes(P, batch);
+}
+
+int mtgseg_forward_train(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, int n_params,
+                         void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, int batch, void* stream) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(x && packed && params && logits && workspace, MTG_ERR_ARG, "forward_train: null pointer");
+  MTG_REQUIRE(n_params == P.n_params, MTG_ERR_ARG, "forward_train: expected %d state_dict entries, got %d", P.n_params, n_params);
+  MTG_REQUIRE(batch > 0, MTG_ERR_ARG, "forward_train: batch must be positive");
+  MTG_REQUIRE(static_cast<long long>(batch) * (desc->in_h / 16) * (desc->in_w / 16) > 1, MTG_ERR_UNSUPPORTED,
+              "forward_train: BatchNorm needs more than one value per channel");
+  MTG_REQUIRE(logits_dtype >= LOGITS_F32 && logits_dtype <= LOGITS_F16, MTG_ERR_ARG, "forward_train: bad logits dtype");
+  MTG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MTG_ERR_ARG, "forward_train: workspace must be 256-byte aligned");
+  TrainIO io;
+  io.x = x; io.packed = packed; io.params = params; io.logits = logits; io.logits_dtype = logits_dtype; io.batch = batch;
+  return run_train_forward(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, S(stream));
+}
+
+int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, float* const* grads,
+                    int n_params, const void* dlogits, int dlogits_dtype, void* workspace, size_t workspace_bytes, int batch,
+                    void* stream) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(x && packed && params && grads && dlogits && workspace, MTG_ERR_ARG, "backward: null pointer");
+  MTG_REQUIRE(n_params == P.n_params, MTG_ERR_ARG, "backward: expected %d state_dict entries, got %d", P.n_params, n_params);
+  MTG_REQUIRE(dlogits_dtype >= LOGITS_F32 && dlogits_dtype <= LOGITS_F16, MTG_ERR_ARG, "backward: bad dlogits dtype");
+  TrainIO io;
+  io.x = x; io.packed = packed; io.params = params; io.grads = grads; io.dlogits = dlogits; io.dlogits_dtype = dlogits_dtype;
+  io.batch = batch;
+  return run_train_backward(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, S(stream));
+}
+
+int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, const float* inv_scale, const float* found_inf, void* stream) {
+  return launch_adamw(chunk_table, n_chunks, lr, beta1, beta2, eps, weight_decay, step, inv_scale, found_inf, S(stream));
+}
+
 unsigned long long mtgseg_launch_count(void) { return launch_count(); }
 
 int mtgseg_forward_infer_profiled(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits,
@@ -145,7 +188,7 @@ int mtgseg_conv3x3(const void* a, const void* w, void* out, int B, int H, int W,
 int mtgseg_dwconv_chunks(int H, int W, int C, int k, int stride, int dil, int need_gap) {
   const int pad = (k - 1) / 2 * dil;
   const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
-  return dwconv_chunks(Ho, Wo, C, need_gap != 0);
+  return dwconv_chunks(Ho, Wo, C, stride, need_gap != 0);
 }
 
 int mtgseg_dwconv(const void* in, const void* w, void* out, int B, int H, int W, int C, int k, int stride, int dil,
@@ -165,8 +208,9 @@ int mtgseg_stem(const float* x, const float* w, const float* scale, const float*
 }
 
 int mtgseg_se_mlp(const float* sums, int chunks, int B, int C, int SQ, int HW, const void* w1, const float* b1, int act1,
-                  const void* w2, const float* b2, int act2, float* out, void* stream) {
+                  const void* w2, const float* b2, int act2, float* out, float* hidden, void* stream) {
   SeMlpArgs a;
+  a.hidden = hidden;
   a.sums = sums; a.chunks = chunks; a.B = B; a.C = C; a.SQ = SQ; a.HW = HW;
   a.w1 = static_cast<const bf16*>(w1); a.b1 = b1; a.act1 = act1; a.w2 = static_cast<const bf16*>(w2); a.b2 = b2; a.act2 = act2;
   a.out = out;

@@ -1,0 +1,324 @@
+// Training-mode BatchNorm (+ activation, residual, squeeze-excite hooks) on NHWC bf16, forward and backward.
+//
+// forward :  z (raw conv output, bf16) --stats--> mean / biased var --finalize--> scale = gamma*rstd,
+//            shift = beta - mean*scale, running-stat EMA (unbiased var), num_batches_tracked++
+//            y = act(z*scale + shift) (+ residual)            [+ per-chunk channel sums of y for the SE pool]
+// backward:  dyh = dy' * act'(z*scale+shift) with dy' = dy (* s[n,c] + dmean[n,c]/HW for SE inputs)
+//            reduce: sum dyh, sum dyh*xhat -> dbeta, dgamma ;  dz = scale*(dyh - mean(dyh) - xhat*mean(dyh*xhat))
+// Semantics: nn.BatchNorm2d in train mode (tv:models/mobilenetv3.py:155 eps 1e-3 / momentum 1e-2 for the backbone,
+// train/model.py:111 defaults for the head), nn.Hardswish / nn.ReLU derivatives as in SURVEY.md App. B.
+// All reductions are two-stage (per-CTA partials in fixed order, then a tiny finalize kernel): deterministic.
+#include "ops.h"
+
+namespace mtgseg {
+
+int group_vectors(int CV);  // dwconv.cu
+
+namespace {
+
+__device__ __forceinline__ float act_grad(float zh, int act) {
+  switch (act) {
+    case ACT_RELU: return zh > 0.f ? 1.f : 0.f;
+    case ACT_HSWISH: return zh <= -3.f ? 0.f : (zh >= 3.f ? 1.f : zh * (1.f / 3.f) + 0.5f);
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+struct Geo {  // thread -> (channel vector, row lane) mapping shared by all kernels here
+  int C, CV, CVc, PL, HW, rows_per_chunk, chunks;
+};
+
+struct Lane {
+  bool active; int c0, pl, vl;
+};
+__device__ __forceinline__ Lane lane_of(const Geo& g) {
+  Lane l;
+  l.vl = threadIdx.x % g.CVc;
+  l.pl = threadIdx.x / g.CVc;
+  const int v = blockIdx.y * g.CVc + l.vl;
+  l.active = l.pl < g.PL && v < g.CV;
+  l.c0 = (l.active ? v : 0) * 8;
+  return l;
+}
+
+// fixed-order reduction of K per-thread 8-vectors over the row lanes; result for channel c (of this CTA) in out[k]
+template <int K>
+__device__ __forceinline__ void block_reduce_store(const Geo& g, const Lane& l, float (&vals)[K][8], float* red,
+                                                   float* const (&dst)[K], size_t dst_index_base) {
+  const int cw = g.CVc * 8;
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();
+    if (l.pl < g.PL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(l.pl * g.CVc + l.vl) * 8 + j] = l.active ? vals[k][j] : 0.f;
+    }
+    __syncthreads();
+    for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < g.C) {
+        float s = 0.f;
+        for (int r = 0; r < g.PL; ++r) s += red[r * cw + cl];
+        dst[k][dst_index_base + c] = s;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+// grid (chunks, groups, B): partial[((n*chunks + chunk)*2 + {0,1})*C + c] = sum z, sum z^2 over the chunk's rows of image n
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ z, float* __restrict__ partial, const Geo g) {
+  __shared__ float red[256 * 8];
+  const Lane l = lane_of(g);
+  const int n = blockIdx.z, chunk = blockIdx.x;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (l.active) {
+    const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const bf16* base = z + static_cast<size_t>(n) * g.HW * g.C + l.c0;
+    for (int r = r0 + l.pl; r < r1; r += g.PL) {
+      float f[8];
+      unpack8(ldg16(base + static_cast<size_t>(r) * g.C), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
+    }
+  }
+  const size_t slot = (static_cast<size_t>(n) * g.chunks + chunk) * 2;
+  float* const dst[2] = {partial + slot * g.C, partial + (slot + 1) * g.C};
+  block_reduce_store<2>(g, l, acc, red, dst, 0);
+}
+
+struct BnFinP {
+  const float* partial; int slots;  // slots = B*chunks ; layout [slot][2][C]
+  double count;                     // B*HW
+  const float* gamma; const float* beta; float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float* scale; float* shift; float* save_mean; float* save_rstd;
+  int C;
+};
+__global__ void bn_finalize_kernel(const BnFinP p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+  if (c >= p.C) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < p.slots; ++k) {
+    s += p.partial[(static_cast<size_t>(k) * 2) * p.C + c];
+    ss += p.partial[(static_cast<size_t>(k) * 2 + 1) * p.C + c];
+  }
+  const double mean = s / p.count;
+  double var = ss / p.count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+  const float sc = p.gamma[c] * rstd;
+  p.scale[c] = sc;
+  p.shift[c] = p.beta[c] - static_cast<float>(mean) * sc;
+  p.save_mean[c] = static_cast<float>(mean);
+  p.save_rstd[c] = rstd;
+  if (p.running_mean) {
+    const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
+    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * static_cast<float>(mean);
+    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * static_cast<float>(unbiased);
+  }
+}
+
+struct BnApplyP {
+  const bf16* z; const float* scale; const float* shift; int act; const bf16* residual; bf16* y; float* gap;
+};
+// grid (chunks, groups, B)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const Geo g) {
+  __shared__ float red[256 * 8];
+  const Lane l = lane_of(g);
+  const int n = blockIdx.z, chunk = blockIdx.x;
+  float gsum[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gsum[0][j] = 0.f;
+  if (l.active) {
+    float sc[8], sh[8];
+    load8f(p.scale + l.c0, sc);
+    load8f(p.shift + l.c0, sh);
+    const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
+    for (int r = r0 + l.pl; r < r1; r += g.PL) {
+      const size_t off = img + static_cast<size_t>(r) * g.C;
+      float f[8];
+      unpack8(ldg16(p.z + off), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], sc[j], sh[j]), p.act);
+      if (p.residual) {
+        float rf[8];
+        unpack8(ldg16(p.residual + off), rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += rf[j];
+      }
+      const uint4 q = pack8(f);
+      *reinterpret_cast<uint4*>(p.y + off) = q;
+      if (p.gap) {
+        float rf[8];
+        unpack8(q, rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gsum[0][j] += rf[j];
+      }
+    }
+  }
+  if (p.gap) {
+    float* const dst[1] = {p.gap};
+    block_reduce_store<1>(g, l, gsum, red, dst, (static_cast<size_t>(n) * g.chunks + chunk) * g.C);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+struct BnBwdP {
+  const bf16* z; const bf16* dy;            // raw conv output, incoming gradient w.r.t. y (or w.r.t. s*y for SE inputs)
+  const float* scale; const float* shift;   // forward scale/shift (gamma*rstd, beta - mean*scale)
+  const float* mean; const float* rstd;     // saved batch statistics
+  int act;
+  const float* se_s; const float* se_dmean; float inv_hw;  // optional: dy' = dy*se_s[n,c] + se_dmean[n,c]*inv_hw
+  const float* c1; const float* c2;         // (apply) mean(dyh), mean(dyh*xhat)
+  float* partial;                           // (reduce) [slot][2][C]
+  bf16* dz;                                 // (apply)
+};
+
+__device__ __forceinline__ void bwd_load(const BnBwdP& p, const Geo& g, const Lane& l, int n, size_t off, const float (&sc)[8],
+                                         const float (&sh)[8], const float (&mu)[8], const float (&rs)[8], const float (&ses)[8],
+                                         const float (&sed)[8], float (&dyh)[8], float (&xh)[8]) {
+  float zf[8], df[8];
+  unpack8(ldg16(p.z + off), zf);
+  unpack8(ldg16(p.dy + off), df);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float d = p.se_s ? fmaf(df[j], ses[j], sed[j]) : df[j];
+    dyh[j] = d * act_grad(fmaf(zf[j], sc[j], sh[j]), p.act);
+    xh[j] = (zf[j] - mu[j]) * rs[j];
+  }
+}
+
+template <bool kApply>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g) {
+  __shared__ float red[256 * 8];
+  const Lane l = lane_of(g);
+  const int n = blockIdx.z, chunk = blockIdx.x;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (l.active) {
+    float sc[8], sh[8], mu[8], rs[8], ses[8], sed[8], c1[8], c2[8];
+    load8f(p.scale + l.c0, sc); load8f(p.shift + l.c0, sh); load8f(p.mean + l.c0, mu); load8f(p.rstd + l.c0, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ses[j] = 1.f; sed[j] = 0.f; c1[j] = c2[j] = 0.f; }
+    if (p.se_s) {
+      load8f(p.se_s + static_cast<size_t>(n) * g.C + l.c0, ses);
+      load8f(p.se_dmean + static_cast<size_t>(n) * g.C + l.c0, sed);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sed[j] *= p.inv_hw;
+    }
+    if (kApply) { load8f(p.c1 + l.c0, c1); load8f(p.c2 + l.c0, c2); }
+    const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
+    for (int r = r0 + l.pl; r < r1; r += g.PL) {
+      const size_t off = img + static_cast<size_t>(r) * g.C;
+      float dyh[8], xh[8];
+      bwd_load(p, g, l, n, off, sc, sh, mu, rs, ses, sed, dyh, xh);
+      if (kApply) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dyh[j] - c1[j] - xh[j] * c2[j]);
+        *reinterpret_cast<uint4*>(p.dz + off) = pack8(o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += dyh[j]; acc[1][j] = fmaf(dyh[j], xh[j], acc[1][j]); }
+      }
+    }
+  }
+  if (!kApply) {
+    const size_t slot = (static_cast<size_t>(n) * g.chunks + chunk) * 2;
+    float* const dst[2] = {p.partial + slot * g.C, p.partial + (slot + 1) * g.C};
+    block_reduce_store<2>(g, l, acc, red, dst, 0);
+  }
+}
+
+// dbeta = sum dyh ; dgamma = sum dyh*xhat ; c1 = dbeta/count ; c2 = dgamma/count
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int slots, double count, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int k = 0; k < slots; ++k) {
+    s += partial[(static_cast<size_t>(k) * 2) * C + c];
+    sx += partial[(static_cast<size_t>(k) * 2 + 1) * C + c];
+  }
+  dbeta[c] = static_cast<float>(s);
+  dgamma[c] = static_cast<float>(sx);
+  c1[c] = static_cast<float>(s / count);
+  c2[c] = static_cast<float>(sx / count);
+}
+
+Geo make_geo(int C, int HW, int want_chunks) {
+  Geo g{};
+  g.C = C; g.CV = C / 8; g.CVc = group_vectors(g.CV); g.PL = 256 / g.CVc; g.HW = HW;
+  g.chunks = want_chunks;
+  g.rows_per_chunk = ceil_div(HW, g.chunks);
+  return g;
+}
+
+}  // namespace
+
+// chunks per image for the BN kernels: ~16 rows per thread, at most 32 per image (bounds the partial buffers)
+int bn_chunks(int HW, int C) {
+  const int PL = 256 / group_vectors(C / 8);
+  int ch = ceil_div(HW, PL * 16);
+  if (ch > 32) ch = 32;
+  if (ch < 1) ch = 1;
+  return ch;
+}
+size_t bn_partial_floats(int B, int HW, int C) { return static_cast<size_t>(B) * bn_chunks(HW, C) * 2 * C; }
+
+int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.z && a.y && a.gamma && a.beta && a.scale && a.shift && a.save_mean && a.save_rstd && a.partial, MTG_ERR_ARG,
+              "bn_train_fwd: null pointer");
+  MTG_REQUIRE(a.C % 8 == 0, MTG_ERR_UNSUPPORTED, "bn_train_fwd: C %% 8 != 0");
+  const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C));
+  dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
+  bn_stats_kernel<<<grid, 256, 0, st>>>(a.z, a.partial, g);
+  MTG_LAUNCH_CHECK();
+  BnFinP f{a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
+           a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd, a.C};
+  bn_finalize_kernel<<<ceil_div(a.C, 128), 128, 0, st>>>(f);
+  MTG_LAUNCH_CHECK();
+  Geo ga = g;
+  if (a.gap) {  // the SE pool wants few partials per image
+    ga = make_geo(a.C, a.HW, a.gap_chunks);
+    grid = dim3(ga.chunks, ceil_div(ga.CV, ga.CVc), a.B);
+  }
+  BnApplyP ap{a.z, a.scale, a.shift, a.act, a.residual, a.y, a.gap};
+  bn_apply_kernel<<<grid, 256, 0, st>>>(ap, ga);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.z && a.dy && a.dz && a.scale && a.shift && a.save_mean && a.save_rstd && a.partial && a.dgamma && a.dbeta &&
+                  a.c1 && a.c2, MTG_ERR_ARG, "bn_train_bwd: null pointer");
+  const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C));
+  dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
+  BnBwdP p{a.z, a.dy, a.scale, a.shift, a.save_mean, a.save_rstd, a.act, a.se_s, a.se_dmean, 1.f / static_cast<float>(a.HW),
+           a.c1, a.c2, a.partial, a.dz};
+  bn_bwd_kernel<false><<<grid, 256, 0, st>>>(p, g);
+  MTG_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<ceil_div(a.C, 128), 128, 0, st>>>(a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.dgamma,
+                                                             a.dbeta, a.c1, a.c2, a.C);
+  MTG_LAUNCH_CHECK();
+  bn_bwd_kernel<true><<<grid, 256, 0, st>>>(p, g);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+}  // namespace mtgseg

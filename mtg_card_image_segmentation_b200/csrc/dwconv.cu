@@ -2,13 +2,15 @@
 // BatchNorm scale/shift and activation fused, plus optional per-chunk channel sums of the output (the
 // squeeze-excite global-average-pool, so the SE block never re-reads the tensor).
 //
-// Bandwidth-bound: every thread owns one 8-channel vector (one 128-bit load/store per tap / output) and
-// walks output pixels; consecutive threads own consecutive vectors, so each warp touches contiguous
-// 512-byte spans.  The block size is a multiple of the vectors-per-pixel count so a thread's channels
-// (hence its weights and BN constants) never change.
+// Bandwidth-bound: every thread owns one 8-channel vector (128-bit loads/stores) and a horizontal strip of
+// output pixels; consecutive threads own consecutive vectors, so each warp touches contiguous 512-byte
+// spans.  The block size is a multiple of the vectors-per-pixel count so a thread's channels (hence its
+// weights and BN constants) never change.
 //
 // Replaces the depthwise Conv2dNormActivation of tv:models/mobilenetv3.py:83-95 (+ the AdaptiveAvgPool2d
 // of tv:ops/misc.py:252-253).
+#include <stdlib.h>
+
 #include "ops.h"
 
 namespace mtgseg {
@@ -18,18 +20,24 @@ struct DwP {
   const bf16* in; const bf16* w; bf16* out;
   const float* scale; const float* shift;
   float* gap;
-  int act, H, W, C, Ho, Wo, stride, dil, pad, CV, PL, pix_per_chunk, chunks;
+  int act, H, W, C, Ho, Wo, pad, CV, CVc, PL, strips, items, items_per_chunk, chunks;
 };
 
-template <int KS>
-__global__ void __launch_bounds__(256) dwconv_kernel(const DwP p) {
+// One thread = one 8-channel vector x one horizontal strip of TW output pixels.  Per kernel row the strip's
+// NI = (TW-1)*STRIDE + (KS-1)*DIL + 1 input vectors are streamed once and scattered into the TW accumulators
+// (compile-time tap/offset matching), so the L1 traffic per output drops from KS*KS loads to ~KS*NI/TW.
+template <int KS, int STRIDE, int DIL, int TW, int MINB>
+__global__ void __launch_bounds__(256, MINB) dwconv_kernel(const DwP p) {
   __shared__ float red[256 * 8];
+  constexpr int NI = (TW - 1) * STRIDE + (KS - 1) * DIL + 1;
   const int tid = threadIdx.x;
-  const int nthreads = p.CV * p.PL;
-  const int n = blockIdx.y, chunk = blockIdx.x;
-  const bool active = tid < nthreads;
-  const int v = active ? tid % p.CV : 0;
-  const int pl = active ? tid / p.CV : 0;
+  const int n = blockIdx.z, chunk = blockIdx.x;
+  // a CTA owns CVc channel vectors (<= 128 channels) of a band of rows: its input footprint fits L1
+  const int vl = tid % p.CVc, pl_raw = tid / p.CVc;
+  const int v_raw = blockIdx.y * p.CVc + vl;
+  const bool active = pl_raw < p.PL && v_raw < p.CV;
+  const int v = active ? v_raw : 0;
+  const int pl = active ? pl_raw : 0;
   const int c0 = v * 8;
   float acc_gap[8];
 #pragma unroll
@@ -43,67 +51,111 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwP p) {
       sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
       sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
     }
-    const int npix = p.Ho * p.Wo;
-    const int p_begin = chunk * p.pix_per_chunk;
-    const int p_end = min(npix, p_begin + p.pix_per_chunk);
+    const int it_begin = chunk * p.items_per_chunk;
+    const int it_end = min(p.items, it_begin + p.items_per_chunk);
     const bf16* in_n = p.in + static_cast<size_t>(n) * p.H * p.W * p.C + c0;
-    bf16* out_n = p.out + static_cast<size_t>(n) * npix * p.C + c0;
-    for (int pix = p_begin + pl; pix < p_end; pix += p.PL) {
-      const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
-      const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-      float acc[8];
+    bf16* out_n = p.out + static_cast<size_t>(n) * p.Ho * p.Wo * p.C + c0;
+    for (int item = it_begin + pl; item < it_end; item += p.PL) {
+      const int oy = item / p.strips, sx = item - oy * p.strips;
+      const int ox0 = sx * TW;
+      const int ix0 = ox0 * STRIDE - p.pad;
+      float acc[TW][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int t = 0; t < TW; ++t)
 #pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll 1  // keep the body (one kernel row) small enough for the instruction cache
       for (int ky = 0; ky < KS; ++ky) {
-        const int iy = iy0 + ky * p.dil;
+        const int iy = oy * STRIDE - p.pad + ky * DIL;
         if (iy < 0 || iy >= p.H) continue;
+        float wv[KS][8];
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
-          const int ix = ix0 + kx * p.dil;
+        for (int kx = 0; kx < KS; ++kx) unpack8(ldg16(p.w + (ky * KS + kx) * p.C + c0), wv[kx]);
+        const bf16* row = in_n + static_cast<size_t>(iy) * p.W * p.C;
+#pragma unroll
+        for (int xi = 0; xi < NI; ++xi) {
+          const int ix = ix0 + xi;
           if (ix < 0 || ix >= p.W) continue;
-          float xf[8], wf[8];
-          unpack8(ldg16(in_n + (static_cast<size_t>(iy) * p.W + ix) * p.C), xf);
-          unpack8(ldg16(p.w + (ky * KS + kx) * p.C + c0), wf);
+          float xf[8];
+          unpack8(ldg16(row + static_cast<size_t>(ix) * p.C), xf);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xf[j], wf[j], acc[j]);
+          for (int kx = 0; kx < KS; ++kx) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int t = xi - kx * DIL;  // compile-time after unrolling
+            if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[t / STRIDE][j] = fmaf(xf[j], wv[kx][j], acc[t / STRIDE][j]);
+            }
+          }
         }
       }
-      float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = apply_act(fmaf(acc[j], sc[j], sh[j]), p.act);
-      const uint4 packed = pack8(o);
-      *reinterpret_cast<uint4*>(out_n + static_cast<size_t>(pix) * p.C) = packed;
-      if (p.gap) {  // pool what the next layer will actually read (the bf16-rounded values)
-        float rf[8];
-        unpack8(packed, rf);
+      for (int t = 0; t < TW; ++t) {
+        if (ox0 + t < p.Wo) {
+          float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc_gap[j] += rf[j];
+          for (int j = 0; j < 8; ++j) o[j] = apply_act(fmaf(acc[t][j], sc[j], sh[j]), p.act);
+          const uint4 packed = pack8(o);
+          *reinterpret_cast<uint4*>(out_n + (static_cast<size_t>(oy) * p.Wo + ox0 + t) * p.C) = packed;
+          if (p.gap) {  // pool what the next layer will actually read (the bf16-rounded values)
+            float rf[8];
+            unpack8(packed, rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc_gap[j] += rf[j];
+          }
+        }
       }
     }
   }
   if (p.gap) {
-    if (active) {
+    const int cw = p.CVc * 8;  // channels of this CTA
+    if (pl_raw < p.PL) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[(pl * p.CV + v) * 8 + j] = acc_gap[j];
+      for (int j = 0; j < 8; ++j) red[(pl_raw * p.CVc + vl) * 8 + j] = active ? acc_gap[j] : 0.f;
     }
     __syncthreads();
-    for (int c = tid; c < p.C; c += blockDim.x) {
-      float s = 0.f;
-      for (int l = 0; l < p.PL; ++l) s += red[l * p.C + c];  // fixed order -> deterministic
-      p.gap[(static_cast<size_t>(n) * p.chunks + chunk) * p.C + c] = s;
+    for (int cl = tid; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < p.C) {
+        float s = 0.f;
+        for (int l = 0; l < p.PL; ++l) s += red[l * cw + cl];  // fixed order -> deterministic
+        p.gap[(static_cast<size_t>(n) * p.chunks + chunk) * p.C + c] = s;
+      }
     }
   }
 }
 
+// MTGSEG_DW_VARIANT=1 selects narrower strips capped at 128 registers (tuning aid; default = wide strips)
+int dw_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTGSEG_DW_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+inline int strip_width(int stride) { return dw_variant() == 1 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
+
 }  // namespace
 
-int dwconv_chunks(int Ho, int Wo, int C, bool need_gap) {
+// vectors per CTA: <= 16 (128 channels), chosen in [8,16] to waste the fewest lanes
+int group_vectors(int CV) {
+  if (CV <= 16) return CV;
+  int best = 16, best_waste = 1 << 30;
+  for (int c = 16; c >= 8; --c) {
+    const int waste = ceil_div(CV, c) * c - CV;
+    if (waste < best_waste) { best_waste = waste; best = c; }
+  }
+  return best;
+}
+
+int dwconv_chunks(int Ho, int Wo, int C, int stride, bool need_gap) {
   const int CV = C / 8;
-  const int PL = 256 / CV > 0 ? 256 / CV : 1;
-  const int npix = Ho * Wo;
-  const int per_thread = need_gap ? 16 : 8;  // output pixels per thread per CTA
-  int chunks = ceil_div(npix, PL * per_thread);
+  const int PL = 256 / group_vectors(CV);
+  const int items = Ho * ceil_div(Wo, strip_width(stride));
+  const int per_thread = need_gap ? 4 : 2;  // strips per thread per CTA
+  int chunks = ceil_div(items, PL * per_thread);
   if (need_gap && chunks > 16) chunks = 16;
   if (chunks < 1) chunks = 1;
   return chunks;
@@ -112,21 +164,42 @@ int dwconv_chunks(int Ho, int Wo, int C, bool need_gap) {
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.in && a.w && a.out && a.scale && a.shift, MTG_ERR_ARG, "dwconv: null pointer");
   MTG_REQUIRE(a.C % 8 == 0 && a.C >= 8 && a.C <= 2048, MTG_ERR_UNSUPPORTED, "dwconv: C=%d must be a multiple of 8 in [8,2048]", a.C);
-  MTG_REQUIRE(a.k == 3 || a.k == 5, MTG_ERR_UNSUPPORTED, "dwconv: kernel size %d unsupported", a.k);
   DwP p{};
   p.in = a.in; p.w = a.w; p.out = a.out; p.scale = a.scale; p.shift = a.shift; p.gap = a.gap_partial; p.act = a.act;
-  p.H = a.H; p.W = a.W; p.C = a.C; p.stride = a.stride; p.dil = a.dil;
+  p.H = a.H; p.W = a.W; p.C = a.C;
   p.pad = (a.k - 1) / 2 * a.dil;
   p.Ho = (a.H + 2 * p.pad - a.dil * (a.k - 1) - 1) / a.stride + 1;
   p.Wo = (a.W + 2 * p.pad - a.dil * (a.k - 1) - 1) / a.stride + 1;
   p.CV = a.C / 8;
-  MTG_REQUIRE(p.CV <= 256, MTG_ERR_UNSUPPORTED, "dwconv: C too large");
-  p.PL = 256 / p.CV;
+  p.CVc = group_vectors(p.CV);
+  p.PL = 256 / p.CVc;
+  p.strips = ceil_div(p.Wo, strip_width(a.stride));
+  p.items = p.Ho * p.strips;
   p.chunks = a.chunks > 0 ? a.chunks : 1;
-  p.pix_per_chunk = ceil_div(p.Ho * p.Wo, p.chunks);
-  dim3 grid(p.chunks, a.B);
-  if (a.k == 3) dwconv_kernel<3><<<grid, 256, 0, st>>>(p);
-  else dwconv_kernel<5><<<grid, 256, 0, st>>>(p);
+  p.items_per_chunk = ceil_div(p.items, p.chunks);
+  dim3 grid(p.chunks, ceil_div(p.CV, p.CVc), a.B);
+  const int key = a.k * 100 + a.stride * 10 + a.dil;
+  if (dw_variant() == 1) {
+    switch (key) {
+      case 311: dwconv_kernel<3, 1, 1, 4, 2><<<grid, 256, 0, st>>>(p); break;
+      case 321: dwconv_kernel<3, 2, 1, 2, 2><<<grid, 256, 0, st>>>(p); break;
+      case 511: dwconv_kernel<5, 1, 1, 4, 2><<<grid, 256, 0, st>>>(p); break;
+      case 521: dwconv_kernel<5, 2, 1, 2, 2><<<grid, 256, 0, st>>>(p); break;
+      case 512: dwconv_kernel<5, 1, 2, 4, 2><<<grid, 256, 0, st>>>(p); break;
+      default:
+        MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: (k=%d, stride=%d, dilation=%d) is not one of the MobileNetV3 shapes", a.k, a.stride, a.dil);
+    }
+  } else {
+    switch (key) {
+      case 311: dwconv_kernel<3, 1, 1, 8, 1><<<grid, 256, 0, st>>>(p); break;
+      case 321: dwconv_kernel<3, 2, 1, 4, 1><<<grid, 256, 0, st>>>(p); break;
+      case 511: dwconv_kernel<5, 1, 1, 8, 1><<<grid, 256, 0, st>>>(p); break;
+      case 521: dwconv_kernel<5, 2, 1, 4, 1><<<grid, 256, 0, st>>>(p); break;
+      case 512: dwconv_kernel<5, 1, 2, 8, 1><<<grid, 256, 0, st>>>(p); break;
+      default:
+        MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: (k=%d, stride=%d, dilation=%d) is not one of the MobileNetV3 shapes", a.k, a.stride, a.dil);
+    }
+  }
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

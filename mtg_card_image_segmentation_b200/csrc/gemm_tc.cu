@@ -12,6 +12,10 @@
 // * warp roles: w0 = TMA producer, w1 = MMA issuer (+ TMEM owner), w2..5 = epilogue (one TMEM lane
 //   quarter each), w6..9 (only with kAScale) = squeeze-excite prologue that rescales the A tile in
 //   shared memory per (image, channel) before the MMA reads it.
+// * epilogue: TMEM -> registers -> folded BN / activation / residual -> bf16 -> 128B-swizzled staging slab
+//   in shared memory -> ONE TMA store per 64-channel slab (double buffered); the residual tile arrives by
+//   TMA as well, so the epilogue warps issue no per-thread global memory instruction at all and the
+//   tensor map clips ragged rows / channels.
 //
 // Replaces, for this path, what the reference delegates to cuDNN/oneDNN: nn.Conv2d 1x1 in
 // tv:models/mobilenetv3.py:71-80,101-105,179-187 and the head's 3x3 (train/model.py:110), with the
@@ -31,6 +35,10 @@ constexpr int BM = 128;           // UMMA M
 constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 6;
+constexpr int BAR_BYTES = 256;               // mbarriers + TMEM slot
+constexpr int SLAB_BYTES = BM * 128;         // one [128 rows][64 bf16] swizzled slab
+constexpr int OUT_BUFS = 2;                  // double-buffered output staging
+constexpr int SS_BYTES = 2 * 256 * 4;        // scale / shift of the current N tile
 
 struct GemmKParams {
   int M, N, K;
@@ -44,26 +52,33 @@ struct GemmKParams {
   bf16* out;
   const float* a_scale;
   int hw;
+  int res_slabs;  // 0 or ceil(BN/64)
   // 3x3 geometry
   int B, H, W, HB, NB, h_tiles;
 };
 
 template <bool kConv3x3, bool kAScale>
-__global__ void __launch_bounds__(kAScale ? 320 : 192, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+__global__ void __launch_bounds__(kAScale ? 320 : 192, 2)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
   const int b_stage_bytes = p.BN * BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * b_stage_bytes);
+  uint8_t* sOut = sB + S * b_stage_bytes;              // OUT_BUFS slabs (1024-aligned: BN % 8 == 0)
+  uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // res_slabs slabs
+  float* sScale = reinterpret_cast<float*>(sRes + p.res_slabs * SLAB_BYTES);
+  float* sShift = sScale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + SS_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* xform = bars + 2 * MAX_STAGES;
   uint64_t* tfull = bars + 3 * MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* resbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,11 +93,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&tfull[b], 1);
       ptx::mbar_init(&tempty[b], 128);
     }
+    ptx::mbar_init(resbar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
     ptx::tma_prefetch_desc(&tmB);
+    ptx::tma_prefetch_desc(&tmO);
+    if (p.res_slabs) ptx::tma_prefetch_desc(&tmR);
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, p.tmem_cols);
@@ -151,59 +169,91 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp < 6) {
     // =============================== epilogue ===============================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    uint32_t tc = 0;
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;             // accumulator row of this thread
+    const int et = threadIdx.x - 64;         // 0..127 among the epilogue threads
+    const bool leader = et == 0;
+    const int slabs = (p.BN + 63) >> 6;
+    uint32_t tc = 0, store_no = 0;
+    int cur_ntile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
-      long long m;
-      bool valid;
+      int oc1 = m_tile * BM, oc2 = 0, oc3 = 0;  // output coordinates after the channel coordinate
       if (kConv3x3) {
-        const int n0 = (m_tile / p.h_tiles) * p.NB, y0 = (m_tile % p.h_tiles) * p.HB;
-        const int wx = r % p.W, t = r / p.W, hb = t % p.HB, nb = t / p.HB;
-        valid = (nb < p.NB) && (y0 + hb < p.H) && (n0 + nb < p.B);
-        m = (static_cast<long long>(n0 + nb) * p.H + (y0 + hb)) * p.W + wx;
-      } else {
-        m = static_cast<long long>(m_tile) * BM + r;
-        valid = m < p.M;
+        oc1 = 0;
+        oc2 = (m_tile % p.h_tiles) * p.HB;
+        oc3 = (m_tile / p.h_tiles) * p.NB;
+      }
+      if (p.res_slabs && leader) {  // residual tile by TMA (all threads finished reading the previous one: barrier below)
+        ptx::mbar_arrive_expect_tx(resbar, slabs * SLAB_BYTES);
+        for (int sl = 0; sl < slabs; ++sl)
+          ptx::tma_load_2d(sRes + sl * SLAB_BYTES, &tmR, resbar, n_tile * p.BN + sl * 64, m_tile * BM);
+      }
+      if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
+        cur_ntile = n_tile;
+        for (int c = et; c < p.BN; c += 128) {
+          const int n = n_tile * p.BN + c;
+          sScale[c] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.f;
+          sShift[c] = (p.shift && n < p.N) ? __ldg(p.shift + n) : 0.f;
+        }
       }
       ptx::mbar_wait(&tfull[buf], aph);
       ptx::tc_fence_after();
+      if (p.res_slabs) ptx::mbar_wait(resbar, tc & 1);
       const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
-      bf16* orow = p.out + m * p.N;
-      const bf16* rrow = p.residual ? p.residual + m * p.N : nullptr;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        const int nbase = n_tile * p.BN + c0;
+      for (int sl = 0; sl < slabs; ++sl, ++store_no) {
+        uint8_t* sbuf = sOut + (store_no & 1) * SLAB_BYTES;
+        // the TMA store that used this buffer two slabs ago must have finished reading it
+        if (leader) ptx::bulk_wait_read<OUT_BUFS - 1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int cols = min(64, p.BN - sl * 64);  // multiple of 16
+        uint8_t* srow = sbuf + r * 128;
+        const uint8_t* rrow = sRes + sl * SLAB_BYTES + r * 128;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int n = nbase + h * 8;
-          if (valid && n < p.N) {  // N % 8 == 0, so groups of 8 never straddle N
-            float f[8];
-            const float4 sc0 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n)) : make_float4(1, 1, 1, 1);
-            const float4 sc1 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n + 4)) : make_float4(1, 1, 1, 1);
-            const float4 sh0 = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + n)) : make_float4(0, 0, 0, 0);
-            const float4 sh1 = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + n + 4)) : make_float4(0, 0, 0, 0);
-            const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-            const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+        for (int half = 0; half < 2; ++half) {  // 32 accumulator columns per TMEM round trip
+          if (half * 32 < cols) {
+            uint32_t v[2][16];
+            ptx::tmem_ld16(taddr + sl * 64 + half * 32, v[0]);
+            if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * 64 + half * 32 + 16, v[1]);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(__uint_as_float(v[h * 8 + j]), sc[j], sh[j]), p.act);
-            if (rrow) {
-              float rf[8];
-              unpack8(ldg16(rrow + n), rf);
+            for (int cc = 0; cc < 2; ++cc) {
+              if (half * 32 + cc * 16 < cols) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += rf[j];
+                for (int h = 0; h < 2; ++h) {
+                  const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the 128-byte slab row
+                  const int c = sl * 64 + chunk * 8;             // column inside the N tile
+                  const int phys = (chunk ^ (r & 7)) * 16;       // 128B swizzle: chunk index XOR (row % 8)
+                  float f[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    f[e] = apply_act(fmaf(__uint_as_float(v[cc][h * 8 + e]), sScale[c + e], sShift[c + e]), p.act);
+                  if (p.res_slabs) {
+                    float rf[8];
+                    unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                  }
+                  *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
+                }
+              }
             }
-            *reinterpret_cast<uint4*>(orow + n) = pack8(f);
           }
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          const int c0 = n_tile * p.BN + sl * 64;
+          if (kConv3x3) ptx::tma_store_4d(&tmO, sbuf, c0, oc1, oc2, oc3);
+          else ptx::tma_store_2d(&tmO, sbuf, c0, oc1);
+          ptx::bulk_commit();
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[buf]);
     }
+    if (leader) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
   } else if (kAScale) {
     // =============================== squeeze-excite prologue on the A tile ===============================
     const int t = threadIdx.x - 192;
@@ -302,14 +352,29 @@ int num_sms() {
 }
 
 template <bool C3, bool AS>
-int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, int grid, size_t smem,
-                   cudaStream_t st) {
+int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+                   const GemmKParams& kp, size_t need, cudaStream_t st) {
   static bool configured = false;  // per template instantiation
   if (!configured) {
     MTG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<C3, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv_gemm_kernel<C3, AS><<<grid, AS ? 320 : 192, smem, st>>>(tmA, tmB, kp);
+  const int threads = AS ? 320 : 192;
+  // co-resident CTAs per SM: what registers + shared memory allow, capped so that all TMEM allocations fit
+  int per_sm = 1;
+  MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_gemm_kernel<C3, AS>, threads, need));
+  if (per_sm > 512 / kp.tmem_cols) per_sm = 512 / kp.tmem_cols;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  // pad the request so that never more than per_sm CTAs share an SM (a persistent CTA that had to wait for TMEM
+  // or for a slot would serialise behind a whole tile list)
+  size_t smem = need;
+  const size_t floor_for_cap = (227 * 1024) / (per_sm + 1) + 1;
+  if (smem < floor_for_cap) smem = floor_for_cap;
+  const long long total_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles;
+  int grid = num_sms() * per_sm;
+  if (grid > total_tiles) grid = static_cast<int>(total_tiles);
+  conv_gemm_kernel<C3, AS><<<grid, threads, smem, st>>>(tmA, tmB, tmO, tmR, kp);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -326,8 +391,20 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
 
   GemmKParams kp{};
   kp.M = g.M; kp.N = g.N; kp.K = g.K;
-  kp.n_tiles = ceil_div(g.N, 256);
-  kp.BN = static_cast<int>(align_up(ceil_div(g.N, kp.n_tiles), 16));
+  if (g.N <= 256) {
+    kp.n_tiles = 1;
+    kp.BN = static_cast<int>(align_up(g.N, 16));
+  } else {
+    // several N tiles: BN must be a multiple of the 64-channel store slab (a slab may never spill into the next
+    // N tile); take the BN with the fewest padded columns, the largest on ties (fewest re-reads of A)
+    int best = 256, best_cols = 1 << 30;
+    for (int bn = 256; bn >= 64; bn -= 64) {
+      const int cols = ceil_div(g.N, bn) * bn;
+      if (cols < best_cols) { best_cols = cols; best = bn; }
+    }
+    kp.BN = best;
+    kp.n_tiles = ceil_div(g.N, best);
+  }
   kp.kb_per_tap = ceil_div(g.K, BK);
   kp.num_kb = kp.kb_per_tap * (g.conv3x3 ? 9 : 1);
   kp.ksteps_last = ceil_div(g.K - (kp.kb_per_tap - 1) * BK, 16);
@@ -337,7 +414,9 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   while (tmem < 2 * kp.BN) tmem <<= 1;
   kp.tmem_cols = tmem;
 
-  CUtensorMap tmA, tmB;
+  kp.res_slabs = g.residual ? ceil_div(kp.BN, 64) : 0;
+  MTG_REQUIRE(!(g.conv3x3 && g.residual), MTG_ERR_UNSUPPORTED, "conv_gemm: residual with conv3x3 is not supported");
+  CUtensorMap tmA, tmB, tmO, tmR;
   if (g.conv3x3) {
     MTG_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && static_cast<long long>(g.B) * g.H * g.W == g.M, MTG_ERR_ARG,
                 "conv_gemm 3x3: geometry mismatch");
@@ -365,6 +444,12 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     const uint32_t wb[2] = {BK, (uint32_t)kp.BN};
     rc = make_map(&tmB, g.w, 2, wd, ws, wb);
     if (rc) return rc;
+    const uint64_t od[4] = {(uint64_t)g.N, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t os[3] = {(uint64_t)g.N * 2, (uint64_t)g.W * g.N * 2, (uint64_t)g.H * g.W * g.N * 2};
+    const uint32_t ob[4] = {64, (uint32_t)g.W, (uint32_t)kp.HB, (uint32_t)kp.NB};
+    rc = make_map(&tmO, g.out, 4, od, os, ob);
+    if (rc) return rc;
+    tmR = tmO;
   } else {
     kp.m_tiles = ceil_div(g.M, BM);
     kp.a_bytes = A_STAGE_BYTES;
@@ -378,30 +463,32 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     const uint32_t wb[2] = {BK, (uint32_t)kp.BN};
     rc = make_map(&tmB, g.w, 2, wd, ws, wb);
     if (rc) return rc;
+    const uint64_t od[2] = {(uint64_t)g.N, (uint64_t)g.M};
+    const uint64_t os[1] = {(uint64_t)g.N * 2};
+    const uint32_t ob[2] = {64, BM};
+    rc = make_map(&tmO, g.out, 2, od, os, ob);
+    if (rc) return rc;
+    tmR = tmO;
+    if (g.residual) {
+      rc = make_map(&tmR, g.residual, 2, od, os, ob);
+      if (rc) return rc;
+    }
   }
 
   const int stage_bytes = A_STAGE_BYTES + kp.BN * BK * 2;
-  int stages = 4;
-  if (kp.num_kb >= 8) stages = 6;
-  while (stages > 2 && stages * stage_bytes > 200 * 1024) --stages;
+  const size_t fixed = 1024 /*align*/ + OUT_BUFS * SLAB_BYTES + static_cast<size_t>(kp.res_slabs) * SLAB_BYTES + SS_BYTES + BAR_BYTES;
+  int stages = kp.num_kb >= 8 ? 6 : (kp.num_kb >= 2 ? 4 : 2);  // one k-block per tile: 2 stages already prefetch the next tile
+  while (stages > 2 && stages * static_cast<size_t>(stage_bytes) + fixed > 227 * 1024) --stages;
+  // prefer two co-resident CTAs (8 epilogue warps per SM) over a deeper ring when that is what it costs
+  if (stages > 3 && 2 * (3 * static_cast<size_t>(stage_bytes) + fixed) <= 227 * 1024 &&
+      2 * (stages * static_cast<size_t>(stage_bytes) + fixed) > 227 * 1024)
+    stages = 3;
   kp.stages = stages;
-  const size_t need = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t need = static_cast<size_t>(stages) * stage_bytes + fixed;
   MTG_REQUIRE(need <= 227 * 1024, MTG_ERR_UNSUPPORTED, "conv_gemm: tile needs %zu B shared memory", need);
-  int per_sm = static_cast<int>((227 * 1024) / need);
-  if (per_sm > 512 / kp.tmem_cols) per_sm = 512 / kp.tmem_cols;
-  if (per_sm > 4) per_sm = 4;
-  if (per_sm < 1) per_sm = 1;
-  // pad the request so that never more than per_sm CTAs share an SM (their TMEM allocations always fit)
-  size_t smem = need;
-  const size_t floor_for_cap = (227 * 1024) / (per_sm + 1) + 1;
-  if (smem < floor_for_cap) smem = floor_for_cap;
-  const long long total_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles;
-  int grid = num_sms() * per_sm;
-  if (grid > total_tiles) grid = static_cast<int>(total_tiles);
-
-  if (g.conv3x3) return launch_variant<true, false>(tmA, tmB, kp, grid, smem, st);
-  if (g.a_scale) return launch_variant<false, true>(tmA, tmB, kp, grid, smem, st);
-  return launch_variant<false, false>(tmA, tmB, kp, grid, smem, st);
+  if (g.conv3x3) return launch_variant<true, false>(tmA, tmB, tmO, tmR, kp, need, st);
+  if (g.a_scale) return launch_variant<false, true>(tmA, tmB, tmO, tmR, kp, need, st);
+  return launch_variant<false, false>(tmA, tmB, tmO, tmR, kp, need, st);
 }
 
 }  // namespace mtgseg

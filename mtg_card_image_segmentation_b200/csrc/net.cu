@@ -36,7 +36,10 @@ struct Bump {
   }
 };
 
-void plan_convbn(ConvBnPlan& c, int& pi, Bump& arena, size_t w_elems, size_t w_elem_bytes, int cout, float eps) {
+void plan_convbn(ConvBnPlan& c, int& pi, Bump& arena, size_t w_elems, size_t w_elem_bytes, int cout, float eps,
+                 bool dgrad_copy = false, int cin = 0) {
+  c.cin = cin;
+  if (dgrad_copy) c.wt_off = arena.take(w_elems * w_elem_bytes);
   c.w_idx = pi++;
   c.gamma = pi; c.beta = pi + 1; c.mean = pi + 2; c.var = pi + 3;
   pi += 5;  // + num_batches_tracked
@@ -78,7 +81,7 @@ int build_plan(const mtgseg_net_desc& d, NetPlan& P) {
     BlockPlan& b = P.blocks[i];
     b.cfg = c;
     b.has_expand = c.cexp != c.cin;
-    if (b.has_expand) plan_convbn(b.expand, pi, arena, static_cast<size_t>(c.cexp) * c.cin, 2, c.cexp, eps_bb);
+    if (b.has_expand) plan_convbn(b.expand, pi, arena, static_cast<size_t>(c.cexp) * c.cin, 2, c.cexp, eps_bb, true, c.cin);
     plan_convbn(b.dw, pi, arena, static_cast<size_t>(c.cexp) * c.k * c.k, 2, c.cexp, eps_bb);
     if (c.se) {
       b.sq = make_divisible8(c.cexp / 4);
@@ -88,11 +91,11 @@ int build_plan(const mtgseg_net_desc& d, NetPlan& P) {
       b.fc2_w_off = arena.take(static_cast<size_t>(b.sq) * c.cexp * 2);
       b.fc2_b_off = arena.take(c.cexp * sizeof(float));
     }
-    plan_convbn(b.project, pi, arena, static_cast<size_t>(c.cout) * c.cexp, 2, c.cout, eps_bb);
+    plan_convbn(b.project, pi, arena, static_cast<size_t>(c.cout) * c.cexp, 2, c.cout, eps_bb, true, c.cexp);
   }
-  plan_convbn(P.last, pi, arena, 960 * 160, 2, 960, eps_bb);
+  plan_convbn(P.last, pi, arena, 960 * 160, 2, 960, eps_bb, true, 160);
   const int ic = d.inter_channels, nc = d.num_classes;
-  plan_convbn(P.cbr, pi, arena, static_cast<size_t>(ic) * 960 * 9, 2, ic, eps_head);
+  plan_convbn(P.cbr, pi, arena, static_cast<size_t>(ic) * 960 * 9, 2, ic, eps_head, true, 960);
   P.scale_w = pi++;
   P.scale_w_off = arena.take(static_cast<size_t>(ic) * 960 * 2);
   P.low_w = pi++; P.low_b = pi++; P.high_w = pi++; P.high_b = pi++;
@@ -121,6 +124,7 @@ int pack_weights(const NetPlan& P, const void* const* params, void* packed, cuda
     const BlockCfg& c = b.cfg;
     if (b.has_expand) {
       RC(launch_cast_bf16(f(b.expand.w_idx), reinterpret_cast<bf16*>(base + b.expand.w_off), static_cast<size_t>(c.cexp) * c.cin, st));
+      RC(launch_pack_transpose_bf16(f(b.expand.w_idx), reinterpret_cast<bf16*>(base + b.expand.wt_off), c.cexp, c.cin, st));
       RC(fold(b.expand));
     }
     RC(launch_pack_dw(f(b.dw.w_idx), reinterpret_cast<bf16*>(base + b.dw.w_off), c.cexp, c.k * c.k, st));
@@ -133,12 +137,15 @@ int pack_weights(const NetPlan& P, const void* const* params, void* packed, cuda
       RC(launch_copy_f32(f(b.fc2_b), reinterpret_cast<float*>(base + b.fc2_b_off), c.cexp, st));
     }
     RC(launch_cast_bf16(f(b.project.w_idx), reinterpret_cast<bf16*>(base + b.project.w_off), static_cast<size_t>(c.cout) * c.cexp, st));
+    RC(launch_pack_transpose_bf16(f(b.project.w_idx), reinterpret_cast<bf16*>(base + b.project.wt_off), c.cout, c.cexp, st));
     RC(fold(b.project));
   }
   RC(launch_cast_bf16(f(P.last.w_idx), reinterpret_cast<bf16*>(base + P.last.w_off), 960 * 160, st));
+  RC(launch_pack_transpose_bf16(f(P.last.w_idx), reinterpret_cast<bf16*>(base + P.last.wt_off), 960, 160, st));
   RC(fold(P.last));
   const int ic = P.desc.inter_channels, nc = P.desc.num_classes;
   RC(launch_pack_oihw_to_otapi(f(P.cbr.w_idx), reinterpret_cast<bf16*>(base + P.cbr.w_off), ic, 960, 9, st));
+  RC(launch_pack_dgrad3x3(f(P.cbr.w_idx), reinterpret_cast<bf16*>(base + P.cbr.wt_off), ic, 960, st));
   RC(fold(P.cbr));
   RC(launch_cast_bf16(f(P.scale_w), reinterpret_cast<bf16*>(base + P.scale_w_off), static_cast<size_t>(ic) * 960, st));
   RC(launch_copy_f32(f(P.low_w), reinterpret_cast<float*>(base + P.low_w_off), nc * 40, st));
@@ -204,9 +211,10 @@ int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes,
     const int stride = c.dil > 1 ? 1 : c.stride;
     const int Ho = conv_out(H, c.k, stride, c.dil), Wo = conv_out(W, c.k, stride, c.dil);
     bf16* dwo = act_buf(static_cast<size_t>(B) * Ho * Wo * c.cexp);
-    const int chunks = dwconv_chunks(Ho, Wo, c.cexp, c.se);
+    const int chunks = dwconv_chunks(Ho, Wo, c.cexp, stride, c.se);
     float* gap = c.se ? f32_buf(static_cast<size_t>(B) * chunks * c.cexp) : nullptr;
     float* sescale = c.se ? f32_buf(static_cast<size_t>(B) * c.cexp) : nullptr;
+    float* sehid = c.se ? f32_buf(static_cast<size_t>(B) * b.sq) : nullptr;
     if (!dry) {
       DwConvArgs a;
       a.in = e; a.w = wb(b.dw.w_off); a.out = dwo; a.scale = wf(b.dw.scale_off); a.shift = wf(b.dw.shift_off);
@@ -218,7 +226,7 @@ int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes,
         SeMlpArgs s;
         s.sums = gap; s.chunks = chunks; s.B = B; s.C = c.cexp; s.SQ = b.sq; s.HW = Ho * Wo;
         s.w1 = wb(b.fc1_w_off); s.b1 = wf(b.fc1_b_off); s.act1 = ACT_RELU;
-        s.w2 = wb(b.fc2_w_off); s.b2 = wf(b.fc2_b_off); s.act2 = ACT_HSIGMOID; s.out = sescale;
+        s.w2 = wb(b.fc2_w_off); s.b2 = wf(b.fc2_b_off); s.act2 = ACT_HSIGMOID; s.out = sescale; s.hidden = sehid;
         snprintf(nm, sizeof(nm), "b%d.se C%d", i + 1, c.cexp);
         PROF("se_mlp", 4.0 * B * c.cexp * (chunks + 1) + 4.0 * b.sq * c.cexp, 4.0 * B * b.sq * c.cexp, launch_se_mlp(s, st));
       }

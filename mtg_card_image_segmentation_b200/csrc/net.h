@@ -15,6 +15,8 @@ struct ConvBnPlan {
   int cout = 0;
   float eps = 1e-3f;
   size_t w_off = 0, scale_off = 0, shift_off = 0;  // offsets into the packed arena
+  size_t wt_off = 0;  // dgrad operand (transposed / flipped weights), 1x1 and 3x3 convs only
+  int cin = 0;        // input channels of the dense convs
 };
 
 struct BlockPlan {
@@ -60,5 +62,20 @@ int build_plan(const mtgseg_net_desc& d, NetPlan& P);
 int pack_weights(const NetPlan& P, const void* const* params, void* packed, cudaStream_t st);
 int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes, size_t* ws_needed, cudaStream_t st,
               LayerProfiler* prof = nullptr);
+
+// training step (net_train.cu): forward with batch-statistics BatchNorm keeping what backward needs in `ws`,
+// then backward producing fp32 parameter gradients in the reference (state_dict) layout.
+struct TrainIO {
+  const float* x = nullptr;             // [B][3][H][W] fp32
+  const void* packed = nullptr;         // packed arena (mtgseg_pack_weights)
+  void* const* params = nullptr;        // 319 state_dict device pointers (gamma/beta read, running stats updated in forward)
+  void* logits = nullptr; int logits_dtype = LOGITS_F32;          // forward output
+  const void* dlogits = nullptr; int dlogits_dtype = LOGITS_F32;  // backward input
+  float* const* grads = nullptr;        // backward: 319 pointers, fp32 grad per state_dict entry (NULL for buffers); pre-zeroed
+  int batch = 0;
+};
+size_t train_workspace_bytes(const NetPlan& P, int batch);
+int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st);
+int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace mtgseg

@@ -34,7 +34,7 @@ struct DwConvArgs {
   float* gap_partial = nullptr;  // optional [B][chunks][C] per-chunk channel sums of the output
   int chunks = 1;                // pixel chunks per image (grid.x); see dwconv_chunks()
 };
-int dwconv_chunks(int Ho, int Wo, int C, bool need_gap);
+int dwconv_chunks(int Ho, int Wo, int C, int stride, bool need_gap);
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st);
 
 struct StemArgs {
@@ -44,6 +44,7 @@ struct StemArgs {
   const float* shift = nullptr;
   bf16* out = nullptr;  // [B][Ho][Wo][16]
   int B = 0, H = 0, W = 0;
+  int act = ACT_HSWISH;  // ACT_NONE in training mode (BatchNorm uses batch statistics afterwards)
 };
 int launch_stem(const StemArgs& a, cudaStream_t st);
 
@@ -62,7 +63,8 @@ struct SeMlpArgs {
   const bf16* w2 = nullptr;   // [C][SQ] or nullptr
   const float* b2 = nullptr;
   int act2 = ACT_HSIGMOID;
-  float* out = nullptr;  // [B][C] (or [B][SQ] when single layer)
+  float* out = nullptr;     // [B][C] (or [B][SQ] when single layer)
+  float* hidden = nullptr;  // [B][SQ] scratch, required for the two-layer form
 };
 int launch_se_mlp(const SeMlpArgs& a, cudaStream_t st);
 
@@ -100,6 +102,80 @@ size_t loss_scratch_bytes();
 // loss3 = {total, dice_loss, ce_loss}; dlogits (same dtype/layout as logits, nullable) = dLoss/dlogits
 int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, float* scratch, float* loss3,
                 long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st);
+
+// ---- training-mode BatchNorm forward / backward (bn_train.cu) --------------------------------------
+int bn_chunks(int HW, int C);
+size_t bn_partial_floats(int B, int HW, int C);
+struct BnTrainFwdArgs {
+  const bf16* z = nullptr;      // [B][HW][C] raw conv output
+  bf16* y = nullptr;            // act(bn(z)) (+ residual)
+  const bf16* residual = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr;
+  float eps = 1e-3f, momentum = 1e-2f;
+  float* running_mean = nullptr; float* running_var = nullptr; long long* num_batches_tracked = nullptr;  // updated in place
+  float* scale = nullptr; float* shift = nullptr; float* save_mean = nullptr; float* save_rstd = nullptr;  // [C] each (saved for bwd)
+  float* partial = nullptr;     // scratch, bn_partial_floats()
+  float* gap = nullptr; int gap_chunks = 1;  // optional [B][gap_chunks][C] channel sums of y (squeeze-excite pool)
+  int act = ACT_NONE, B = 0, HW = 0, C = 0;
+};
+int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st);
+struct BnTrainBwdArgs {
+  const bf16* z = nullptr; const bf16* dy = nullptr; bf16* dz = nullptr;
+  const float* scale = nullptr; const float* shift = nullptr; const float* save_mean = nullptr; const float* save_rstd = nullptr;
+  const float* se_s = nullptr; const float* se_dmean = nullptr;  // optional [B][C]: dy' = dy*se_s + se_dmean/HW
+  float* partial = nullptr; float* dgamma = nullptr; float* dbeta = nullptr; float* c1 = nullptr; float* c2 = nullptr;
+  int act = ACT_NONE, B = 0, HW = 0, C = 0;
+};
+int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st);
+
+// ---- convolution backward kernels (train_conv.cu) ---------------------------------------------------
+struct WgradArgs {
+  const bf16* dz = nullptr;   // [M][N] gradient w.r.t. the raw conv output
+  const bf16* x = nullptr;    // [M][K] conv input (NHWC)
+  float* dw = nullptr;        // fp32 [N][K][taps] (OIHW), ACCUMULATED with atomics: zero it first
+  const float* a_scale = nullptr; int hw = 0;  // squeeze-excite multiplier [B][K] the forward applied to x
+  long long M = 0; int N = 0, K = 0, taps = 1, H = 0, W = 0;
+};
+int launch_wgrad(const WgradArgs& a, cudaStream_t st);
+struct DwBwdArgs {
+  const bf16* dz = nullptr; const bf16* x = nullptr; const bf16* w = nullptr;  // w: bf16 [k*k][C]
+  bf16* dx = nullptr; float* dw = nullptr;                                      // dw: fp32 [C][k*k], accumulated
+  int B = 0, H = 0, W = 0, C = 0, k = 3, stride = 1, dil = 1;
+};
+int launch_dw_dgrad(const DwBwdArgs& a, cudaStream_t st);
+int launch_dw_wgrad(const DwBwdArgs& a, cudaStream_t st);
+int launch_stem_wgrad(const float* x, const bf16* dz, float* dw, int B, int H, int W, cudaStream_t st);
+
+// ---- small backward kernels + AdamW (train_misc.cu) --------------------------------------------------
+int launch_dot_pool(const bf16* a, const bf16* b, float* out, int B, int HW, int C, int chunks, cudaStream_t st);
+struct SeBwdArgs {
+  const float* ds_partial = nullptr; int chunks = 1;
+  const float* s = nullptr; const float* hid = nullptr;
+  const float* w1 = nullptr; const float* w2 = nullptr;  // fp32 master weights; w2 == nullptr: single sigmoid layer
+  float* dpre2 = nullptr; float* dpre1 = nullptr; float* dmean = nullptr;
+  int B = 0, C = 0, SQ = 0;
+};
+int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st);
+int launch_outer_sum(const float* u, const float* v, int v_chunks, float vscale, float* dw, float* dbias, int B, int I, int J,
+                     cudaStream_t st);
+int launch_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int Hc, int Wc, int Hf, int Wf, long long sn, long long sc,
+                        long long sp, cudaStream_t st);
+struct HeadBwdArgs {
+  const float* d_o = nullptr; const float* dh2 = nullptr; const bf16* cbr = nullptr; const float* s = nullptr; const bf16* low = nullptr;
+  const float* w_high = nullptr; const float* w_low = nullptr;
+  bf16* dcbr = nullptr; float* ds = nullptr; bf16* dlow = nullptr;
+  float* dw_high = nullptr; float* dw_low = nullptr; float* db_high = nullptr; float* db_low = nullptr;  // accumulated (atomics)
+  int B = 0, Hh = 0, Wh = 0, Hl = 0, Wl = 0, IC = 0, LC = 0, NC = 0;
+};
+int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);
+int launch_add_bf16(const bf16* a, const bf16* b, bf16* out, size_t n, cudaStream_t st);
+int launch_fill_f32(float* p, float v, size_t n, cudaStream_t st);
+// chunk_table: device array of {float* p; const float* g; float* m; float* v; int n;} (one CTA per entry)
+int launch_adamw(const void* chunk_table, int n_chunks, float lr, float b1, float b2, float eps, float wd, int step,
+                 const float* inv_scale, const float* found_inf, cudaStream_t st);
+// [N][K] fp32 -> [K][N] bf16 ; [O][I][3][3] fp32 -> [I][9 (flipped)][O] bf16   (dgrad operands)
+int launch_pack_transpose_bf16(const float* in, bf16* out, int N, int K, cudaStream_t st);
+int launch_pack_dgrad3x3(const float* in, bf16* out, int O, int I, cudaStream_t st);
 
 // ---- weight packing (pack.cu) --------------------------------------------------------------------
 int launch_cast_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);

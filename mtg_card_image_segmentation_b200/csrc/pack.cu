@@ -47,6 +47,26 @@ __global__ void fold_bn_kernel(const float* __restrict__ g, const float* __restr
   }
 }
 
+// in [N][K] -> out [K][N]
+__global__ void transpose_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int N, int K) {
+  const size_t n = static_cast<size_t>(N) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int nn = static_cast<int>(i % N), kk = static_cast<int>(i / N);
+    out[i] = __float2bfloat16(in[static_cast<size_t>(nn) * K + kk]);
+  }
+}
+// in [O][I][9] -> out [I][9][O] with the taps flipped (dgrad of a stride-1 pad-1 3x3 conv is a 3x3 conv with w^T, rot180)
+__global__ void dgrad3x3_kernel(const float* __restrict__ in, bf16* __restrict__ out, int O, int I) {
+  const size_t n = static_cast<size_t>(O) * I * 9;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i % O);
+    const size_t r = i / O;
+    const int t = static_cast<int>(r % 9);
+    const size_t ci = r / 9;
+    out[i] = __float2bfloat16(in[(static_cast<size_t>(o) * I + ci) * 9 + (8 - t)]);
+  }
+}
+
 inline int blocks_for(size_t n) {
   size_t b = (n + 255) / 256;
   if (b > 1024) b = 1024;
@@ -73,6 +93,16 @@ int launch_pack_oihw_to_otapi(const float* in, bf16* out, int O, int I, int taps
 }
 int launch_pack_dw(const float* in, bf16* out, int C, int taps, cudaStream_t st) {
   pack_dw_kernel<<<blocks_for(static_cast<size_t>(C) * taps), 256, 0, st>>>(in, out, C, taps);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_pack_transpose_bf16(const float* in, bf16* out, int N, int K, cudaStream_t st) {
+  transpose_bf16_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(in, out, N, K);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_pack_dgrad3x3(const float* in, bf16* out, int O, int I, cudaStream_t st) {
+  dgrad3x3_kernel<<<blocks_for(static_cast<size_t>(O) * I * 9), 256, 0, st>>>(in, out, O, I);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -40,87 +40,74 @@ __global__ void __launch_bounds__(256) gap_kernel(const bf16* __restrict__ in, f
   }
 }
 
-constexpr int IPC = 2;  // images per CTA (each weight element is loaded once per IPC images)
+constexpr int FC_IMGS = 8;   // images per CTA: each weight element is loaded once per 8 images
+constexpr int FC_OUTS = 32;  // outputs per CTA (4 per warp)
 
-struct SeP {
-  const float* sums; int chunks, B, C, SQ; float inv_hw;
-  const bf16* w1; const float* b1; int act1;
-  const bf16* w2; const float* b2; int act2;
-  float* out;
+struct FcP {
+  const float* in; int chunks; float in_scale;  // in [B][chunks][C] (summed over chunks, times in_scale)
+  int B, C, O;
+  const bf16* w; const float* bias; int act;
+  float* out;  // [B][O]
 };
 
-__global__ void __launch_bounds__(256) se_mlp_kernel(const SeP p) {
-  extern __shared__ float sm[];
-  float* mean = sm;                   // [IPC][C]
-  float* hid = sm + IPC * p.C;        // [IPC][SQ]
-  const int n0 = blockIdx.x * IPC;
+// out[n][o] = act( sum_c w[o][c] * (in_scale * sum_k in[n][k][c]) + bias[o] )
+// grid (ceil(O/32), ceil(B/8)); each warp owns 4 outputs x 8 images, lanes stride over C in 8-wide vectors.
+__global__ void __launch_bounds__(256) fc_batched_kernel(const FcP p) {
+  extern __shared__ float xin[];  // [FC_IMGS][C]
+  const int n0 = blockIdx.y * FC_IMGS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = 0; i < IPC; ++i) {
-    const int n = n0 + i;
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-      float s = 0.f;
-      if (n < p.B)
-        for (int k = 0; k < p.chunks; ++k) s += p.sums[(static_cast<size_t>(n) * p.chunks + k) * p.C + c];
-      mean[i * p.C + c] = s * p.inv_hw;
-    }
+  for (int idx = threadIdx.x; idx < FC_IMGS * p.C; idx += blockDim.x) {
+    const int i = idx / p.C, c = idx - i * p.C;
+    float s = 0.f;
+    if (n0 + i < p.B)
+      for (int k = 0; k < p.chunks; ++k) s += p.in[(static_cast<size_t>(n0 + i) * p.chunks + k) * p.C + c];
+    xin[idx] = s * p.in_scale;
   }
   __syncthreads();
-  // layer 1: one warp per hidden unit, lanes stride over C in 8-channel vectors
-  for (int j = warp; j < p.SQ; j += 8) {
-    float acc[IPC];
+  const int o0 = blockIdx.x * FC_OUTS + warp * 4;
+  if (o0 >= p.O) return;
+  float acc[4][FC_IMGS];
 #pragma unroll
-    for (int i = 0; i < IPC; ++i) acc[i] = 0.f;
-    const bf16* wr = p.w1 + static_cast<size_t>(j) * p.C;
-    for (int c = lane * 8; c < p.C; c += 256) {
-      float wf[8];
-      unpack8(ldg16(wr + c), wf);
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int i = 0; i < IPC; ++i)
+    for (int i = 0; i < FC_IMGS; ++i) acc[a][i] = 0.f;
+  for (int c = lane * 8; c < p.C; c += 256) {
+    float wf[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i] = fmaf(wf[e], mean[i * p.C + c + e], acc[i]);
+    for (int a = 0; a < 4; ++a) {
+      if (o0 + a < p.O) unpack8(ldg16(p.w + static_cast<size_t>(o0 + a) * p.C + c), wf[a]);
+      else
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wf[a][e] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < IPC; ++i) {
+    for (int i = 0; i < FC_IMGS; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xin + i * p.C + c);
+      const float4 x1 = *reinterpret_cast<const float4*>(xin + i * p.C + c + 4);
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-    }
-    if (lane == 0) {
-      const float b = p.b1 ? p.b1[j] : 0.f;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int i = 0; i < IPC; ++i) {
-        const float h = apply_act(acc[i] + b, p.act1);
-        hid[i * p.SQ + j] = h;
-        if (!p.w2 && n0 + i < p.B) p.out[static_cast<size_t>(n0 + i) * p.SQ + j] = h;
-      }
+        for (int e = 0; e < 8; ++e) acc[a][i] = fmaf(wf[a][e], xv[e], acc[a][i]);
     }
   }
-  if (!p.w2) return;
-  __syncthreads();
-  // layer 2: one warp per output channel, lanes stride over SQ (SQ % 8 == 0)
-  for (int c = warp; c < p.C; c += 8) {
-    float acc[IPC];
 #pragma unroll
-    for (int i = 0; i < IPC; ++i) acc[i] = 0.f;
-    const bf16* wr = p.w2 + static_cast<size_t>(c) * p.SQ;
-    for (int j = lane * 8; j < p.SQ; j += 256) {
-      float wf[8];
-      unpack8(ldg16(wr + j), wf);
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int i = 0; i < IPC; ++i)
+    for (int i = 0; i < FC_IMGS; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i] = fmaf(wf[e], hid[i * p.SQ + j + e], acc[i]);
-    }
+      for (int o = 16; o > 0; o >>= 1) acc[a][i] += __shfl_xor_sync(0xffffffffu, acc[a][i], o);
+  // lane (a*8 + i) writes output a of image i
+  const int a_sel = lane >> 3, i_sel = lane & 7;
+  float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < IPC; ++i) {
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-    }
-    if (lane == 0) {
-      const float b = p.b2 ? p.b2[c] : 0.f;
-#pragma unroll
-      for (int i = 0; i < IPC; ++i)
-        if (n0 + i < p.B) p.out[static_cast<size_t>(n0 + i) * p.C + c] = apply_act(acc[i] + b, p.act2);
-    }
+    for (int i = 0; i < FC_IMGS; ++i)
+      if (a == a_sel && i == i_sel) v = acc[a][i];
+  if (o0 + a_sel < p.O && n0 + i_sel < p.B) {
+    const float b = p.bias ? p.bias[o0 + a_sel] : 0.f;
+    p.out[static_cast<size_t>(n0 + i_sel) * p.O + o0 + a_sel] = apply_act(v + b, p.act);
   }
 }
 
@@ -137,11 +124,19 @@ int launch_gap(const bf16* in, float* out, int B, int HW, int C, cudaStream_t st
 int launch_se_mlp(const SeMlpArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.sums && a.w1 && a.out && a.HW > 0, MTG_ERR_ARG, "se_mlp: null pointer");
   MTG_REQUIRE(a.C % 8 == 0 && a.SQ % 8 == 0, MTG_ERR_UNSUPPORTED, "se_mlp: C=%d SQ=%d must be multiples of 8", a.C, a.SQ);
-  SeP p{a.sums, a.chunks, a.B, a.C, a.SQ, 1.0f / static_cast<float>(a.HW), a.w1, a.b1, a.act1, a.w2, a.b2, a.act2, a.out};
-  const size_t smem = static_cast<size_t>(IPC) * (a.C + a.SQ) * sizeof(float);
-  MTG_REQUIRE(smem <= 48 * 1024, MTG_ERR_UNSUPPORTED, "se_mlp: C too large");
-  se_mlp_kernel<<<ceil_div(a.B, IPC), 256, smem, st>>>(p);
+  MTG_REQUIRE(!a.w2 || a.hidden, MTG_ERR_ARG, "se_mlp: the two-layer form needs a hidden scratch buffer [B][SQ]");
+  const int cmax = a.C > a.SQ ? a.C : a.SQ;
+  MTG_REQUIRE(static_cast<size_t>(FC_IMGS) * cmax * sizeof(float) <= 48 * 1024, MTG_ERR_UNSUPPORTED, "se_mlp: C too large");
+  FcP l1{a.sums, a.chunks, 1.0f / static_cast<float>(a.HW), a.B, a.C, a.SQ, a.w1, a.b1, a.act1, a.w2 ? a.hidden : a.out};
+  dim3 g1(ceil_div(a.SQ, FC_OUTS), ceil_div(a.B, FC_IMGS));
+  fc_batched_kernel<<<g1, 256, static_cast<size_t>(FC_IMGS) * a.C * sizeof(float), st>>>(l1);
   MTG_LAUNCH_CHECK();
+  if (a.w2) {
+    FcP l2{a.hidden, 1, 1.0f, a.B, a.SQ, a.C, a.w2, a.b2, a.act2, a.out};
+    dim3 g2(ceil_div(a.C, FC_OUTS), ceil_div(a.B, FC_IMGS));
+    fc_batched_kernel<<<g2, 256, static_cast<size_t>(FC_IMGS) * a.SQ * sizeof(float), st>>>(l2);
+    MTG_LAUNCH_CHECK();
+  }
   return MTG_OK;
 }
 

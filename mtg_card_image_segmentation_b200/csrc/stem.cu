@@ -11,7 +11,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                                   bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo) {
+                                                   bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int act) {
   __shared__ float4 sw[27 * 4];
   __shared__ float ssc[16], ssh[16];
   for (int i = threadIdx.x; i < 27 * 4; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     float o0[8], o1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      o0[j] = apply_act(fmaf(acc[j], ssc[j], ssh[j]), ACT_HSWISH);
-      o1[j] = apply_act(fmaf(acc[8 + j], ssc[8 + j], ssh[8 + j]), ACT_HSWISH);
+      o0[j] = apply_act(fmaf(acc[j], ssc[j], ssh[j]), act);
+      o1[j] = apply_act(fmaf(acc[8 + j], ssc[8 + j], ssh[8 + j]), act);
     }
     uint4* op = reinterpret_cast<uint4*>(out + idx * 16);
     op[0] = pack8(o0);
@@ -71,7 +71,7 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
   const long long total = static_cast<long long>(a.B) * Ho * Wo;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stem_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(a.x, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo);
+  stem_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(a.x, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

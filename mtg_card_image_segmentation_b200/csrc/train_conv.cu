@@ -1,0 +1,316 @@
+// Backward kernels of the convolutions that are not (yet) on the tensor cores:
+//   wgrad of the 1x1 / 3x3 convolutions (CUDA-core tiled GEMM over the pixel dimension, split-K + fp32 atomics),
+//   depthwise dgrad and wgrad, stem wgrad.
+// dgrad of the 1x1 / 3x3 convolutions reuses the tcgen05 implicit-GEMM kernel (gemm_tc.cu) with transposed weights.
+// Gradients of parameters are accumulated in fp32 directly in the reference's OIHW layout.
+#include "ops.h"
+
+namespace mtgseg {
+
+int group_vectors(int CV);  // dwconv.cu
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// dW[n][k][tap] += sum_m dz[m][n] * x[shift_tap(m)][k] (* a_scale[img(m)][k])
+// CTA tile 64 (n) x 64 (k), 256 threads x (4 x 4) outputs, 16 pixels per smem step.
+// ---------------------------------------------------------------------------------------------------------
+struct WgP {
+  const bf16* dz; const bf16* x; float* dw; const float* a_scale;
+  long long M; int N, K, taps, H, W, hw;  // taps = 1 or 9 (3x3 pad 1)
+  long long rows_per_chunk;
+};
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgP p) {
+  __shared__ __align__(16) float sdz[16][64];
+  __shared__ __align__(16) float sx[16][64];
+  const int k_tiles = (p.K + 63) / 64;
+  const int n0 = (blockIdx.x / k_tiles) * 64, k0 = (blockIdx.x % k_tiles) * 64;
+  const int tap = blockIdx.y;
+  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const long long m_begin = blockIdx.z * p.rows_per_chunk;
+  const long long m_end = min(p.M, m_begin + p.rows_per_chunk);
+  const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;
+  // loader role: threads 0..127 load dz (16 px x 8 vectors), 128..255 load x
+  const int lrole = threadIdx.x >> 7, lt = threadIdx.x & 127, lp = lt >> 3, lv = lt & 7;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long m0 = m_begin; m0 < m_end; m0 += 16) {
+    const long long m = m0 + lp;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (m < m_end) {
+      if (lrole == 0) {
+        const int n = n0 + lv * 8;
+        if (n < p.N) unpack8(ldg16(p.dz + m * p.N + n), f);
+      } else {
+        const int k = k0 + lv * 8;
+        if (k < p.K) {
+          long long ms = m;
+          bool ok = true;
+          if (p.taps == 9) {
+            const int px = static_cast<int>(m % p.W), py = static_cast<int>((m / p.W) % p.H);
+            ok = (px + dx >= 0) && (px + dx < p.W) && (py + dy >= 0) && (py + dy < p.H);
+            ms = m + dy * p.W + dx;
+          }
+          if (ok) {
+            unpack8(ldg16(p.x + ms * p.K + k), f);
+            if (p.a_scale) {
+              const float* sp = p.a_scale + (m / p.hw) * p.K + k;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j] * sp[j]));  // what the forward MMA consumed
+            }
+          }
+        }
+      }
+    }
+    float* dst = lrole == 0 ? &sdz[lp][lv * 8] : &sx[lp][lv * 8];
+    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < 16; ++pp) {
+      const float4 a = *reinterpret_cast<const float4*>(&sdz[pp][tn * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sx[pp][tk * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + tn * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + j;
+      if (n < p.N && k < p.K) atomicAdd(p.dw + (static_cast<size_t>(n) * p.K + k) * p.taps + tap, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// depthwise
+// ---------------------------------------------------------------------------------------------------------
+struct DwBwdP {
+  const bf16* dz; const bf16* x; const bf16* w; bf16* dx; float* dw;
+  int H, W, C, Ho, Wo, k, stride, dil, pad, CV, CVc, PL, rows_per_chunk, chunks;
+};
+
+// dx[n,iy,ix,c] = sum_taps w[tap][c] * dz[n,(iy+pad-ky*d)/s,(ix+pad-kx*d)/s,c]   (grid: chunks, groups, B)
+template <int KS>
+__global__ void __launch_bounds__(256) dw_dgrad_kernel(const DwBwdP p) {
+  const int vl = threadIdx.x % p.CVc, pl = threadIdx.x / p.CVc;
+  const int v = blockIdx.y * p.CVc + vl;
+  if (pl >= p.PL || v >= p.CV) return;
+  const int c0 = v * 8, n = blockIdx.z;
+  const int npix = p.H * p.W;
+  const int r0 = blockIdx.x * p.rows_per_chunk, r1 = min(npix, r0 + p.rows_per_chunk);
+  const bf16* dz_n = p.dz + static_cast<size_t>(n) * p.Ho * p.Wo * p.C + c0;
+  bf16* dx_n = p.dx + static_cast<size_t>(n) * npix * p.C + c0;
+  for (int pix = r0 + pl; pix < r1; pix += p.PL) {
+    const int iy = pix / p.W, ix = pix - iy * p.W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int ty = iy + p.pad - ky * p.dil;
+      if (ty < 0 || ty % p.stride) continue;
+      const int oy = ty / p.stride;
+      if (oy >= p.Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int tx = ix + p.pad - kx * p.dil;
+        if (tx < 0 || tx % p.stride) continue;
+        const int ox = tx / p.stride;
+        if (ox >= p.Wo) continue;
+        float g[8], wf[8];
+        unpack8(ldg16(dz_n + (static_cast<size_t>(oy) * p.Wo + ox) * p.C), g);
+        unpack8(ldg16(p.w + (ky * KS + kx) * p.C + c0), wf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], wf[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx_n + static_cast<size_t>(pix) * p.C) = pack8(acc);
+  }
+}
+
+// dW[c][ky][kx] += sum dz[n,oy,ox,c] * x[n,oy*s-pad+ky*d,ox*s-pad+kx*d,c]; one kernel row (ky) per CTA:
+// grid (chunks*KS, groups, B)
+template <int KS>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const DwBwdP p) {
+  __shared__ float red[256 * 8];
+  const int vl = threadIdx.x % p.CVc, pl = threadIdx.x / p.CVc;
+  const int v = blockIdx.y * p.CVc + vl;
+  const bool active = pl < p.PL && v < p.CV;
+  const int c0 = (active ? v : 0) * 8, n = blockIdx.z;
+  const int chunk = blockIdx.x / KS, ky = blockIdx.x % KS;
+  float acc[KS][8];
+#pragma unroll
+  for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[kx][j] = 0.f;
+  if (active) {
+    const int npix = p.Ho * p.Wo;
+    const int r0 = chunk * p.rows_per_chunk, r1 = min(npix, r0 + p.rows_per_chunk);
+    const bf16* dz_n = p.dz + static_cast<size_t>(n) * npix * p.C + c0;
+    const bf16* x_n = p.x + static_cast<size_t>(n) * p.H * p.W * p.C + c0;
+    for (int pix = r0 + pl; pix < r1; pix += p.PL) {
+      const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+      const int iy = oy * p.stride - p.pad + ky * p.dil;
+      if (iy < 0 || iy >= p.H) continue;
+      float g[8];
+      unpack8(ldg16(dz_n + static_cast<size_t>(pix) * p.C), g);
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int ix = ox * p.stride - p.pad + kx * p.dil;
+        if (ix < 0 || ix >= p.W) continue;
+        float xf[8];
+        unpack8(ldg16(x_n + (static_cast<size_t>(iy) * p.W + ix) * p.C), xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], xf[j], acc[kx][j]);
+      }
+    }
+  }
+  const int cw = p.CVc * 8;
+#pragma unroll
+  for (int kx = 0; kx < KS; ++kx) {
+    __syncthreads();
+    if (pl < p.PL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(pl * p.CVc + vl) * 8 + j] = active ? acc[kx][j] : 0.f;
+    }
+    __syncthreads();
+    for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < p.C) {
+        float s = 0.f;
+        for (int r = 0; r < p.PL; ++r) s += red[r * cw + cl];
+        atomicAdd(p.dw + static_cast<size_t>(c) * KS * KS + ky * KS + kx, s);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stem wgrad: dW[o][ci][ky][kx] += sum dz[n,oy,ox,o] * x[n,ci,2oy-1+ky,2ox-1+kx]   (432 outputs)
+// CTA: 64 output pixels staged in smem (27 patch values + 16 gradients each); thread t < 432 owns one weight.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(448) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz,
+                                                         float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
+                                                         long long pix_per_cta) {
+  __shared__ float sp[64][28];
+  __shared__ float sg[64][16];
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const long long p_begin = blockIdx.x * pix_per_cta, p_end = min(total, p_begin + pix_per_cta);
+  const int t = threadIdx.x;
+  const int o = t / 27, q = t % 27;  // weight (o, q) with q = ci*9 + ky*3 + kx
+  float acc = 0.f;
+  for (long long p0 = p_begin; p0 < p_end; p0 += 64) {
+    for (int i = t; i < 64 * 27; i += blockDim.x) {
+      const int pp = i / 27, qq = i % 27;
+      const long long pix = p0 + pp;
+      float v = 0.f;
+      if (pix < p_end) {
+        const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho), n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+        const int ci = qq / 9, ky = (qq % 9) / 3, kx = qq % 3;
+        const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<size_t>(n) * 3 + ci) * H + iy) * W + ix);
+      }
+      sp[pp][qq] = v;
+    }
+    for (int i = t; i < 64 * 16; i += blockDim.x) {
+      const int pp = i / 16, oo = i % 16;
+      const long long pix = p0 + pp;
+      sg[pp][oo] = pix < p_end ? __bfloat162float(dz[pix * 16 + oo]) : 0.f;
+    }
+    __syncthreads();
+    if (t < 432) {
+#pragma unroll 8
+      for (int pp = 0; pp < 64; ++pp) acc = fmaf(sg[pp][o], sp[pp][q], acc);
+    }
+    __syncthreads();
+  }
+  if (t < 432) atomicAdd(dw + o * 27 + q, acc);
+}
+
+}  // namespace
+
+int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.dz && a.x && a.dw, MTG_ERR_ARG, "wgrad: null pointer");
+  MTG_REQUIRE(a.N % 8 == 0 && a.K % 8 == 0, MTG_ERR_UNSUPPORTED, "wgrad: channels must be multiples of 8");
+  MTG_REQUIRE(a.taps == 1 || a.taps == 9, MTG_ERR_UNSUPPORTED, "wgrad: taps must be 1 or 9");
+  WgP p{a.dz, a.x, a.dw, a.a_scale, a.M, a.N, a.K, a.taps, a.H, a.W, a.hw, 0};
+  const int tiles = ceil_div(a.N, 64) * ceil_div(a.K, 64);
+  // enough pixel chunks to fill the machine (~4 CTAs per SM), at least 256 pixels per chunk
+  long long chunks = (148 * 4 + tiles * a.taps - 1) / (tiles * a.taps);
+  const long long max_chunks = (a.M + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  p.rows_per_chunk = (((a.M + chunks - 1) / chunks) + 15) / 16 * 16;
+  chunks = (a.M + p.rows_per_chunk - 1) / p.rows_per_chunk;
+  dim3 grid(tiles, a.taps, static_cast<unsigned>(chunks));
+  wgrad_kernel<<<grid, 256, 0, st>>>(p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+static int fill_dw(const DwBwdArgs& a, DwBwdP& p, int rows) {
+  p.dz = a.dz; p.x = a.x; p.w = a.w; p.dx = a.dx; p.dw = a.dw;
+  p.H = a.H; p.W = a.W; p.C = a.C; p.k = a.k; p.stride = a.stride; p.dil = a.dil;
+  p.pad = (a.k - 1) / 2 * a.dil;
+  p.Ho = (a.H + 2 * p.pad - a.dil * (a.k - 1) - 1) / a.stride + 1;
+  p.Wo = (a.W + 2 * p.pad - a.dil * (a.k - 1) - 1) / a.stride + 1;
+  p.CV = a.C / 8; p.CVc = group_vectors(p.CV); p.PL = 256 / p.CVc;
+  const int npix = rows == 0 ? a.H * a.W : p.Ho * p.Wo;
+  p.chunks = ceil_div(npix, p.PL * 8);
+  if (p.chunks > 64) p.chunks = 64;
+  p.rows_per_chunk = ceil_div(npix, p.chunks);
+  return MTG_OK;
+}
+
+int launch_dw_dgrad(const DwBwdArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.dz && a.w && a.dx, MTG_ERR_ARG, "dw_dgrad: null pointer");
+  MTG_REQUIRE(a.C % 8 == 0 && (a.k == 3 || a.k == 5), MTG_ERR_UNSUPPORTED, "dw_dgrad: unsupported shape");
+  DwBwdP p{};
+  fill_dw(a, p, 0);
+  dim3 grid(p.chunks, ceil_div(p.CV, p.CVc), a.B);
+  if (a.k == 3) dw_dgrad_kernel<3><<<grid, 256, 0, st>>>(p);
+  else dw_dgrad_kernel<5><<<grid, 256, 0, st>>>(p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_dw_wgrad(const DwBwdArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.dz && a.x && a.dw, MTG_ERR_ARG, "dw_wgrad: null pointer");
+  MTG_REQUIRE(a.C % 8 == 0 && (a.k == 3 || a.k == 5), MTG_ERR_UNSUPPORTED, "dw_wgrad: unsupported shape");
+  DwBwdP p{};
+  fill_dw(a, p, 1);
+  dim3 grid(p.chunks * a.k, ceil_div(p.CV, p.CVc), a.B);
+  if (a.k == 3) dw_wgrad_kernel<3><<<grid, 256, 0, st>>>(p);
+  else dw_wgrad_kernel<5><<<grid, 256, 0, st>>>(p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_stem_wgrad(const float* x, const bf16* dz, float* dw, int B, int H, int W, cudaStream_t st) {
+  MTG_REQUIRE(x && dz && dw, MTG_ERR_ARG, "stem_wgrad: null pointer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  long long ctas = 148 * 4;
+  long long per = ((total + ctas - 1) / ctas + 63) / 64 * 64;
+  ctas = (total + per - 1) / per;
+  stem_wgrad_kernel<<<static_cast<unsigned>(ctas), 448, 0, st>>>(x, dz, dw, B, H, W, Ho, Wo, per);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+}  // namespace mtgseg

@@ -1,0 +1,370 @@
+// Small backward kernels of the training step: squeeze-excite, head tail (bilinear transposes, classifiers,
+// scale branch), elementwise helpers and the fused multi-tensor AdamW.
+// Everything here moves little data (pooled vectors, 2-channel maps) or is a single streaming pass.
+#include <cuda_fp16.h>
+
+#include "ops.h"
+
+namespace mtgseg {
+
+int group_vectors(int CV);  // dwconv.cu
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// ds[n][c] partials = sum_p a[n,p,c] * b[n,p,c]   (grid: chunks, groups, B) -> out [B][chunks][C]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dot_pool_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, float* __restrict__ out,
+                                                       int HW, int C, int CV, int CVc, int PL, int rows_per_chunk, int chunks) {
+  __shared__ float red[256 * 8];
+  const int vl = threadIdx.x % CVc, pl = threadIdx.x / CVc;
+  const int v = blockIdx.y * CVc + vl;
+  const bool active = pl < PL && v < CV;
+  const int c0 = (active ? v : 0) * 8, n = blockIdx.z, chunk = blockIdx.x;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (active) {
+    const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+    const size_t img = static_cast<size_t>(n) * HW * C + c0;
+    for (int r = r0 + pl; r < r1; r += PL) {
+      float fa[8], fb[8];
+      unpack8(ldg16(a + img + static_cast<size_t>(r) * C), fa);
+      unpack8(ldg16(b + img + static_cast<size_t>(r) * C), fb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(fa[j], fb[j], acc[j]);
+    }
+  }
+  if (pl < PL) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[(pl * CVc + vl) * 8 + j] = active ? acc[j] : 0.f;
+  }
+  __syncthreads();
+  const int cw = CVc * 8;
+  for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
+    const int c = blockIdx.y * cw + cl;
+    if (c < C) {
+      float s = 0.f;
+      for (int r = 0; r < PL; ++r) s += red[r * cw + cl];
+      out[(static_cast<size_t>(n) * chunks + chunk) * C + c] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SE MLP backward, one CTA per image.  Forward: mean -> hid = relu(W1 mean + b1) -> s = hsig(W2 hid + b2)
+// (or, single layer: s = sigmoid(W1 mean)).  In: ds partial sums.  Out: dpre2[n][C], dpre1[n][SQ], dmean[n][C].
+// ---------------------------------------------------------------------------------------------------------
+struct SeBwdP {
+  const float* ds_partial; int chunks;
+  const float* s; const float* hid;
+  const float* w1; const float* w2;  // fp32 master weights: w1 [SQ][C], w2 [C][SQ]
+  float* dpre2; float* dpre1; float* dmean;
+  int C, SQ, single;                 // single: s = sigmoid(W1 mean), C = pooled channels, SQ = outputs
+};
+__global__ void __launch_bounds__(256) se_bwd_kernel(const SeBwdP p) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.x;
+  if (p.single) {
+    // s[n][j] (SQ outputs) = sigmoid(sum_c w1[j][c] mean[c]);  ds given per output j
+    float* dpre = sm;  // [SQ]
+    for (int j = threadIdx.x; j < p.SQ; j += blockDim.x) {
+      float d = 0.f;
+      for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.SQ + j];
+      const float sv = p.s[static_cast<size_t>(n) * p.SQ + j];
+      d *= sv * (1.f - sv);
+      dpre[j] = d;
+      p.dpre1[static_cast<size_t>(n) * p.SQ + j] = d;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      float a = 0.f;
+      for (int j = 0; j < p.SQ; ++j) a = fmaf(p.w1[static_cast<size_t>(j) * p.C + c], dpre[j], a);
+      p.dmean[static_cast<size_t>(n) * p.C + c] = a;
+    }
+    return;
+  }
+  float* dpre2 = sm;            // [C]
+  float* dpre1 = sm + p.C;      // [SQ]
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float d = 0.f;
+    for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.C + c];
+    const float sv = p.s[static_cast<size_t>(n) * p.C + c];
+    d = (sv > 0.f && sv < 1.f) ? d * (1.f / 6.f) : 0.f;  // hardsigmoid'
+    dpre2[c] = d;
+    p.dpre2[static_cast<size_t>(n) * p.C + c] = d;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < p.SQ; j += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < p.C; ++c) a = fmaf(p.w2[static_cast<size_t>(c) * p.SQ + j], dpre2[c], a);
+    a = p.hid[static_cast<size_t>(n) * p.SQ + j] > 0.f ? a : 0.f;  // relu'
+    dpre1[j] = a;
+    p.dpre1[static_cast<size_t>(n) * p.SQ + j] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < p.SQ; ++j) a = fmaf(p.w1[static_cast<size_t>(j) * p.C + c], dpre1[j], a);
+    p.dmean[static_cast<size_t>(n) * p.C + c] = a;
+  }
+}
+
+// dW[i][j] = sum_n u[n][i] * v[n][j] * vscale ; optional dbias[i] = sum_n u[n][i].   v may be chunked partial sums.
+__global__ void outer_sum_kernel(const float* __restrict__ u, const float* __restrict__ v, int v_chunks, float vscale,
+                                 float* __restrict__ dw, float* __restrict__ dbias, int B, int I, int J) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I * J) return;
+  const int i = idx / J, j = idx - i * J;
+  float a = 0.f, bsum = 0.f;
+  for (int n = 0; n < B; ++n) {
+    float vv = 0.f;
+    for (int k = 0; k < v_chunks; ++k) vv += v[(static_cast<size_t>(n) * v_chunks + k) * J + j];
+    const float uu = u[static_cast<size_t>(n) * I + i];
+    a = fmaf(uu, vv * vscale, a);
+    bsum += uu;
+  }
+  dw[idx] = a;
+  if (dbias && j == 0) dbias[i] = bsum;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// transpose of the bilinear upsample (align_corners=False): dlow[n,q,c] = sum_pix w(pix -> q) dhigh_res[n,c,pix]
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+
+// g: gradient at the fine resolution, element (n, c, y, x) at g[n*sn + c*sc + (y*Wf + x)*sp]; out fp32 [n][q][c]
+template <typename T>
+__global__ void __launch_bounds__(128) upsample_bwd_kernel(const T* __restrict__ g, float* __restrict__ out, int B, int NC, int Hc, int Wc,
+                                                           int Hf, int Wf, long long sn, long long sc, long long sp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Hc * Wc * NC) return;
+  const int c = idx % NC;
+  int t = idx / NC;
+  const int qx = t % Wc; t /= Wc;
+  const int qy = t % Hc;
+  const int n = t / Hc;
+  const float sy = static_cast<float>(Hc) / Hf, sx = static_cast<float>(Wc) / Wf;
+  // fine rows whose source interval can touch qy: src in (qy-1, qy+1)
+  const int y_lo = max(0, static_cast<int>(floorf((qy - 1 + 0.5f) / sy - 0.5f)) - 1);
+  const int y_hi = min(Hf - 1, static_cast<int>(ceilf((qy + 1 + 0.5f) / sy - 0.5f)) + 1);
+  const int x_lo = max(0, static_cast<int>(floorf((qx - 1 + 0.5f) / sx - 0.5f)) - 1);
+  const int x_hi = min(Wf - 1, static_cast<int>(ceilf((qx + 1 + 0.5f) / sx - 0.5f)) + 1);
+  const T* gp = g + n * sn + c * sc;
+  float acc = 0.f;
+  for (int y = y_lo; y <= y_hi; ++y) {
+    int y0, y1; float ly;
+    src_index(y, sy, Hc, y0, y1, ly);
+    const float wy = (y0 == qy ? 1.f - ly : 0.f) + (y1 == qy ? ly : 0.f);
+    if (wy == 0.f) continue;
+    float row = 0.f;
+    for (int x = x_lo; x <= x_hi; ++x) {
+      int x0, x1; float lx;
+      src_index(x, sx, Wc, x0, x1, lx);
+      const float wx = (x0 == qx ? 1.f - lx : 0.f) + (x1 == qx ? lx : 0.f);
+      if (wx != 0.f) row = fmaf(wx, ldf(gp + (static_cast<long long>(y) * Wf + x) * sp), row);
+    }
+    acc = fmaf(wy, row, acc);
+  }
+  out[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// head tail backward, one CTA per image (see tail.cu for the forward):
+//   in : dlow_logits do[n,q,c] (40x30), dh2[n,p,c] (20x15, = up2^T(do)), cbr, s, low
+//   out: dcbr[n,p,i] = s[n,i] * sum_c dh2 Wh[c,i] ; ds partial[n][i] = sum_p (sum_c dh2 Wh[c,i]) cbr ;
+//        dlow[n,q,k] = sum_c do Wl[c,k] ; atomics into dWh[c,i], dWl[c,k], dbias[c] (both biases get the same gradient)
+// ---------------------------------------------------------------------------------------------------------
+struct HeadBwdP {
+  const float* d_o; const float* dh2; const bf16* cbr; const float* s; const bf16* low;
+  const float* w_high; const float* w_low;
+  bf16* dcbr; float* ds; bf16* dlow; float* dw_high; float* dw_low; float* db_high; float* db_low;
+  int Hh, Wh, Hl, Wl, IC, LC, NC;
+};
+constexpr int MAX_NC = 8;
+__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
+  const int n = blockIdx.x;
+  const int nh = p.Hh * p.Wh, nl = p.Hl * p.Wl;
+  // part 1: thread i < IC owns inter channel i over all high-res pixels
+  for (int i = threadIdx.x; i < p.IC; i += blockDim.x) {
+    const float sv = p.s[static_cast<size_t>(n) * p.IC + i];
+    float wh[MAX_NC], dwh[MAX_NC];
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c) { wh[c] = c < p.NC ? p.w_high[c * p.IC + i] : 0.f; dwh[c] = 0.f; }
+    float dsv = 0.f;
+    for (int px = 0; px < nh; ++px) {
+      const size_t row = static_cast<size_t>(n) * nh + px;
+      const float cv = __bfloat162float(p.cbr[row * p.IC + i]);
+      float dt = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAX_NC; ++c)
+        if (c < p.NC) {
+          const float g = p.dh2[row * p.NC + c];
+          dt = fmaf(g, wh[c], dt);
+          dwh[c] = fmaf(g, sv * cv, dwh[c]);
+        }
+      p.dcbr[row * p.IC + i] = __float2bfloat16(dt * sv);
+      dsv = fmaf(dt, cv, dsv);
+    }
+    p.ds[static_cast<size_t>(n) * p.IC + i] = dsv;
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c)
+      if (c < p.NC) atomicAdd(p.dw_high + c * p.IC + i, dwh[c]);
+  }
+  // part 2: thread k < LC owns low channel k over all low-res pixels
+  for (int k = threadIdx.x; k < p.LC; k += blockDim.x) {
+    float wl[MAX_NC], dwl[MAX_NC];
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c) { wl[c] = c < p.NC ? p.w_low[c * p.LC + k] : 0.f; dwl[c] = 0.f; }
+    for (int q = 0; q < nl; ++q) {
+      const size_t row = static_cast<size_t>(n) * nl + q;
+      const float lv = __bfloat162float(p.low[row * p.LC + k]);
+      float dl = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAX_NC; ++c)
+        if (c < p.NC) {
+          const float g = p.d_o[row * p.NC + c];
+          dl = fmaf(g, wl[c], dl);
+          dwl[c] = fmaf(g, lv, dwl[c]);
+        }
+      p.dlow[row * p.LC + k] = __float2bfloat16(dl);
+    }
+#pragma unroll
+    for (int c = 0; c < MAX_NC; ++c)
+      if (c < p.NC) atomicAdd(p.dw_low + c * p.LC + k, dwl[c]);
+  }
+  // part 3: bias gradients
+  if (threadIdx.x < p.NC) {
+    float b = 0.f;
+    for (int q = 0; q < nl; ++q) b += p.d_o[(static_cast<size_t>(n) * nl + q) * p.NC + threadIdx.x];
+    atomicAdd(p.db_high + threadIdx.x, b);
+    atomicAdd(p.db_low + threadIdx.x, b);
+  }
+}
+
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, size_t nvec) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float fa[8], fb[8];
+    unpack8(ldg16(a + i * 8), fa);
+    unpack8(ldg16(b + i * 8), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(fa);
+  }
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, float v, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AdamW, all parameter tensors in one launch (torch.optim.AdamW maths, decoupled weight decay):
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// grads are multiplied by *inv_scale (GradScaler) when given; the whole step is skipped when *found_inf != 0.
+// ---------------------------------------------------------------------------------------------------------
+struct AdamChunk { float* p; const float* g; float* m; float* v; int n; };
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale,
+                                                    const float* __restrict__ found_inf) {
+  if (found_inf && *found_inf != 0.f) return;
+  const AdamChunk c = chunks[blockIdx.x];
+  const float gs = inv_scale ? *inv_scale : 1.f;
+  const float step_size = lr / bc1;
+  for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
+    const float g = c.g[i] * gs;
+    float pv = c.p[i] * (1.f - lr * wd);
+    const float m = b1 * c.m[i] + (1.f - b1) * g;
+    const float v = b2 * c.v[i] + (1.f - b2) * g * g;
+    pv -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+    c.p[i] = pv; c.m[i] = m; c.v[i] = v;
+  }
+}
+
+}  // namespace
+
+int launch_dot_pool(const bf16* a, const bf16* b, float* out, int B, int HW, int C, int chunks, cudaStream_t st) {
+  MTG_REQUIRE(a && b && out && C % 8 == 0, MTG_ERR_ARG, "dot_pool: bad arguments");
+  const int CV = C / 8, CVc = group_vectors(CV), PL = 256 / CVc;
+  dim3 grid(chunks, ceil_div(CV, CVc), B);
+  dot_pool_kernel<<<grid, 256, 0, st>>>(a, b, out, HW, C, CV, CVc, PL, ceil_div(HW, chunks), chunks);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.ds_partial && a.s && a.w1 && a.dpre1 && a.dmean, MTG_ERR_ARG, "se_bwd: null pointer");
+  SeBwdP p{a.ds_partial, a.chunks, a.s, a.hid, a.w1, a.w2, a.dpre2, a.dpre1, a.dmean, a.C, a.SQ, a.w2 ? 0 : 1};
+  se_bwd_kernel<<<a.B, 256, sizeof(float) * (a.C + a.SQ), st>>>(p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_outer_sum(const float* u, const float* v, int v_chunks, float vscale, float* dw, float* dbias, int B, int I, int J,
+                     cudaStream_t st) {
+  MTG_REQUIRE(u && v && dw, MTG_ERR_ARG, "outer_sum: null pointer");
+  outer_sum_kernel<<<ceil_div(I * J, 256), 256, 0, st>>>(u, v, v_chunks, vscale, dw, dbias, B, I, J);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int Hc, int Wc, int Hf, int Wf, long long sn, long long sc,
+                        long long sp, cudaStream_t st) {
+  MTG_REQUIRE(g && out, MTG_ERR_ARG, "upsample_bwd: null pointer");
+  const int total = B * Hc * Wc * NC;
+  const int grid = ceil_div(total, 128);
+  if (dtype == LOGITS_F32) upsample_bwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp);
+  else if (dtype == LOGITS_BF16) upsample_bwd_kernel<bf16><<<grid, 128, 0, st>>>(static_cast<const bf16*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp);
+  else if (dtype == LOGITS_F16) upsample_bwd_kernel<__half><<<grid, 128, 0, st>>>(static_cast<const __half*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp);
+  else MTG_REQUIRE(false, MTG_ERR_ARG, "upsample_bwd: unknown dtype %d", dtype);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st) {
+  MTG_REQUIRE(a.NC >= 1 && a.NC <= MAX_NC, MTG_ERR_UNSUPPORTED, "head_bwd: num_classes out of range");
+  HeadBwdP p{a.d_o, a.dh2, a.cbr, a.s, a.low, a.w_high, a.w_low, a.dcbr, a.ds, a.dlow, a.dw_high, a.dw_low, a.db_high, a.db_low,
+             a.Hh, a.Wh, a.Hl, a.Wl, a.IC, a.LC, a.NC};
+  head_bwd_kernel<<<a.B, 256, 0, st>>>(p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_add_bf16(const bf16* a, const bf16* b, bf16* out, size_t n, cudaStream_t st) {
+  MTG_REQUIRE(n % 8 == 0, MTG_ERR_ARG, "add_bf16: n %% 8 != 0");
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  add_bf16_kernel<<<static_cast<unsigned>(blocks ? blocks : 1), 256, 0, st>>>(a, b, out, n / 8);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_fill_f32(float* p, float v, size_t n, cudaStream_t st) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fill_f32_kernel<<<static_cast<unsigned>(blocks ? blocks : 1), 256, 0, st>>>(p, v, n);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_adamw(const void* chunk_table, int n_chunks, float lr, float b1, float b2, float eps, float wd, int step,
+                 const float* inv_scale, const float* found_inf, cudaStream_t st) {
+  MTG_REQUIRE(chunk_table && n_chunks > 0 && step > 0, MTG_ERR_ARG, "adamw: bad arguments");
+  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+  const float bc2s = sqrtf(1.f - powf(b2, static_cast<float>(step)));
+  adamw_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const AdamChunk*>(chunk_table), lr, b1, b2, eps, wd, bc1, bc2s, inv_scale, found_inf);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+}  // namespace mtgseg

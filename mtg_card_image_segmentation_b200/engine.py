@@ -19,6 +19,8 @@ class SegEngine:
         self._packed = None
         self._packed_sig = None
         self._ws = None
+        self._train_ws = None
+        self._stats_dirty = False
         self._desc_cache = {}
 
     def desc(self, h: int, w: int) -> N.NetDesc:
@@ -31,8 +33,9 @@ class SegEngine:
     def pack(self, tensors, device) -> torch.Tensor:
         """(Re)pack the reference-layout state tensors when any of them changed (version counters)."""
         sig = (str(device), tuple((t.data_ptr(), t._version) for t in tensors))
-        if self._packed is not None and sig == self._packed_sig:
+        if self._packed is not None and sig == self._packed_sig and not self._stats_dirty:
             return self._packed
+        self._stats_dirty = False
         n = self.lib.mtgseg_param_count()
         if len(tensors) != n:
             raise RuntimeError(f"expected {n} state_dict entries, got {len(tensors)}")
@@ -91,6 +94,53 @@ class SegEngine:
             return {"logits": logits, "mask": mask, "counts": counts}
         return logits
 
+
+    # -- training ----------------------------------------------------------------------------
+    def _ptr_array(self, tensors):
+        return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+    def train_forward(self, tensors, x, logits_dtype=torch.float32):
+        """model.train(); model(x): batch-statistics BatchNorm, running stats updated in place, activations saved."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"expected a (B,3,H,W) batch, got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        B, _, H, W = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            packed = self.pack(tensors, dev)
+            d = self.desc(H, W)
+            need = self.lib.mtgseg_train_workspace_bytes(C.byref(d), B)
+            if need == 0:
+                raise RuntimeError(f"mtgseg_train_workspace_bytes failed: {self.lib.mtgseg_last_error().decode()}")
+            if self._train_ws is None or self._train_ws.numel() < need or self._train_ws.device != dev:
+                self._train_ws = None
+                self._train_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            logits = torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
+            rc = self.lib.mtgseg_forward_train(C.byref(d), x.data_ptr(), packed.data_ptr(), self._ptr_array(tensors), len(tensors),
+                                               logits.data_ptr(), _TORCH_TO_LOGITS[logits_dtype], self._train_ws.data_ptr(),
+                                               self._train_ws.numel(), B, N.stream_ptr())
+            N.check(rc, "mtgseg_forward_train")
+        self._stats_dirty = True  # running statistics changed under the folded-BN cache
+        return logits, x
+
+    def train_backward(self, tensors, is_param, x, dlogits):
+        """loss.backward(): returns (flat fp32 gradient buffer, list of per-state-entry views or None)."""
+        B, _, H, W = x.shape
+        dev = x.device
+        dlogits = dlogits.contiguous()
+        with torch.cuda.device(dev):
+            sizes = [t.numel() if p else 0 for t, p in zip(tensors, is_param)]
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for t, n in zip(tensors, sizes):
+                views.append(flat[off:off + n].view_as(t) if n else None)
+                off += n
+            d = self.desc(H, W)
+            rc = self.lib.mtgseg_backward(C.byref(d), x.data_ptr(), self._packed.data_ptr(), self._ptr_array(tensors),
+                                          self._ptr_array(views), len(tensors), dlogits.data_ptr(), _TORCH_TO_LOGITS[dlogits.dtype],
+                                          self._train_ws.data_ptr(), self._train_ws.numel(), B, N.stream_ptr())
+            N.check(rc, "mtgseg_backward")
+        return flat, views
 
     def profile(self, tensors, x, logits_dtype=torch.bfloat16):
         """One forward with CUDA events around every kernel launch -> list of dicts (bench.py roofline)."""

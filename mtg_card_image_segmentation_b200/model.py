@@ -137,6 +137,31 @@ class _LRASPP(nn.Module):
         return OrderedDict(out=out)
 
 
+class _TrainStep(torch.autograd.Function):
+    """Whole-network autograd node: forward = mtgseg_forward_train, backward = mtgseg_backward.  The parameters are
+    passed as inputs only so that autograd routes their gradients; the kernels read them through the engine."""
+
+    @staticmethod
+    def forward(ctx, model, x, out_dtype, *params):
+        tensors = model._state_tensors()
+        logits, x32 = model.engine().train_forward(tensors, x, out_dtype)
+        ctx.model, ctx.tensors, ctx.x32 = model, tensors, x32
+        ctx.param_ids = {id(p): i for i, p in enumerate(params)}
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, tensors = ctx.model, ctx.tensors
+        is_param = [id(t) in ctx.param_ids for t in tensors]
+        flat, views = model.engine().train_backward(tensors, is_param, ctx.x32, dlogits)
+        model.last_flat_grad = flat  # one contiguous buffer: a data-parallel driver all-reduces it in one call
+        grads = [None] * len(ctx.param_ids)
+        for t, v in zip(tensors, views):
+            if v is not None:
+                grads[ctx.param_ids[id(t)]] = v
+        return (None, None, None, *grads)
+
+
 class CardSegmentationModel(nn.Module):
     """LR-ASPP / MobileNetV3-Large card segmenter (background 0, card 1) running on hand-written B200 kernels."""
 
@@ -149,6 +174,7 @@ class CardSegmentationModel(nn.Module):
         self.num_classes = num_classes
         self.model = _LRASPP(num_classes, inter_channels=128)
         self._engine = None
+        self.last_flat_grad = None
 
     # -- engine plumbing ---------------------------------------------------------------------
     def engine(self) -> SegEngine:
@@ -168,8 +194,12 @@ class CardSegmentationModel(nn.Module):
                                "CPU fallback. Move the model and the batch to 'cuda'.")
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
         if self.training:
-            raise NotImplementedError("the CUDA training step (batch-statistics BatchNorm + backward) is not built yet; "
-                                      "call model.eval() for inference")
+            params = list(self.parameters())
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                if not all(p.requires_grad for p in params):
+                    raise RuntimeError("the CUDA training step computes all parameter gradients; freezing a subset is not supported")
+                return _TrainStep.apply(self, x, out_dtype, *params)
+            return self.engine().train_forward(self._state_tensors(), x, out_dtype)[0]
         return self.engine().infer(self._state_tensors(), x, logits_dtype=out_dtype)
 
     @torch.no_grad()

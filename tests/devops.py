@@ -55,8 +55,9 @@ def se_mlp(sums, hw, w1, b1, act1, w2=None, b2=None, act2=0):
     B, chunks, Cc = sums.shape
     SQ = w1.shape[0]
     out = torch.empty(B, Cc if w2 is not None else SQ, dtype=torch.float32, device=sums.device)
+    hidden = torch.empty(B, SQ, dtype=torch.float32, device=sums.device) if w2 is not None else None
     N.check(N.load().mtgseg_se_mlp(sums.data_ptr(), chunks, B, Cc, SQ, hw, w1.data_ptr(), N.ptr(b1), act1, N.ptr(w2), N.ptr(b2),
-                                   act2, out.data_ptr(), _s()), "se_mlp")
+                                   act2, out.data_ptr(), N.ptr(hidden), _s()), "se_mlp")
     return out
 
 

@@ -5,7 +5,8 @@ Three levels of evidence, because bf16 STORAGE noise at random-init weights is i
 (the reference's own ``torch.autocast(bfloat16)`` run differs from its fp32 run by as much -- measured in
 ``_autocast_noise`` below and in DESIGN.md §Parity):
   1. CUDA vs ``oracle.forward_bf16_emulated`` (same roundings, fp32 maths): <= 1e-2 max and rel-L2 -- kernel correctness;
-  2. CUDA vs the fp32 oracle / golden logits: <= max(2e-2, 1.25 x the reference's own bf16-autocast noise);
+  2. CUDA vs the fp32 oracle / golden logits: no worse than the bf16 storage format itself, i.e.
+     <= max(2e-2, 1.15 x error(bf16-emulated oracle vs fp32 oracle) + 2e-3); the reference's own autocast noise is printed;
   3. thresholded masks >= 99.9 % identical outside a +-0.02*max|z| margin band; integer counts bit-exact."""
 import pytest
 import torch
@@ -38,9 +39,10 @@ def _check_three_levels(name, z, sd, x, ref):
     emax, el2 = D.report(name + " vs bf16-emulated oracle", z, emu)
     assert emax <= 1e-2 and el2 <= 1e-2
     nmax, nl2 = _autocast_noise(sd, x, ref)
+    smax, sl2 = D.report(name + " bf16-emulated oracle vs fp32 oracle (storage-format noise)", emu, ref)
     fmax, fl2 = D.report(name + " vs fp32 oracle", z, ref)
     print(f"[{name}] reference autocast-bf16 noise vs its fp32: max {nmax:.4f} rel-L2 {nl2:.4f}")
-    assert fmax <= max(2e-2, 1.25 * nmax) and fl2 <= max(2e-2, 1.25 * nl2)
+    assert fmax <= max(2e-2, 1.15 * smax + 2e-3) and fl2 <= max(2e-2, 1.15 * sl2 + 2e-3)
     ok_band, ok_all, band = _mask_agreement(z, ref)
     print(f"[{name}] mask agreement: {ok_band:.5f} outside margin band ({band:.3f} of pixels), {ok_all:.5f} overall")
     assert ok_band >= 0.999
