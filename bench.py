@@ -255,6 +255,47 @@ def run_ours(args):
                 with open(args.layers_out, "w") as f:
                     json.dump({"batch": B, "layers": layers, "families": roofline["families"]}, f, indent=1)
 
+    # ---------------- training step (configs[2]/[3]): fwd + CombinedLoss + bwd (+ grad all-reduce) + AdamW ----------
+    train = None
+    if not args.no_train:
+        from mtg_card_image_segmentation_b200.optim import FusedAdamW
+        TB = args.train_batch
+        tmodel = M.create_model(2, pretrained=False).to(dev).train()
+        opt = FusedAdamW(tmodel.parameters(), lr=1e-3, weight_decay=1e-4)  # train/config.py:28-29
+        crit = M.CombinedLoss(0.5, 0.5)
+        xt, mt = x[:TB].contiguous(), m_host[:TB].to(dev)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            out = tmodel(xt)
+            loss = crit(out, mt)
+            loss.backward()
+            if world > 1:  # data parallel: average the flat gradient buffer (per-replica BatchNorm, like DDP)
+                dist.all_reduce(tmodel.last_flat_grad)
+                tmodel.last_flat_grad.div_(world)
+            opt.step()
+            return loss
+
+        for _ in range(3):
+            train_step()
+        barrier()
+        l0 = lib.mtgseg_launch_count()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tsteps = max(5, args.steps // 2)
+        t0e.record()
+        for _ in range(tsteps):
+            last = train_step()
+        t1e.record()
+        barrier()
+        tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        train = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "value": world * TB * tsteps / (tt.item() * 1e-3),
+                 "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps, "batch_per_gpu": TB, "global_batch": TB * world,
+                 "loss": float(last.item()), "gpu_launches_per_step": int((lib.mtgseg_launch_count() - l0) // tsteps),
+                 "parallelism": f"data parallel x{world}, per-replica BatchNorm, NCCL all-reduce of 16.8 MB fp32 grads after backward"}
+        del tmodel, opt
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -277,7 +318,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "CardSegmentationModel.predict (uint8 mask), pinned host buffers, copy/compute double-buffered"},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -293,6 +334,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step (train/config.py:26)")
     ap.add_argument("--layers-out", default=None, help="write the per-layer profile (JSON) here")
     args = ap.parse_args()
     if args.impl == "reference":

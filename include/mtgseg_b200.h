@@ -158,6 +158,28 @@ int mtgseg_head_mix(const void* cbr, const float* s, const void* low, const floa
 int mtgseg_upsample_out(const float* lowres, void* logits, int logits_dtype, uint8_t* mask, const int64_t* targets,
                         uint64_t* counts4, int B, int Hl, int Wl, int H, int W, int NC, void* stream);
 
+/* ---- per-operator training entry points (unit tests) --------------------------------------------------- */
+/* nn.BatchNorm2d in train mode (+ activation, residual, per-image channel sums) on NHWC bf16 z[B,HW,C];
+ * scratch >= mtgseg_bn_scratch_floats(B,HW,C) floats (+ 2*C for the backward call) */
+size_t mtgseg_bn_scratch_floats(int B, int HW, int C);
+int mtgseg_bn_train_fwd(const void* z, void* y, const void* residual, const float* gamma, const float* beta, float eps,
+                        float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                        float* shift, float* save_mean, float* save_rstd, float* scratch, float* gap, int gap_chunks, int act,
+                        int B, int HW, int C, void* stream);
+/* backward of the above: dz from dy (optionally dy' = dy*se_s[b,c] + se_dmean[b,c]/HW), dgamma, dbeta */
+int mtgseg_bn_train_bwd(const void* z, const void* dy, void* dz, const float* scale, const float* shift, const float* save_mean,
+                        const float* save_rstd, const float* se_s, const float* se_dmean, float* scratch, float* dgamma,
+                        float* dbeta, int act, int B, int HW, int C, void* stream);
+/* weight gradient of a 1x1 (taps=1) or 3x3 pad-1 (taps=9) convolution: dw[N,K,taps] (fp32 OIHW) += dz[M,N]^T x[M,K] */
+int mtgseg_wgrad(const void* dz, const void* x, float* dw, const float* a_scale, int hw, int64_t M, int N, int K, int taps, int H,
+                 int W, void* stream);
+/* depthwise conv backward: dx (if non-NULL) and dw[C,k*k] (fp32, accumulated, if non-NULL) */
+int mtgseg_dw_bwd(const void* dz, const void* x, const void* w, void* dx, float* dw, int B, int H, int W, int C, int k, int stride,
+                  int dil, void* stream);
+int mtgseg_stem_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream);
+/* transpose of the align_corners=False bilinear upsample: g[B,NC,Hf,Wf] -> out fp32 [B,Hc,Wc,NC] */
+int mtgseg_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int Hc, int Wc, int Hf, int Wf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

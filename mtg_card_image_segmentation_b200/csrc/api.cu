@@ -112,6 +112,62 @@ int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float bet
   return launch_adamw(chunk_table, n_chunks, lr, beta1, beta2, eps, weight_decay, step, inv_scale, found_inf, S(stream));
 }
 
+// ---- per-operator training entry points (unit tests) ---------------------------------------------------
+size_t mtgseg_bn_scratch_floats(int B, int HW, int C) { return bn_partial_floats(B, HW, C); }
+
+int mtgseg_bn_train_fwd(const void* z, void* y, const void* residual, const float* gamma, const float* beta, float eps,
+                        float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                        float* shift, float* save_mean, float* save_rstd, float* scratch, float* gap, int gap_chunks, int act,
+                        int B, int HW, int C, void* stream) {
+  BnTrainFwdArgs a;
+  a.z = static_cast<const bf16*>(z); a.y = static_cast<bf16*>(y); a.residual = static_cast<const bf16*>(residual);
+  a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum; a.running_mean = running_mean; a.running_var = running_var;
+  a.num_batches_tracked = reinterpret_cast<long long*>(num_batches_tracked);
+  a.scale = scale; a.shift = shift; a.save_mean = save_mean; a.save_rstd = save_rstd; a.partial = scratch;
+  a.gap = gap; a.gap_chunks = gap_chunks; a.act = act; a.B = B; a.HW = HW; a.C = C;
+  return launch_bn_train_fwd(a, S(stream));
+}
+
+int mtgseg_bn_train_bwd(const void* z, const void* dy, void* dz, const float* scale, const float* shift, const float* save_mean,
+                        const float* save_rstd, const float* se_s, const float* se_dmean, float* scratch, float* dgamma,
+                        float* dbeta, int act, int B, int HW, int C, void* stream) {
+  BnTrainBwdArgs a;
+  a.z = static_cast<const bf16*>(z); a.dy = static_cast<const bf16*>(dy); a.dz = static_cast<bf16*>(dz);
+  a.scale = scale; a.shift = shift; a.save_mean = save_mean; a.save_rstd = save_rstd; a.se_s = se_s; a.se_dmean = se_dmean;
+  a.partial = scratch; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.c1 = scratch + bn_partial_floats(B, HW, C); a.c2 = a.c1 + C;  // scratch holds bn_scratch_floats + 2*C floats
+  a.act = act; a.B = B; a.HW = HW; a.C = C;
+  return launch_bn_train_bwd(a, S(stream));
+}
+
+int mtgseg_wgrad(const void* dz, const void* x, float* dw, const float* a_scale, int hw, int64_t M, int N, int K, int taps, int H,
+                 int W, void* stream) {
+  WgradArgs a;
+  a.dz = static_cast<const bf16*>(dz); a.x = static_cast<const bf16*>(x); a.dw = dw; a.a_scale = a_scale; a.hw = hw;
+  a.M = M; a.N = N; a.K = K; a.taps = taps; a.H = H; a.W = W;
+  return launch_wgrad(a, S(stream));
+}
+
+int mtgseg_dw_bwd(const void* dz, const void* x, const void* w, void* dx, float* dw, int B, int H, int W, int C, int k, int stride,
+                  int dil, void* stream) {
+  DwBwdArgs a;
+  a.dz = static_cast<const bf16*>(dz); a.x = static_cast<const bf16*>(x); a.w = static_cast<const bf16*>(w);
+  a.dx = static_cast<bf16*>(dx); a.dw = dw; a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride; a.dil = dil;
+  int rc = MTG_OK;
+  if (dx) rc = launch_dw_dgrad(a, S(stream));
+  if (rc == MTG_OK && dw) rc = launch_dw_wgrad(a, S(stream));
+  return rc;
+}
+
+int mtgseg_stem_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream) {
+  return launch_stem_wgrad(x, static_cast<const bf16*>(dz), dw, B, H, W, S(stream));
+}
+
+int mtgseg_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int Hc, int Wc, int Hf, int Wf, void* stream) {
+  return launch_upsample_bwd(g, dtype, out, B, NC, Hc, Wc, Hf, Wf, static_cast<long long>(NC) * Hf * Wf,
+                             static_cast<long long>(Hf) * Wf, 1, S(stream));
+}
+
 unsigned long long mtgseg_launch_count(void) { return launch_count(); }
 
 int mtgseg_forward_infer_profiled(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits,

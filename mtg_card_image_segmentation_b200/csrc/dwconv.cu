@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, MINB) dwconv_kernel(const DwP p) {
   }
 }
 
-// MTGSEG_DW_VARIANT=1 selects narrower strips capped at 128 registers (tuning aid; default = wide strips)
+// MTGSEG_DW_VARIANT=1 selects the wide-strip instantiations (tuning aid; the narrow strips are the default)
 int dw_variant() {
   static int v = -1;
   if (v < 0) {
@@ -135,7 +135,7 @@ int dw_variant() {
   }
   return v;
 }
-inline int strip_width(int stride) { return dw_variant() == 1 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
+inline int strip_width(int stride) { return dw_variant() == 0 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
 
 }  // namespace
 
@@ -179,7 +179,7 @@ int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
   p.items_per_chunk = ceil_div(p.items, p.chunks);
   dim3 grid(p.chunks, ceil_div(p.CV, p.CVc), a.B);
   const int key = a.k * 100 + a.stride * 10 + a.dil;
-  if (dw_variant() == 1) {
+  if (dw_variant() == 0) {  // default: narrow strips, <= 128 registers, two CTAs per SM (measured faster)
     switch (key) {
       case 311: dwconv_kernel<3, 1, 1, 4, 2><<<grid, 256, 0, st>>>(p); break;
       case 321: dwconv_kernel<3, 2, 1, 2, 2><<<grid, 256, 0, st>>>(p); break;

