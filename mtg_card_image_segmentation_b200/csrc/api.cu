@@ -242,9 +242,7 @@ int mtgseg_conv3x3(const void* a, const void* w, void* out, int B, int H, int W,
 }
 
 int mtgseg_dwconv_chunks(int H, int W, int C, int k, int stride, int dil, int need_gap) {
-  const int pad = (k - 1) / 2 * dil;
-  const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
-  return dwconv_chunks(Ho, Wo, C, stride, need_gap != 0);
+  return dwconv_chunks(H, W, C, k, stride, dil, need_gap != 0);
 }
 
 int mtgseg_dwconv(const void* in, const void* w, void* out, int B, int H, int W, int C, int k, int stride, int dil,

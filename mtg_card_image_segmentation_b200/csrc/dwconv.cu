@@ -126,7 +126,140 @@ __global__ void __launch_bounds__(256, MINB) dwconv_kernel(const DwP p) {
   }
 }
 
-// MTGSEG_DW_VARIANT=1 selects the wide-strip instantiations (tuning aid; the narrow strips are the default)
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory staged variant (default): a CTA owns CVc channel vectors of a band of output rows of one image.
+// Phase 1 streams the band's input rows (zero padded in x and y, so phase 2 needs no bounds checks) and the
+// k*k weight vectors into shared memory with 16-byte cp.async (many loads in flight, no registers held);
+// phase 2 is the same register-strip arithmetic as above, fed by LDS.128 instead of L1/L2 round trips.
+// Every input byte leaves L2 exactly once per band (+ halo rows).
+// ---------------------------------------------------------------------------------------------------------
+struct DwS {
+  const bf16* in; const bf16* w; bf16* out;
+  const float* scale; const float* shift;
+  float* gap;
+  int act, H, W, C, Ho, Wo, pad, CV, CVc, PL, strips, band, bands, R, Wp;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;  // src-size 0 -> the 16 bytes are zero filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+
+template <int KS, int STRIDE, int DIL, int TW>
+__global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const DwS p) {
+  extern __shared__ uint4 dsm[];
+  __shared__ float red[256 * 8];
+  constexpr int NI = (TW - 1) * STRIDE + (KS - 1) * DIL + 1;
+  uint4* sw = dsm;                      // [KS*KS][CVc]
+  uint4* sx = dsm + KS * KS * p.CVc;    // [R][Wp][CVc]
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z, band = blockIdx.x;
+  const int v0 = blockIdx.y * p.CVc;
+  const int nv = min(p.CVc, p.CV - v0);  // vectors of this group that exist
+  const int oy0 = band * p.band, oy1 = min(p.Ho, oy0 + p.band);
+  const int iy_base = oy0 * STRIDE - p.pad;
+  const int rows = (oy1 - oy0 - 1) * STRIDE + (KS - 1) * DIL + 1;
+  // ---- phase 1: stage ----
+  const bf16* in_n = p.in + static_cast<size_t>(n) * p.H * p.W * p.C + v0 * 8;
+  const int per_row = p.Wp * p.CVc;
+  for (int i = tid; i < rows * per_row; i += 256) {
+    const int r = i / per_row, rem = i - r * per_row;
+    const int xp = rem / p.CVc, vl = rem - xp * p.CVc;
+    const int iy = iy_base + r, ix = xp - p.pad;
+    const bool ok = vl < nv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    const bf16* src = ok ? in_n + (static_cast<size_t>(iy) * p.W + ix) * p.C + vl * 8 : p.in;
+    cp_async16(sx + i, src, ok);
+  }
+  for (int i = tid; i < KS * KS * p.CVc; i += 256) {
+    const int t = i / p.CVc, vl = i - t * p.CVc;
+    const bool ok = vl < nv;
+    cp_async16(sw + i, ok ? p.w + t * p.C + (v0 + vl) * 8 : p.w, ok);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- phase 2: compute ----
+  const int vl = tid % p.CVc, pl = tid / p.CVc;
+  const bool active = pl < p.PL && vl < nv;
+  const int c0 = (v0 + (active ? vl : 0)) * 8;
+  float acc_gap[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc_gap[j] = 0.f;
+  if (active) {
+    float sc[8], sh[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), b = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), d = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+      sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+      sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+    }
+    bf16* out_n = p.out + static_cast<size_t>(n) * p.Ho * p.Wo * p.C + c0;
+    const int items = (oy1 - oy0) * p.strips;
+    for (int item = pl; item < items; item += p.PL) {
+      const int ry = item / p.strips, sxi = item - ry * p.strips;
+      const int ox0 = sxi * TW;
+      float acc[TW][8];
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll 1
+      for (int ky = 0; ky < KS; ++ky) {
+        float wv[KS][8];
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) unpack8(sw[(ky * KS + kx) * p.CVc + vl], wv[kx]);
+        const uint4* row = sx + (static_cast<size_t>(ry * STRIDE + ky * DIL) * p.Wp + ox0 * STRIDE) * p.CVc + vl;
+#pragma unroll
+        for (int xi = 0; xi < NI; ++xi) {
+          float xf[8];
+          unpack8(row[xi * p.CVc], xf);
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const int t = xi - kx * DIL;  // compile-time after unrolling
+            if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[t / STRIDE][j] = fmaf(xf[j], wv[kx][j], acc[t / STRIDE][j]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < TW; ++t) {
+        if (ox0 + t < p.Wo) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = apply_act(fmaf(acc[t][j], sc[j], sh[j]), p.act);
+          const uint4 packed = pack8(o);
+          *reinterpret_cast<uint4*>(out_n + (static_cast<size_t>(oy0 + ry) * p.Wo + ox0 + t) * p.C) = packed;
+          if (p.gap) {
+            float rf[8];
+            unpack8(packed, rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc_gap[j] += rf[j];
+          }
+        }
+      }
+    }
+  }
+  if (p.gap) {
+    const int cw = p.CVc * 8;
+    if (pl < p.PL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(pl * p.CVc + vl) * 8 + j] = active ? acc_gap[j] : 0.f;
+    }
+    __syncthreads();
+    for (int cl = tid; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < p.C) {
+        float s = 0.f;
+        for (int l = 0; l < p.PL; ++l) s += red[l * cw + cl];
+        p.gap[(static_cast<size_t>(n) * p.bands + band) * p.C + c] = s;
+      }
+    }
+  }
+}
+
+// MTGSEG_DW_VARIANT: 0 (default) shared-memory staged kernel; 2 legacy direct kernel, narrow strips; 1 legacy, wide strips
 int dw_variant() {
   static int v = -1;
   if (v < 0) {
@@ -135,7 +268,7 @@ int dw_variant() {
   }
   return v;
 }
-inline int strip_width(int stride) { return dw_variant() == 0 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
+inline int strip_width(int stride) { return dw_variant() != 1 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
 
 }  // namespace
 
@@ -150,20 +283,81 @@ int group_vectors(int CV) {
   return best;
 }
 
-int dwconv_chunks(int Ho, int Wo, int C, int stride, bool need_gap) {
-  const int CV = C / 8;
-  const int PL = 256 / group_vectors(CV);
-  const int items = Ho * ceil_div(Wo, strip_width(stride));
-  const int per_thread = need_gap ? 4 : 2;  // strips per thread per CTA
-  int chunks = ceil_div(items, PL * per_thread);
-  if (need_gap && chunks > 16) chunks = 16;
-  if (chunks < 1) chunks = 1;
-  return chunks;
+struct DwPlan { int pad, Ho, Wo, CV, CVc, PL, TW, strips, band, bands, R, Wp; size_t smem; bool ok; };
+
+DwPlan dw_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
+  DwPlan q{};
+  q.pad = (k - 1) / 2 * dil;
+  q.Ho = (H + 2 * q.pad - dil * (k - 1) - 1) / stride + 1;
+  q.Wo = (W + 2 * q.pad - dil * (k - 1) - 1) / stride + 1;
+  q.CV = C / 8; q.CVc = group_vectors(q.CV); q.PL = 256 / q.CVc;
+  q.TW = strip_width(stride);
+  q.strips = ceil_div(q.Wo, q.TW);
+  // padded row: every strip (including the ragged last one) may read NI inputs from its first column
+  const int NI = (q.TW - 1) * stride + (k - 1) * dil + 1;
+  q.Wp = (q.strips - 1) * q.TW * stride + NI;
+  if (q.Wp < W + 2 * q.pad) q.Wp = W + 2 * q.pad;
+  const size_t budget = 108 * 1024;
+  const size_t wbytes = static_cast<size_t>(k) * k * q.CVc * 16;
+  auto bytes = [&](int band) { return (static_cast<size_t>((band - 1) * stride + (k - 1) * dil + 1) * q.Wp * q.CVc) * 16 + wbytes; };
+  q.ok = bytes(1) <= budget;
+  int band = 1;
+  while (band < q.Ho && bytes(band + 1) <= budget) ++band;
+  // keep at least ~2 strips per thread-lane of work and, for the SE pool, at most 16 partials per image
+  int bands = ceil_div(q.Ho, band);
+  if (need_gap && bands > 16) q.ok = false;
+  band = ceil_div(q.Ho, bands);  // even bands
+  q.band = band; q.bands = ceil_div(q.Ho, band);
+  q.R = (band - 1) * stride + (k - 1) * dil + 1;
+  q.smem = bytes(band);
+  return q;
+}
+
+int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
+  if (dw_variant() == 2) {  // legacy direct-from-L1 kernel
+    const int pad = (k - 1) / 2 * dil;
+    const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    const int PL = 256 / group_vectors(C / 8);
+    const int items = Ho * ceil_div(Wo, strip_width(stride));
+    int chunks = ceil_div(items, PL * (need_gap ? 4 : 2));
+    if (need_gap && chunks > 16) chunks = 16;
+    return chunks < 1 ? 1 : chunks;
+  }
+  return dw_plan(H, W, C, k, stride, dil, need_gap).bands;
+}
+
+template <int KS, int STRIDE, int DIL, int TW>
+int launch_smem(const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MTG_CUDA(cudaFuncSetAttribute(dwconv_smem_kernel<KS, STRIDE, DIL, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    configured = true;
+  }
+  dwconv_smem_kernel<KS, STRIDE, DIL, TW><<<grid, 256, smem, st>>>(p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
 }
 
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.in && a.w && a.out && a.scale && a.shift, MTG_ERR_ARG, "dwconv: null pointer");
   MTG_REQUIRE(a.C % 8 == 0 && a.C >= 8 && a.C <= 2048, MTG_ERR_UNSUPPORTED, "dwconv: C=%d must be a multiple of 8 in [8,2048]", a.C);
+  if (dw_variant() != 2) {
+    const DwPlan q = dw_plan(a.H, a.W, a.C, a.k, a.stride, a.dil, a.gap_partial != nullptr);
+    MTG_REQUIRE(q.ok, MTG_ERR_UNSUPPORTED, "dwconv: feature map %dx%d (C=%d, k=%d) does not fit the shared-memory tiling", a.H, a.W, a.C, a.k);
+    MTG_REQUIRE(!a.gap_partial || a.chunks == q.bands, MTG_ERR_ARG, "dwconv: gap_partial must have mtgseg_dwconv_chunks() = %d chunks, got %d", q.bands, a.chunks);
+    DwS s{a.in, a.w, a.out, a.scale, a.shift, a.gap_partial, a.act, a.H, a.W, a.C, q.Ho, q.Wo, q.pad, q.CV, q.CVc, q.PL, q.strips,
+          q.band, q.bands, q.R, q.Wp};
+    dim3 grid(q.bands, ceil_div(q.CV, q.CVc), a.B);
+    switch (a.k * 100 + a.stride * 10 + a.dil) {
+      case 311: return launch_smem<3, 1, 1, 4>(s, grid, q.smem, st);
+      case 321: return launch_smem<3, 2, 1, 2>(s, grid, q.smem, st);
+      case 511: return launch_smem<5, 1, 1, 4>(s, grid, q.smem, st);
+      case 521: return launch_smem<5, 2, 1, 2>(s, grid, q.smem, st);
+      case 512: return launch_smem<5, 1, 2, 4>(s, grid, q.smem, st);
+      default:
+        MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: (k=%d, stride=%d, dilation=%d) is not one of the MobileNetV3 shapes", a.k, a.stride, a.dil);
+    }
+  }
   DwP p{};
   p.in = a.in; p.w = a.w; p.out = a.out; p.scale = a.scale; p.shift = a.shift; p.gap = a.gap_partial; p.act = a.act;
   p.H = a.H; p.W = a.W; p.C = a.C;
@@ -179,7 +373,7 @@ int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
   p.items_per_chunk = ceil_div(p.items, p.chunks);
   dim3 grid(p.chunks, ceil_div(p.CV, p.CVc), a.B);
   const int key = a.k * 100 + a.stride * 10 + a.dil;
-  if (dw_variant() == 0) {  // default: narrow strips, <= 128 registers, two CTAs per SM (measured faster)
+  if (dw_variant() != 1) {  // narrow strips, <= 128 registers, two CTAs per SM
     switch (key) {
       case 311: dwconv_kernel<3, 1, 1, 4, 2><<<grid, 256, 0, st>>>(p); break;
       case 321: dwconv_kernel<3, 2, 1, 2, 2><<<grid, 256, 0, st>>>(p); break;

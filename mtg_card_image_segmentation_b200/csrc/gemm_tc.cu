@@ -9,9 +9,10 @@
 // * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with both operands K-major in 128B-swizzled shared
 //   memory; accumulators live in TMEM, double buffered so the epilogue of tile i overlaps the loads and
 //   MMAs of tile i+1.  Persistent CTAs walk the tile list round-robin.
-// * warp roles: w0 = TMA producer, w1 = MMA issuer (+ TMEM owner), w2..5 = epilogue (one TMEM lane
-//   quarter each), w6..9 (only with kAScale) = squeeze-excite prologue that rescales the A tile in
-//   shared memory per (image, channel) before the MMA reads it.
+// * warp roles: w0 = TMA producer, w1 = MMA issuer (+ TMEM owner), w2..9 = epilogue (4 TMEM lane quarters x
+//   2 column halves: the epilogue is instruction-latency bound, so it gets two warps per scheduler),
+//   w10..13 (only with kAScale) = squeeze-excite prologue that rescales the A tile in shared memory per
+//   (image, channel) before the MMA reads it.
 // * epilogue: TMEM -> registers -> folded BN / activation / residual -> bf16 -> 128B-swizzled staging slab
 //   in shared memory -> ONE TMA store per 64-channel slab (double buffered); the residual tile arrives by
 //   TMA as well, so the epilogue warps issue no per-thread global memory instruction at all and the
@@ -58,7 +59,7 @@ struct GemmKParams {
 };
 
 template <bool kConv3x3, bool kAScale>
-__global__ void __launch_bounds__(kAScale ? 320 : 192, 2)
+__global__ void __launch_bounds__(kAScale ? 448 : 320, kAScale ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,7 +92,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull[b], 1);
-      ptx::mbar_init(&tempty[b], 128);
+      ptx::mbar_init(&tempty[b], 256);
     }
     ptx::mbar_init(resbar, 1);
     ptx::fence_mbar_init();
@@ -167,11 +168,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
       }
     }
-  } else if (warp < 6) {
-    // =============================== epilogue ===============================
+  } else if (warp < 10) {
+    // =============================== epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) ===============================
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which 32 of the 64 slab columns this warp converts
     const int r = q * 32 + lane;             // accumulator row of this thread
-    const int et = threadIdx.x - 64;         // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
     const bool leader = et == 0;
     const int slabs = (p.BN + 63) >> 6;
     uint32_t tc = 0, store_no = 0;
@@ -192,7 +194,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
         cur_ntile = n_tile;
-        for (int c = et; c < p.BN; c += 128) {
+        for (int c = et; c < p.BN; c += 256) {
           const int n = n_tile * p.BN + c;
           sScale[c] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.f;
           sShift[c] = (p.shift && n < p.N) ? __ldg(p.shift + n) : 0.f;
@@ -206,43 +208,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* sbuf = sOut + (store_no & 1) * SLAB_BYTES;
         // the TMA store that used this buffer two slabs ago must have finished reading it
         if (leader) ptx::bulk_wait_read<OUT_BUFS - 1>();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int cols = min(64, p.BN - sl * 64);  // multiple of 16
         uint8_t* srow = sbuf + r * 128;
         const uint8_t* rrow = sRes + sl * SLAB_BYTES + r * 128;
+        if (half * 32 < cols) {  // this warp's 32 accumulator columns: one TMEM round trip
+          uint32_t v[2][16];
+          ptx::tmem_ld16(taddr + sl * 64 + half * 32, v[0]);
+          if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * 64 + half * 32 + 16, v[1]);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {  // 32 accumulator columns per TMEM round trip
-          if (half * 32 < cols) {
-            uint32_t v[2][16];
-            ptx::tmem_ld16(taddr + sl * 64 + half * 32, v[0]);
-            if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * 64 + half * 32 + 16, v[1]);
-            ptx::tmem_ld_wait();
+          for (int cc = 0; cc < 2; ++cc) {
+            if (half * 32 + cc * 16 < cols) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              if (half * 32 + cc * 16 < cols) {
+              for (int h = 0; h < 2; ++h) {
+                const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the 128-byte slab row
+                const int c = sl * 64 + chunk * 8;             // column inside the N tile
+                const int phys = (chunk ^ (r & 7)) * 16;       // 128B swizzle: chunk index XOR (row % 8)
+                const float4 s0 = *reinterpret_cast<const float4*>(sScale + c), s1 = *reinterpret_cast<const float4*>(sScale + c + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(sShift + c), h1 = *reinterpret_cast<const float4*>(sShift + c + 4);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                float f[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the 128-byte slab row
-                  const int c = sl * 64 + chunk * 8;             // column inside the N tile
-                  const int phys = (chunk ^ (r & 7)) * 16;       // 128B swizzle: chunk index XOR (row % 8)
-                  float f[8];
+                for (int e = 0; e < 8; ++e) f[e] = apply_act(fmaf(__uint_as_float(v[cc][h * 8 + e]), sc[e], sh[e]), p.act);
+                if (p.res_slabs) {
+                  float rf[8];
+                  unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    f[e] = apply_act(fmaf(__uint_as_float(v[cc][h * 8 + e]), sScale[c + e], sShift[c + e]), p.act);
-                  if (p.res_slabs) {
-                    float rf[8];
-                    unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] += rf[e];
-                  }
-                  *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
+                  for (int e = 0; e < 8; ++e) f[e] += rf[e];
                 }
+                *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
               }
             }
           }
         }
         ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader) {
           const int c0 = n_tile * p.BN + sl * 64;
           if (kConv3x3) ptx::tma_store_4d(&tmO, sbuf, c0, oc1, oc2, oc3);
@@ -256,7 +258,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (leader) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
   } else if (kAScale) {
     // =============================== squeeze-excite prologue on the A tile ===============================
-    const int t = threadIdx.x - 192;
+    const int t = threadIdx.x - 320;
     const int chunk = t & 7;  // physical 16-byte chunk inside the 128-byte row
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -359,7 +361,7 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     MTG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<C3, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int threads = AS ? 320 : 192;
+  const int threads = AS ? 448 : 320;
   // co-resident CTAs per SM: what registers + shared memory allow, capped so that all TMEM allocations fit
   int per_sm = 1;
   MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_gemm_kernel<C3, AS>, threads, need));

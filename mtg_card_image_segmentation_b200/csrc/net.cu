@@ -211,7 +211,7 @@ int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes,
     const int stride = c.dil > 1 ? 1 : c.stride;
     const int Ho = conv_out(H, c.k, stride, c.dil), Wo = conv_out(W, c.k, stride, c.dil);
     bf16* dwo = act_buf(static_cast<size_t>(B) * Ho * Wo * c.cexp);
-    const int chunks = dwconv_chunks(Ho, Wo, c.cexp, stride, c.se);
+    const int chunks = dwconv_chunks(H, W, c.cexp, c.k, stride, c.dil, c.se);
     float* gap = c.se ? f32_buf(static_cast<size_t>(B) * chunks * c.cexp) : nullptr;
     float* sescale = c.se ? f32_buf(static_cast<size_t>(B) * c.cexp) : nullptr;
     float* sehid = c.se ? f32_buf(static_cast<size_t>(B) * b.sq) : nullptr;

@@ -196,7 +196,7 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
       DwConvArgs a;
       a.in = e; a.w = c.wb(b.dw.w_off); a.out = K.dw.z; a.scale = T.ones; a.shift = T.zeros; a.act = ACT_NONE;
       a.B = B; a.H = K.Hin; a.W = K.Win; a.C = cf.cexp; a.k = cf.k; a.stride = stride; a.dil = cf.dil;
-      a.gap_partial = nullptr; a.chunks = dwconv_chunks(K.dw.H, K.dw.W, cf.cexp, stride, false);
+      a.gap_partial = nullptr; a.chunks = dwconv_chunks(K.Hin, K.Win, cf.cexp, cf.k, stride, cf.dil, false);
       RC(launch_dwconv(a, st));
       RC(bn_fwd(c, b.dw, K.dw, cf.act, nullptr, cf.se ? K.gap : nullptr, K.gap_chunks, mom_bb));
     }

@@ -34,7 +34,7 @@ struct DwConvArgs {
   float* gap_partial = nullptr;  // optional [B][chunks][C] per-chunk channel sums of the output
   int chunks = 1;                // pixel chunks per image (grid.x); see dwconv_chunks()
 };
-int dwconv_chunks(int Ho, int Wo, int C, int stride, bool need_gap);
+int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap);
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st);
 
 struct StemArgs {
