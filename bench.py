@@ -259,6 +259,7 @@ def run_ours(args):
     train = None
     if not args.no_train:
         from mtg_card_image_segmentation_b200.optim import FusedAdamW
+        from mtg_card_image_segmentation_b200.parallel import average_gradients
         TB = args.train_batch
         tmodel = M.create_model(2, pretrained=False).to(dev).train()
         opt = FusedAdamW(tmodel.parameters(), lr=1e-3, weight_decay=1e-4)  # train/config.py:28-29
@@ -270,9 +271,7 @@ def run_ours(args):
             out = tmodel(xt)
             loss = crit(out, mt)
             loss.backward()
-            if world > 1:  # data parallel: average the flat gradient buffer (per-replica BatchNorm, like DDP)
-                dist.all_reduce(tmodel.last_flat_grad)
-                tmodel.last_flat_grad.div_(world)
+            average_gradients(tmodel.last_flat_grad)  # data parallel: one all-reduce of the flat gradient buffer
             opt.step()
             return loss
 

@@ -103,15 +103,25 @@ struct BnFinP {
   float* scale; float* shift; float* save_mean; float* save_rstd;
   int C;
 };
-__global__ void bn_finalize_kernel(const BnFinP p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+// one warp per channel: lanes stride over the (image, chunk) partial slots, fp64 shuffle reduction (fixed order)
+__device__ __forceinline__ void warp_sum2(double& a, double& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinP p) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c == 0 && lane == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
   if (c >= p.C) return;
   double s = 0.0, ss = 0.0;
-  for (int k = 0; k < p.slots; ++k) {
+  for (int k = lane; k < p.slots; k += 32) {
     s += p.partial[(static_cast<size_t>(k) * 2) * p.C + c];
     ss += p.partial[(static_cast<size_t>(k) * 2 + 1) * p.C + c];
   }
+  warp_sum2(s, ss);
+  if (lane != 0) return;
   const double mean = s / p.count;
   double var = ss / p.count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -246,15 +256,18 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g
 }
 
 // dbeta = sum dyh ; dgamma = sum dyh*xhat ; c1 = dbeta/count ; c2 = dgamma/count
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int slots, double count, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int slots, double count,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              float* __restrict__ c1, float* __restrict__ c2, int C) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, sx = 0.0;
-  for (int k = 0; k < slots; ++k) {
+  for (int k = lane; k < slots; k += 32) {
     s += partial[(static_cast<size_t>(k) * 2) * C + c];
     sx += partial[(static_cast<size_t>(k) * 2 + 1) * C + c];
   }
+  warp_sum2(s, sx);
+  if (lane != 0) return;
   dbeta[c] = static_cast<float>(s);
   dgamma[c] = static_cast<float>(sx);
   c1[c] = static_cast<float>(s / count);
@@ -291,7 +304,7 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
   MTG_LAUNCH_CHECK();
   BnFinP f{a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
            a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd, a.C};
-  bn_finalize_kernel<<<ceil_div(a.C, 128), 128, 0, st>>>(f);
+  bn_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(f);
   MTG_LAUNCH_CHECK();
   Geo ga = g;
   if (a.gap) {  // the SE pool wants few partials per image
@@ -313,7 +326,7 @@ int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st) {
            a.c1, a.c2, a.partial, a.dz};
   bn_bwd_kernel<false><<<grid, 256, 0, st>>>(p, g);
   MTG_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(a.C, 128), 128, 0, st>>>(a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.dgamma,
+  bn_bwd_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.dgamma,
                                                              a.dbeta, a.c1, a.c2, a.C);
   MTG_LAUNCH_CHECK();
   bn_bwd_kernel<true><<<grid, 256, 0, st>>>(p, g);

@@ -33,9 +33,7 @@ namespace mtgseg {
 namespace {
 
 constexpr int BM = 128;           // UMMA M
-constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
-constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int BAR_BYTES = 256;               // mbarriers + TMEM slot
 constexpr int SLAB_BYTES = BM * 128;         // one [128 rows][64 bf16] swizzled slab
 constexpr int OUT_BUFS = 2;                  // double-buffered output staging
@@ -46,6 +44,8 @@ struct GemmKParams {
   int BN, n_tiles, m_tiles;
   int num_kb, kb_per_tap, ksteps_last;
   int stages, tmem_cols, a_bytes;  // a_bytes: bytes one A TMA box delivers
+  int kbox;                        // K elements per stage: 64 / 32 / 16 <-> 128B / 64B / 32B swizzled rows
+  uint32_t desc_hi;                // upper half of the smem matrix descriptors (SBO, version, swizzle mode)
   const float* scale;
   const float* shift;
   int act;
@@ -65,10 +65,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
+  const int BK = p.kbox;
+  const int A_STAGE_BYTES = BM * BK * 2;
   const int b_stage_bytes = p.BN * BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * A_STAGE_BYTES;
-  uint8_t* sOut = sB + S * b_stage_bytes;              // OUT_BUFS slabs (1024-aligned: BN % 8 == 0)
+  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + S * b_stage_bytes) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
   uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // res_slabs slabs
   float* sScale = reinterpret_cast<float*>(sRes + p.res_slabs * SLAB_BYTES);
   float* sShift = sScale + 256;
@@ -159,8 +161,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tc_fence_after();
           const int kc = kb % p.kb_per_tap;
           const int ksteps = (kc == p.kb_per_tap - 1) ? p.ksteps_last : (BK / 16);
-          const uint64_t adesc = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sA + s * A_STAGE_BYTES));
-          const uint64_t bdesc = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sB + s * b_stage_bytes));
+          const uint64_t adesc = ptx::umma_desc_kmajor(ptx::smem_u32(sA + s * A_STAGE_BYTES), p.desc_hi);
+          const uint64_t bdesc = ptx::umma_desc_kmajor(ptx::smem_u32(sB + s * b_stage_bytes), p.desc_hi);
           for (int k = 0; k < ksteps; ++k)  // +32 B along K inside the swizzle row == +2 in the address field
             ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
@@ -268,22 +270,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t ph = (it / S) & 1;
         ptx::mbar_wait(&full[s], ph);
         uint8_t* base = sA + s * A_STAGE_BYTES;
-#pragma unroll 4
-        for (int j = 0; j < 8; ++j) {
-          const int row = (t >> 3) + 16 * j;
-          const long long m = static_cast<long long>(m_tile) * BM + row;
-          const int k = kb * BK + ((chunk ^ (row & 7)) << 3);  // undo the 128B swizzle: logical channel of this chunk
-          if (m < p.M && k < p.K) {
-            const int img = static_cast<int>(m / p.hw);
-            const float* sp = p.a_scale + static_cast<size_t>(img) * p.K + k;
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
-            uint4* ptr = reinterpret_cast<uint4*>(base + row * 128 + chunk * 16);
-            float f[8];
-            unpack8(*ptr, f);
-            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-            *ptr = pack8(f);
+        // this thread's 16-byte chunk holds the same 8 logical channels in every row it touches (rows differ by 16,
+        // the swizzle only looks at row % 8), and a 128-row tile spans at most two images when hw >= 128: fetch the
+        // (at most two) gate vectors once per stage, then the row loop is pure shared-memory work
+        const int k = kb * BK + ((chunk ^ ((t >> 3) & 7)) << 3);
+        const long long m0 = static_cast<long long>(m_tile) * BM;
+        const int img0 = static_cast<int>(m0 / p.hw);
+        const long long split = static_cast<long long>(img0 + 1) * p.hw;  // first row index of the next image
+        float sa[8], sb[8];
+        if (k < p.K && p.hw < BM) {  // tiny feature maps (tests): a tile may span many images, fetch the gate per row
+          for (int j = 0; j < 8; ++j) {
+            const int row = (t >> 3) + 16 * j;
+            const long long m = m0 + row;
+            if (m < p.M) {
+              const float* sp = p.a_scale + static_cast<size_t>(m / p.hw) * p.K + k;
+              uint4* ptr = reinterpret_cast<uint4*>(base + row * 128 + chunk * 16);
+              float f[8];
+              unpack8(*ptr, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] *= __ldg(sp + e);
+              *ptr = pack8(f);
+            }
+          }
+        } else if (k < p.K) {
+          const float* sp = p.a_scale + static_cast<size_t>(img0) * p.K + k;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(sp)), a1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+          sa[0] = a0.x; sa[1] = a0.y; sa[2] = a0.z; sa[3] = a0.w; sa[4] = a1.x; sa[5] = a1.y; sa[6] = a1.z; sa[7] = a1.w;
+          const bool two = split < m0 + BM && split < p.M;
+          const float* sq = two ? sp + p.K : sp;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(sq)), b1 = __ldg(reinterpret_cast<const float4*>(sq + 4));
+          sb[0] = b0.x; sb[1] = b0.y; sb[2] = b0.z; sb[3] = b0.w; sb[4] = b1.x; sb[5] = b1.y; sb[6] = b1.z; sb[7] = b1.w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = (t >> 3) + 16 * j;
+            const long long m = m0 + row;
+            if (m < p.M) {
+              uint4* ptr = reinterpret_cast<uint4*>(base + row * 128 + chunk * 16);
+              float f[8];
+              unpack8(*ptr, f);
+              const bool second = m >= split;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] *= second ? sb[e] : sa[e];
+              *ptr = pack8(f);
+            }
           }
         }
         ptx::fence_proxy_async_smem();
@@ -322,7 +351,7 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes for dims 1..
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, int kbox = 64) {
   EncodeTiledFn fn = get_encode_fn();
   MTG_REQUIRE(fn != nullptr, MTG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -335,7 +364,9 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MTG_REQUIRE(r == CUDA_SUCCESS, MTG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu)",
               static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]));
@@ -407,6 +438,16 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     kp.BN = best;
     kp.n_tiles = ceil_div(g.N, best);
   }
+  // narrow layers (K <= 32) use narrower swizzled rows so that a stage is 6-12 KB instead of 24 KB: the ring can then
+  // be deep enough to cover HBM latency (these layers move 4 KB of A per tile)
+  const int BK = (!g.conv3x3 && !g.a_scale && g.K <= 16) ? 16 : ((!g.conv3x3 && !g.a_scale && g.K <= 32) ? 32 : 64);
+  const int A_STAGE_BYTES = BM * BK * 2;
+  kp.kbox = BK;
+  {
+    const uint32_t sbo = static_cast<uint32_t>(8 * BK * 2) >> 4;             // 8 rows of the swizzle atom
+    const uint32_t layout = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);            // SWIZZLE_128B / 64B / 32B
+    kp.desc_hi = sbo | (1u << 14) | (layout << 29);                          // bits 32-45 SBO, 46-48 version 1, 61-63 layout
+  }
   kp.kb_per_tap = ceil_div(g.K, BK);
   kp.num_kb = kp.kb_per_tap * (g.conv3x3 ? 9 : 1);
   kp.ksteps_last = ceil_div(g.K - (kp.kb_per_tap - 1) * BK, 16);
@@ -438,12 +479,12 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     kp.a_bytes = kp.NB * kp.HB * g.W * BK * 2;
     const uint64_t dims[4] = {(uint64_t)g.K, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
     const uint64_t strides[3] = {(uint64_t)g.K * 2, (uint64_t)g.W * g.K * 2, (uint64_t)g.H * g.W * g.K * 2};
-    const uint32_t box[4] = {BK, (uint32_t)g.W, (uint32_t)kp.HB, (uint32_t)kp.NB};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)g.W, (uint32_t)kp.HB, (uint32_t)kp.NB};
     int rc = make_map(&tmA, g.a, 4, dims, strides, box);
     if (rc) return rc;
     const uint64_t wd[2] = {(uint64_t)g.K * 9, (uint64_t)g.N};
     const uint64_t ws[1] = {(uint64_t)g.K * 9 * 2};
-    const uint32_t wb[2] = {BK, (uint32_t)kp.BN};
+    const uint32_t wb[2] = {(uint32_t)BK, (uint32_t)kp.BN};
     rc = make_map(&tmB, g.w, 2, wd, ws, wb);
     if (rc) return rc;
     const uint64_t od[4] = {(uint64_t)g.N, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
@@ -457,13 +498,13 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     kp.a_bytes = A_STAGE_BYTES;
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
     const uint64_t strides[1] = {(uint64_t)g.K * 2};
-    const uint32_t box[2] = {BK, BM};
-    int rc = make_map(&tmA, g.a, 2, dims, strides, box);
+    const uint32_t box[2] = {(uint32_t)BK, BM};
+    int rc = make_map(&tmA, g.a, 2, dims, strides, box, BK);
     if (rc) return rc;
     const uint64_t wd[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t ws[1] = {(uint64_t)g.K * 2};
-    const uint32_t wb[2] = {BK, (uint32_t)kp.BN};
-    rc = make_map(&tmB, g.w, 2, wd, ws, wb);
+    const uint32_t wb[2] = {(uint32_t)BK, (uint32_t)kp.BN};
+    rc = make_map(&tmB, g.w, 2, wd, ws, wb, BK);
     if (rc) return rc;
     const uint64_t od[2] = {(uint64_t)g.N, (uint64_t)g.M};
     const uint64_t os[1] = {(uint64_t)g.N * 2};
@@ -478,8 +519,10 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   }
 
   const int stage_bytes = A_STAGE_BYTES + kp.BN * BK * 2;
-  const size_t fixed = 1024 /*align*/ + OUT_BUFS * SLAB_BYTES + static_cast<size_t>(kp.res_slabs) * SLAB_BYTES + SS_BYTES + BAR_BYTES;
-  int stages = kp.num_kb >= 8 ? 6 : (kp.num_kb >= 2 ? 4 : 2);  // one k-block per tile: 2 stages already prefetch the next tile
+  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * SLAB_BYTES + static_cast<size_t>(kp.res_slabs) * SLAB_BYTES + SS_BYTES + BAR_BYTES;
+  // ring depth: enough stages that two co-resident CTAs keep >= ~64 KB of loads in flight per SM (HBM latency x bandwidth)
+  int stages = kp.num_kb >= 8 ? 6 : 4;
+  if (stage_bytes <= 12 * 1024) stages = 8;
   while (stages > 2 && stages * static_cast<size_t>(stage_bytes) + fixed > 227 * 1024) --stages;
   // prefer two co-resident CTAs (8 epilogue warps per SM) over a deeper ring when that is what it costs
   if (stages > 3 && 2 * (3 * static_cast<size_t>(stage_bytes) + fixed) <= 227 * 1024 &&

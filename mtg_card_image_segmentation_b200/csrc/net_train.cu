@@ -261,6 +261,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   bf16* dcbr = T.g[0];
   bf16* dlow = T.g[4];  // kept until block 4's output gradient is formed
   float* ds_head = T.pooled[0];
+  RC(launch_fill_f32(ds_head, 0.f, static_cast<size_t>(B) * ic, st));
   {
     HeadBwdArgs a;
     a.d_o = T.d_o; a.dh2 = T.dh2; a.cbr = T.cbr.y; a.s = T.hscale; a.low = T.blk[3].project.y;

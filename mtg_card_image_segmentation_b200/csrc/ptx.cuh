@@ -155,6 +155,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// Generic K-major descriptor: `hi` carries SBO (bits 32-45), version (46-48) and the swizzle mode (61-63) for
+// 128B / 64B / 32B swizzled rows; the low half is the 16-byte-granular start address (+ ignored LBO = 1).
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t hi) {
+  return static_cast<uint64_t>(((smem_addr & 0x3FFFF) >> 4) | (1u << 16)) | (static_cast<uint64_t>(hi) << 32);
+}
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, shape M x N.
 __device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

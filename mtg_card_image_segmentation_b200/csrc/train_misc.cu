@@ -62,52 +62,65 @@ struct SeBwdP {
   float* dpre2; float* dpre1; float* dmean;
   int C, SQ, single;                 // single: s = sigmoid(W1 mean), C = pooled channels, SQ = outputs
 };
-__global__ void __launch_bounds__(256) se_bwd_kernel(const SeBwdP p) {
+// out[o] = sum_r w[r * ldr + o * ldo] * x[r], o < O, r < R : threads are (o, group) pairs, groups split the
+// reduction range, partial sums meet in shared memory (fixed order)
+__device__ __forceinline__ void grouped_matvec(const float* __restrict__ w, int ldr, int ldo, const float* x, int R, int O,
+                                               float* scratch, float* out_smem) {
+  const int Op = (O + 31) & ~31;
+  const int G = max(1, static_cast<int>(blockDim.x) / Op);
+  const int o = threadIdx.x % Op, grp = threadIdx.x / Op;
+  float a = 0.f;
+  if (o < O && grp < G)
+    for (int r = grp; r < R; r += G) a = fmaf(w[static_cast<size_t>(r) * ldr + static_cast<size_t>(o) * ldo], x[r], a);
+  if (grp < G) scratch[grp * Op + o] = a;
+  __syncthreads();
+  if (threadIdx.x < O) {
+    float t = 0.f;
+    for (int gq = 0; gq < G; ++gq) t += scratch[gq * Op + threadIdx.x];
+    out_smem[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) se_bwd_kernel(const SeBwdP p) {
   extern __shared__ float sm[];
   const int n = blockIdx.x;
+  float* va = sm;                 // [max(C, SQ)]
+  float* vb = va + max(p.C, p.SQ);  // [max(C, SQ)]
+  float* scratch = vb + max(p.C, p.SQ);  // [1024 + 32]
   if (p.single) {
     // s[n][j] (SQ outputs) = sigmoid(sum_c w1[j][c] mean[c]);  ds given per output j
-    float* dpre = sm;  // [SQ]
     for (int j = threadIdx.x; j < p.SQ; j += blockDim.x) {
       float d = 0.f;
       for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.SQ + j];
       const float sv = p.s[static_cast<size_t>(n) * p.SQ + j];
       d *= sv * (1.f - sv);
-      dpre[j] = d;
+      va[j] = d;
       p.dpre1[static_cast<size_t>(n) * p.SQ + j] = d;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-      float a = 0.f;
-      for (int j = 0; j < p.SQ; ++j) a = fmaf(p.w1[static_cast<size_t>(j) * p.C + c], dpre[j], a);
-      p.dmean[static_cast<size_t>(n) * p.C + c] = a;
-    }
+    grouped_matvec(p.w1, p.C, 1, va, p.SQ, p.C, scratch, vb);  // dmean[c] = sum_j w1[j][c] dpre[j]
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) p.dmean[static_cast<size_t>(n) * p.C + c] = vb[c];
     return;
   }
-  float* dpre2 = sm;            // [C]
-  float* dpre1 = sm + p.C;      // [SQ]
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     float d = 0.f;
     for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.C + c];
     const float sv = p.s[static_cast<size_t>(n) * p.C + c];
     d = (sv > 0.f && sv < 1.f) ? d * (1.f / 6.f) : 0.f;  // hardsigmoid'
-    dpre2[c] = d;
+    va[c] = d;
     p.dpre2[static_cast<size_t>(n) * p.C + c] = d;
   }
   __syncthreads();
+  grouped_matvec(p.w2, p.SQ, 1, va, p.C, p.SQ, scratch, vb);  // dhid[j] = sum_c w2[c][j] dpre2[c]
   for (int j = threadIdx.x; j < p.SQ; j += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < p.C; ++c) a = fmaf(p.w2[static_cast<size_t>(c) * p.SQ + j], dpre2[c], a);
-    a = p.hid[static_cast<size_t>(n) * p.SQ + j] > 0.f ? a : 0.f;  // relu'
-    dpre1[j] = a;
+    const float a = p.hid[static_cast<size_t>(n) * p.SQ + j] > 0.f ? vb[j] : 0.f;  // relu'
+    vb[j] = a;
     p.dpre1[static_cast<size_t>(n) * p.SQ + j] = a;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    float a = 0.f;
-    for (int j = 0; j < p.SQ; ++j) a = fmaf(p.w1[static_cast<size_t>(j) * p.C + c], dpre1[j], a);
-    p.dmean[static_cast<size_t>(n) * p.C + c] = a;
-  }
+  grouped_matvec(p.w1, p.C, 1, vb, p.SQ, p.C, scratch, va);  // dmean[c] = sum_j w1[j][c] dpre1[j]
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) p.dmean[static_cast<size_t>(n) * p.C + c] = va[c];
 }
 
 // dW[i][j] = sum_n u[n][i] * v[n][j] * vscale ; optional dbias[i] = sum_n u[n][i].   v may be chunked partial sums.
@@ -196,14 +209,15 @@ constexpr int MAX_NC = 8;
 __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
   const int n = blockIdx.x;
   const int nh = p.Hh * p.Wh, nl = p.Hl * p.Wl;
-  // part 1: thread i < IC owns inter channel i over all high-res pixels
-  for (int i = threadIdx.x; i < p.IC; i += blockDim.x) {
+  // part 1: thread (i, grp) owns inter channel i over every (blockDim/IC)-th high-res pixel
+  const int g1 = max(1, static_cast<int>(blockDim.x) / p.IC);
+  for (int i = threadIdx.x % p.IC, grp = threadIdx.x / p.IC; grp < g1; grp = g1) {
     const float sv = p.s[static_cast<size_t>(n) * p.IC + i];
     float wh[MAX_NC], dwh[MAX_NC];
 #pragma unroll
     for (int c = 0; c < MAX_NC; ++c) { wh[c] = c < p.NC ? p.w_high[c * p.IC + i] : 0.f; dwh[c] = 0.f; }
     float dsv = 0.f;
-    for (int px = 0; px < nh; ++px) {
+    for (int px = grp; px < nh; px += g1) {
       const size_t row = static_cast<size_t>(n) * nh + px;
       const float cv = __bfloat162float(p.cbr[row * p.IC + i]);
       float dt = 0.f;
@@ -217,17 +231,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
       p.dcbr[row * p.IC + i] = __float2bfloat16(dt * sv);
       dsv = fmaf(dt, cv, dsv);
     }
-    p.ds[static_cast<size_t>(n) * p.IC + i] = dsv;
+    atomicAdd(p.ds + static_cast<size_t>(n) * p.IC + i, dsv);  // ds is zeroed by the caller
 #pragma unroll
     for (int c = 0; c < MAX_NC; ++c)
       if (c < p.NC) atomicAdd(p.dw_high + c * p.IC + i, dwh[c]);
   }
-  // part 2: thread k < LC owns low channel k over all low-res pixels
-  for (int k = threadIdx.x; k < p.LC; k += blockDim.x) {
+  // part 2: thread (k, grp) owns low channel k over every (blockDim/LC)-th low-res pixel
+  const int g2 = max(1, static_cast<int>(blockDim.x) / p.LC);
+  for (int k = threadIdx.x % p.LC, grp = threadIdx.x / p.LC; grp < g2; grp = g2) {
     float wl[MAX_NC], dwl[MAX_NC];
 #pragma unroll
     for (int c = 0; c < MAX_NC; ++c) { wl[c] = c < p.NC ? p.w_low[c * p.LC + k] : 0.f; dwl[c] = 0.f; }
-    for (int q = 0; q < nl; ++q) {
+    for (int q = grp; q < nl; q += g2) {
       const size_t row = static_cast<size_t>(n) * nl + q;
       const float lv = __bfloat162float(p.low[row * p.LC + k]);
       float dl = 0.f;
@@ -273,22 +288,31 @@ __global__ void fill_f32_kernel(float* __restrict__ p, float v, size_t n) {
 //   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // grads are multiplied by *inv_scale (GradScaler) when given; the whole step is skipped when *found_inf != 0.
 // ---------------------------------------------------------------------------------------------------------
-struct AdamChunk { float* p; const float* g; float* m; float* v; int n; };
+struct AdamChunk { float* p; const float* g; float* m; float* v; int n; int pad; };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale,
                                                     const float* __restrict__ found_inf) {
   if (found_inf && *found_inf != 0.f) return;
   const AdamChunk c = chunks[blockIdx.x];
   const float gs = inv_scale ? *inv_scale : 1.f;
-  const float step_size = lr / bc1;
-  for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
-    const float g = c.g[i] * gs;
-    float pv = c.p[i] * (1.f - lr * wd);
-    const float m = b1 * c.m[i] + (1.f - b1) * g;
-    const float v = b2 * c.v[i] + (1.f - b2) * g * g;
+  const float step_size = lr / bc1, decay = 1.f - lr * wd;
+  auto upd = [&](float& pv, float g, float& m, float& v) {
+    g *= gs;
+    pv *= decay;
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
     pv -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
-    c.p[i] = pv; c.m[i] = m; c.v[i] = v;
+  };
+  const bool aligned = ((reinterpret_cast<uintptr_t>(c.p) | reinterpret_cast<uintptr_t>(c.g) | reinterpret_cast<uintptr_t>(c.m) |
+                         reinterpret_cast<uintptr_t>(c.v)) & 15) == 0;
+  const int n4 = aligned ? c.n / 4 : 0;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 p4 = reinterpret_cast<float4*>(c.p)[i], m4 = reinterpret_cast<float4*>(c.m)[i], v4 = reinterpret_cast<float4*>(c.v)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(c.g)[i];
+    upd(p4.x, g4.x, m4.x, v4.x); upd(p4.y, g4.y, m4.y, v4.y); upd(p4.z, g4.z, m4.z, v4.z); upd(p4.w, g4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(c.p)[i] = p4; reinterpret_cast<float4*>(c.m)[i] = m4; reinterpret_cast<float4*>(c.v)[i] = v4;
   }
+  for (int i = n4 * 4 + threadIdx.x; i < c.n; i += blockDim.x) upd(c.p[i], c.g[i], c.m[i], c.v[i]);
 }
 
 }  // namespace
@@ -305,7 +329,9 @@ int launch_dot_pool(const bf16* a, const bf16* b, float* out, int B, int HW, int
 int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.ds_partial && a.s && a.w1 && a.dpre1 && a.dmean, MTG_ERR_ARG, "se_bwd: null pointer");
   SeBwdP p{a.ds_partial, a.chunks, a.s, a.hid, a.w1, a.w2, a.dpre2, a.dpre1, a.dmean, a.C, a.SQ, a.w2 ? 0 : 1};
-  se_bwd_kernel<<<a.B, 256, sizeof(float) * (a.C + a.SQ), st>>>(p);
+  MTG_REQUIRE(a.C <= 1024 && a.SQ <= 1024, MTG_ERR_UNSUPPORTED, "se_bwd: C / SQ above 1024");
+  const int mx = a.C > a.SQ ? a.C : a.SQ;
+  se_bwd_kernel<<<a.B, 1024, sizeof(float) * (2 * mx + 1024 + 64), st>>>(p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -9,7 +9,7 @@ import torch
 
 from . import _native as N
 
-_CHUNK = 1 << 16
+_CHUNK = 1 << 14
 _REC = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i4"), ("pad", "<i4")])
 
 
