@@ -130,7 +130,7 @@ def run_reference(args):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -319,12 +319,30 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "train": train,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun children) write to fd 1; the contract is ONE JSON line on stdout.
+    Route fd 1 to stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
