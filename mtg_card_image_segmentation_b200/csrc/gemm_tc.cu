@@ -72,7 +72,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = smem + S * A_STAGE_BYTES;
   uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + S * b_stage_bytes) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
   uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // res_slabs slabs
-  float* sScale = reinterpret_cast<float*>(sRes + p.res_slabs * SLAB_BYTES);
+  float* sScale = reinterpret_cast<float*>(sRes + 2 * p.res_slabs * SLAB_BYTES);
   float* sShift = sScale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + SS_BYTES);
   uint64_t* full = bars;
@@ -80,8 +80,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* xform = bars + 2 * MAX_STAGES;
   uint64_t* tfull = bars + 3 * MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* resbar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + 1);
+  uint64_t* resbar = tempty + 2;  // [2]: the residual tile is double buffered and prefetched one tile ahead
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,7 +96,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&tfull[b], 1);
       ptx::mbar_init(&tempty[b], 256);
     }
-    ptx::mbar_init(resbar, 1);
+    ptx::mbar_init(&resbar[0], 1);
+    ptx::mbar_init(&resbar[1], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -180,6 +181,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int slabs = (p.BN + 63) >> 6;
     uint32_t tc = 0, store_no = 0;
     int cur_ntile = -1;
+    auto load_residual = [&](int t, uint32_t rb) {  // leader only: residual tile of `t` -> buffer rb by TMA
+      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      ptx::mbar_arrive_expect_tx(&resbar[rb], slabs * SLAB_BYTES);
+      for (int sl = 0; sl < slabs; ++sl)
+        ptx::tma_load_2d(sRes + (rb * slabs + sl) * SLAB_BYTES, &tmR, &resbar[rb], nt * p.BN + sl * 64, mt * BM);
+    };
+    if (p.res_slabs && leader && static_cast<int>(blockIdx.x) < total_tiles) load_residual(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
@@ -189,11 +197,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         oc2 = (m_tile % p.h_tiles) * p.HB;
         oc3 = (m_tile / p.h_tiles) * p.NB;
       }
-      if (p.res_slabs && leader) {  // residual tile by TMA (all threads finished reading the previous one: barrier below)
-        ptx::mbar_arrive_expect_tx(resbar, slabs * SLAB_BYTES);
-        for (int sl = 0; sl < slabs; ++sl)
-          ptx::tma_load_2d(sRes + sl * SLAB_BYTES, &tmR, resbar, n_tile * p.BN + sl * 64, m_tile * BM);
-      }
+      const uint32_t rb = tc & 1;
+      // prefetch the NEXT tile's residual into the other buffer (its last readers finished before the final
+      // bar.sync of the previous iteration)
+      if (p.res_slabs && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, rb ^ 1);
       if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
         cur_ntile = n_tile;
         for (int c = et; c < p.BN; c += 256) {
@@ -204,7 +211,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       ptx::mbar_wait(&tfull[buf], aph);
       ptx::tc_fence_after();
-      if (p.res_slabs) ptx::mbar_wait(resbar, tc & 1);
+      if (p.res_slabs) ptx::mbar_wait(&resbar[rb], (tc >> 1) & 1);
       const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
       for (int sl = 0; sl < slabs; ++sl, ++store_no) {
         uint8_t* sbuf = sOut + (store_no & 1) * SLAB_BYTES;
@@ -213,7 +220,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int cols = min(64, p.BN - sl * 64);  // multiple of 16
         uint8_t* srow = sbuf + r * 128;
-        const uint8_t* rrow = sRes + sl * SLAB_BYTES + r * 128;
+        const uint8_t* rrow = sRes + (rb * slabs + sl) * SLAB_BYTES + r * 128;
         if (half * 32 < cols) {  // this warp's 32 accumulator columns: one TMEM round trip
           uint32_t v[2][16];
           ptx::tmem_ld16(taddr + sl * 64 + half * 32, v[0]);
@@ -519,7 +526,7 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   }
 
   const int stage_bytes = A_STAGE_BYTES + kp.BN * BK * 2;
-  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * SLAB_BYTES + static_cast<size_t>(kp.res_slabs) * SLAB_BYTES + SS_BYTES + BAR_BYTES;
+  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * SLAB_BYTES + 2 * static_cast<size_t>(kp.res_slabs) * SLAB_BYTES + SS_BYTES + BAR_BYTES;
   // ring depth: enough stages that two co-resident CTAs keep >= ~64 KB of loads in flight per SM (HBM latency x bandwidth)
   int stages = kp.num_kb >= 8 ? 6 : 4;
   if (stage_bytes <= 12 * 1024) stages = 8;

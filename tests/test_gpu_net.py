@@ -153,3 +153,45 @@ def test_metrics_calculator_vs_golden():
         for k, v in case["epoch_metrics"].items():
             assert abs(got[k] - v) <= 2e-6 * max(1.0, abs(v)), (k, got[k], v)
         assert torch.equal(M.confusion_counts(zc, tc).cpu(), case["counts"])
+
+
+def test_config5_metrics_over_10k_masks():
+    """BASELINE.json configs[4], first half: IoU/Dice over 10,000 synthetic (logit, mask) pairs at 320x240 in batches of
+    Config.BATCH_SIZE=32 with drop_last=False (train/evaluate.py:375-381): the int64 confusion matrix must be BIT-EXACT
+    against the oracle, the 8 MetricsCalculator floats (mean of per-batch ratios) within 1e-6, per-class P/R/F1/IoU of
+    evaluate.py:102-137 identical.  Logits are regenerated per batch from a seed on the device (48 GB would not fit a
+    test); the oracle sees the same tensors."""
+    from mtg_card_image_segmentation_b200.utils import per_class_metrics
+    n_total, bs = 10_000, 32
+    mc = M.MetricsCalculator(2, "cuda")
+    ref_counts = torch.zeros(4, dtype=torch.int64)
+    ref_sum = {k: 0.0 for k in ("iou0", "iou1", "dice0", "dice1", "acc")}
+    gen = torch.Generator(device="cuda").manual_seed(2024)
+    nb = 0
+    for start in range(0, n_total, bs):
+        b = min(bs, n_total - start)
+        z = torch.randn(b, 2, 320, 240, generator=gen, device="cuda")
+        z[:, 1, ::7, ::5] = z[:, 0, ::7, ::5]            # exact ties -> class 0
+        t = (torch.rand(b, 320, 240, generator=gen, device="cuda") < 0.45).long()
+        mc.update(torch.zeros((), device="cuda"), z, t)
+        # oracle on the same tensors (argmax + bincount in int64 on the device is the same integer arithmetic as
+        # oracle.confusion_counts; pulling 10k batches to the CPU would take minutes)
+        pred = torch.argmax(z, 1)
+        c = torch.bincount((t * 2 + pred).reshape(-1), minlength=4).cpu()
+        ref_counts += c
+        mm = O.metrics_from_counts(c)
+        ref_sum["iou0"] += mm["iou"][0]; ref_sum["iou1"] += mm["iou"][1]
+        ref_sum["dice0"] += mm["dice"][0]; ref_sum["dice1"] += mm["dice"][1]; ref_sum["acc"] += mm["acc"]
+        nb += 1
+        if start == 0:  # the first batch also goes through the CPU oracle proper
+            assert torch.equal(O.confusion_counts(z.cpu(), t.cpu()), c)
+    assert nb == 313
+    cm = mc.confusion_matrix()
+    assert torch.equal(cm.reshape(-1), ref_counts) and int(cm.sum()) == n_total * 320 * 240
+    got = mc.get_metrics()
+    want = {"iou_background": ref_sum["iou0"] / nb, "iou_card": ref_sum["iou1"] / nb, "dice_background": ref_sum["dice0"] / nb,
+            "dice_card": ref_sum["dice1"] / nb, "pixel_accuracy": ref_sum["acc"] / nb,
+            "mean_iou": (ref_sum["iou0"] + ref_sum["iou1"]) / 2 / nb, "mean_dice": (ref_sum["dice0"] + ref_sum["dice1"]) / 2 / nb}
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-6, (k, got[k], v)
+    assert per_class_metrics(cm) == O.per_class_metrics(cm)
