@@ -35,7 +35,6 @@ namespace {
 constexpr int BM = 128;           // UMMA M
 constexpr int MAX_STAGES = 8;
 constexpr int BAR_BYTES = 256;               // mbarriers + TMEM slot
-constexpr int SLAB_BYTES = BM * 128;         // one [128 rows][64 bf16] swizzled slab
 constexpr int OUT_BUFS = 2;                  // double-buffered output staging
 constexpr int SS_BYTES = 2 * 256 * 4;        // scale / shift of the current N tile
 
@@ -53,7 +52,8 @@ struct GemmKParams {
   bf16* out;
   const float* a_scale;
   int hw;
-  int res_slabs;  // 0 or ceil(BN/64)
+  int res_slabs;  // 0 or ceil(BN/obox)
+  int obox;       // output / residual slab width in channels: 64 / 32 / 16 <-> 128B / 64B / 32B swizzled rows
   // 3x3 geometry
   int B, H, W, HB, NB, h_tiles;
 };
@@ -71,7 +71,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * A_STAGE_BYTES;
   uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + S * b_stage_bytes) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
-  uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // res_slabs slabs
+  const int SLAB_BYTES = BM * p.obox * 2;
+  uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // 2 x res_slabs slabs
   float* sScale = reinterpret_cast<float*>(sRes + 2 * p.res_slabs * SLAB_BYTES);
   float* sShift = sScale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + SS_BYTES);
@@ -178,14 +179,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = q * 32 + lane;             // accumulator row of this thread
     const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
     const bool leader = et == 0;
-    const int slabs = (p.BN + 63) >> 6;
+    const int OB = p.obox, opitch = OB * 2;  // slab columns, slab row pitch in bytes
+    const int slabs = (p.BN + OB - 1) / OB;
     uint32_t tc = 0, store_no = 0;
     int cur_ntile = -1;
     auto load_residual = [&](int t, uint32_t rb) {  // leader only: residual tile of `t` -> buffer rb by TMA
       const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
       ptx::mbar_arrive_expect_tx(&resbar[rb], slabs * SLAB_BYTES);
       for (int sl = 0; sl < slabs; ++sl)
-        ptx::tma_load_2d(sRes + (rb * slabs + sl) * SLAB_BYTES, &tmR, &resbar[rb], nt * p.BN + sl * 64, mt * BM);
+        ptx::tma_load_2d(sRes + (rb * slabs + sl) * SLAB_BYTES, &tmR, &resbar[rb], nt * p.BN + sl * OB, mt * BM);
     };
     if (p.res_slabs && leader && static_cast<int>(blockIdx.x) < total_tiles) load_residual(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
@@ -218,22 +220,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // the TMA store that used this buffer two slabs ago must have finished reading it
         if (leader) ptx::bulk_wait_read<OUT_BUFS - 1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int cols = min(64, p.BN - sl * 64);  // multiple of 16
-        uint8_t* srow = sbuf + r * 128;
-        const uint8_t* rrow = sRes + (rb * slabs + sl) * SLAB_BYTES + r * 128;
+        const int cols = min(OB, p.BN - sl * OB);  // multiple of 16
+        uint8_t* srow = sbuf + r * opitch;
+        const uint8_t* rrow = sRes + (rb * slabs + sl) * SLAB_BYTES + r * opitch;
+        // swizzle XOR term of this row: 128B rows: row % 8 ; 64B rows: (row / 2) % 4 ; 32B rows: (row / 4) % 2
+        const int rx = OB == 64 ? (r & 7) : (OB == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
         if (half * 32 < cols) {  // this warp's 32 accumulator columns: one TMEM round trip
           uint32_t v[2][16];
-          ptx::tmem_ld16(taddr + sl * 64 + half * 32, v[0]);
-          if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * 64 + half * 32 + 16, v[1]);
+          ptx::tmem_ld16(taddr + sl * OB + half * 32, v[0]);
+          if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * OB + half * 32 + 16, v[1]);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             if (half * 32 + cc * 16 < cols) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the 128-byte slab row
-                const int c = sl * 64 + chunk * 8;             // column inside the N tile
-                const int phys = (chunk ^ (r & 7)) * 16;       // 128B swizzle: chunk index XOR (row % 8)
+                const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the slab row
+                const int c = sl * OB + chunk * 8;             // column inside the N tile
+                const int phys = (chunk ^ rx) * 16;            // TMA swizzle of the staging slab
                 const float4 s0 = *reinterpret_cast<const float4*>(sScale + c), s1 = *reinterpret_cast<const float4*>(sScale + c + 4);
                 const float4 h0 = *reinterpret_cast<const float4*>(sShift + c), h1 = *reinterpret_cast<const float4*>(sShift + c + 4);
                 const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -255,7 +259,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader) {
-          const int c0 = n_tile * p.BN + sl * 64;
+          const int c0 = n_tile * p.BN + sl * OB;
           if (kConv3x3) ptx::tma_store_4d(&tmO, sbuf, c0, oc1, oc2, oc3);
           else ptx::tma_store_2d(&tmO, sbuf, c0, oc1);
           ptx::bulk_commit();
@@ -464,7 +468,8 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   while (tmem < 2 * kp.BN) tmem <<= 1;
   kp.tmem_cols = tmem;
 
-  kp.res_slabs = g.residual ? ceil_div(kp.BN, 64) : 0;
+  kp.obox = (g.conv3x3 || kp.BN > 32) ? 64 : (kp.BN > 16 ? 32 : 16);  // narrow layers stage narrow slabs: more CTAs per SM
+  kp.res_slabs = g.residual ? ceil_div(kp.BN, kp.obox) : 0;
   MTG_REQUIRE(!(g.conv3x3 && g.residual), MTG_ERR_UNSUPPORTED, "conv_gemm: residual with conv3x3 is not supported");
   CUtensorMap tmA, tmB, tmO, tmR;
   if (g.conv3x3) {
@@ -515,21 +520,22 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     if (rc) return rc;
     const uint64_t od[2] = {(uint64_t)g.N, (uint64_t)g.M};
     const uint64_t os[1] = {(uint64_t)g.N * 2};
-    const uint32_t ob[2] = {64, BM};
-    rc = make_map(&tmO, g.out, 2, od, os, ob);
+    const uint32_t ob[2] = {(uint32_t)kp.obox, BM};
+    rc = make_map(&tmO, g.out, 2, od, os, ob, kp.obox);
     if (rc) return rc;
     tmR = tmO;
     if (g.residual) {
-      rc = make_map(&tmR, g.residual, 2, od, os, ob);
+      rc = make_map(&tmR, g.residual, 2, od, os, ob, kp.obox);
       if (rc) return rc;
     }
   }
 
   const int stage_bytes = A_STAGE_BYTES + kp.BN * BK * 2;
-  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * SLAB_BYTES + 2 * static_cast<size_t>(kp.res_slabs) * SLAB_BYTES + SS_BYTES + BAR_BYTES;
+  const size_t slab_bytes = static_cast<size_t>(BM) * kp.obox * 2;
+  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * slab_bytes + 2 * static_cast<size_t>(kp.res_slabs) * slab_bytes + SS_BYTES + BAR_BYTES;
   // ring depth: enough stages that two co-resident CTAs keep >= ~64 KB of loads in flight per SM (HBM latency x bandwidth)
   int stages = kp.num_kb >= 8 ? 6 : 4;
-  if (stage_bytes <= 12 * 1024) stages = 8;
+  if (stage_bytes <= 16 * 1024) stages = 8;
   while (stages > 2 && stages * static_cast<size_t>(stage_bytes) + fixed > 227 * 1024) --stages;
   // prefer two co-resident CTAs (8 epilogue warps per SM) over a deeper ring when that is what it costs
   if (stages > 3 && 2 * (3 * static_cast<size_t>(stage_bytes) + fixed) <= 227 * 1024 &&

@@ -24,31 +24,33 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     const long long t = idx / Wo;
     const int oy = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
+    // gather the 27 taps first (predicated, no branches between them: all loads are in flight together)
+    float xin[27];
+    const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+          const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          xin[ci * 9 + ky * 3 + kx] = ok ? __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix) : 0.f;
+        }
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
+    for (int t = 0; t < 27; ++t) {
+      const float xv = xin[t];
+      const float4* wp = &sw[t * 4];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = oy * 2 - 1 + ky;
-        if (iy < 0 || iy >= H) continue;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = ox * 2 - 1 + kx;
-          if (ix < 0 || ix >= W) continue;
-          const float xv = __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix);
-          const float4* wp = &sw[(ci * 9 + ky * 3 + kx) * 4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 wv = wp[q];
-            acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
-          }
-        }
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = wp[q];
+        acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
       }
     }
     float o0[8], o1[8];
