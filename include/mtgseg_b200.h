@@ -173,6 +173,9 @@ int mtgseg_bn_train_bwd(const void* z, const void* dy, void* dz, const float* sc
 /* weight gradient of a 1x1 (taps=1) or 3x3 pad-1 (taps=9) convolution: dw[N,K,taps] (fp32 OIHW) += dz[M,N]^T x[M,K] */
 int mtgseg_wgrad(const void* dz, const void* x, float* dw, const float* a_scale, int hw, int64_t M, int N, int K, int taps, int H,
                  int W, void* stream);
+/* the same on the tensor cores (tcgen05, MN-major operands; what mtgseg_backward uses): dz[B*hw,N], x[B*hw,K] */
+int mtgseg_wgrad_tc(const void* dz, const void* x, float* dw, const float* a_scale, int B, int hw, int N, int K, int taps, int H,
+                    int W, void* stream);
 /* depthwise conv backward: dx (if non-NULL) and dw[C,k*k] (fp32, accumulated, if non-NULL) */
 int mtgseg_dw_bwd(const void* dz, const void* x, const void* w, void* dx, float* dw, int B, int H, int W, int C, int k, int stride,
                   int dil, void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
                                  _i, _i, _i, _i, _vp]),
     "mtgseg_bn_train_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mtgseg_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, C.c_int64, _i, _i, _i, _i, _i, _vp]),
+    "mtgseg_wgrad_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mtgseg_dw_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mtgseg_stem_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mtgseg_upsample_bwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),

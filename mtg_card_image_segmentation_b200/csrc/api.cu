@@ -148,6 +148,14 @@ int mtgseg_wgrad(const void* dz, const void* x, float* dw, const float* a_scale,
   return launch_wgrad(a, S(stream));
 }
 
+int mtgseg_wgrad_tc(const void* dz, const void* x, float* dw, const float* a_scale, int B, int hw, int N, int K, int taps, int H,
+                    int W, void* stream) {
+  WgradArgs a;
+  a.dz = static_cast<const bf16*>(dz); a.x = static_cast<const bf16*>(x); a.dw = dw; a.a_scale = a_scale; a.hw = hw;
+  a.M = static_cast<long long>(B) * hw; a.N = N; a.K = K; a.taps = taps; a.H = H; a.W = W;
+  return launch_wgrad_tc(a, B, S(stream));
+}
+
 int mtgseg_dw_bwd(const void* dz, const void* x, const void* w, void* dx, float* dw, int B, int H, int W, int C, int k, int stride,
                   int dil, void* stream) {
   DwBwdArgs a;

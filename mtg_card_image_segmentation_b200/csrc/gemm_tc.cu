@@ -384,6 +384,19 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
   return MTG_OK;
 }
 
+}  // namespace
+
+// shared with wgrad_tc.cu
+int make_tma_map_bf16(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides_bytes, const unsigned* box, int kbox) {
+  uint64_t d[5], s[4];
+  uint32_t b[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; if (i > 0) s[i - 1] = strides_bytes[i - 1]; }
+  return make_map(map, base, rank, d, s, b, kbox);
+}
+
+namespace {
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {

@@ -10,6 +10,8 @@
 // Backward per conv+BN(+act): BN/act backward (two-phase reduce + apply, with the SE scale/pool terms folded
 // in) -> dz ; wgrad (fp32, reference OIHW layout) ; dgrad (tcgen05 GEMM with transposed weights, residual
 // gradient fused as the epilogue's "residual") or the depthwise dgrad kernel.
+#include <stdlib.h>
+
 #include "net.h"
 
 namespace mtgseg {
@@ -146,6 +148,14 @@ int bn_bwd(const Ctx& c, const ConvBnPlan& cp, const LayerBufs& L, int act, cons
   a.act = act; a.B = c.B; a.HW = L.H * L.W; a.C = L.C;
   MTG_REQUIRE(a.dgamma && a.dbeta, MTG_ERR_ARG, "backward: missing gradient buffer for a BatchNorm parameter");
   return launch_bn_train_bwd(a, c.st);
+}
+
+// weight gradient: tensor cores (MN-major tcgen05) unless MTGSEG_WGRAD=simt or the shape is outside its tiling
+int wgrad(const Ctx& c, WgradArgs& w, int hw) {
+  static const bool simt = [] { const char* e = getenv("MTGSEG_WGRAD"); return e && e[0] == 's'; }();
+  if (!w.hw) w.hw = hw;
+  if (simt || (w.taps == 9 && w.W > 64)) return launch_wgrad(w, c.st);
+  return launch_wgrad_tc(w, c.B, c.st);
 }
 
 int conv1x1_raw(const Ctx& c, const bf16* a, const bf16* w, bf16* out, int M, int N, int K, const float* a_scale, int hw,
@@ -286,7 +296,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   {
     WgradArgs w;
     w.dz = dz_cbr; w.x = T.last.y; w.dw = c.grad(P.cbr.w_idx); w.M = Mh; w.N = ic; w.K = 960; w.taps = 9; w.H = Hh; w.W = Wh;
-    RC(launch_wgrad(w, st));
+    RC(wgrad(c, w, Hh * Wh));
     ConvGemmArgs g;
     g.a = dz_cbr; g.w = c.wb(P.cbr.wt_off); g.out = T.g[0]; g.M = Mh; g.N = 960; g.K = ic; g.act = ACT_NONE;
     g.conv3x3 = 1; g.B = B; g.H = Hh; g.W = Wh;
@@ -299,7 +309,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   {
     WgradArgs w;
     w.dz = dz_last; w.x = last_in; w.dw = c.grad(P.last.w_idx); w.M = Mh; w.N = 960; w.K = 160;
-    RC(launch_wgrad(w, st));
+    RC(wgrad(c, w, Hh * Wh));
   }
   bf16* d_out = T.g[0];  // gradient w.r.t. the current block's output
   RC(conv1x1_raw(c, dz_last, c.wb(P.last.wt_off), d_out, Mh, 160, 960, nullptr, 0, nullptr));
@@ -323,7 +333,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
       WgradArgs w;
       w.dz = dz_p; w.x = K.dw.y; w.dw = c.grad(b.project.w_idx); w.M = Mo; w.N = cf.cout; w.K = cf.cexp;
       w.a_scale = cf.se ? K.s : nullptr; w.hw = HWo;
-      RC(launch_wgrad(w, st));
+      RC(wgrad(c, w, HWo));
     }
     bf16* da = T.g[2];
     RC(conv1x1_raw(c, dz_p, c.wb(b.project.wt_off), da, Mo, cf.cexp, cf.cout, nullptr, 0, nullptr));
@@ -363,7 +373,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
       RC(bn_bwd(c, b.expand, K.expand, cf.act, dy_e, dz_e, nullptr, nullptr));
       WgradArgs w;
       w.dz = dz_e; w.x = inp; w.dw = c.grad(b.expand.w_idx); w.M = Mi; w.N = cf.cexp; w.K = cf.cin;
-      RC(launch_wgrad(w, st));
+      RC(wgrad(c, w, K.Hin * K.Win));
       RC(conv1x1_raw(c, dz_e, c.wb(b.expand.wt_off), d_inp, Mi, cf.cin, cf.cexp, nullptr, 0, res ? d_out : nullptr));
     } else if (res) {
       RC(launch_add_bf16(dy_e, d_out, d_inp, static_cast<size_t>(Mi) * cf.cin, st));

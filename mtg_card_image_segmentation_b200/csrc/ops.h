@@ -136,7 +136,8 @@ struct WgradArgs {
   const float* a_scale = nullptr; int hw = 0;  // squeeze-excite multiplier [B][K] the forward applied to x
   long long M = 0; int N = 0, K = 0, taps = 1, H = 0, W = 0;
 };
-int launch_wgrad(const WgradArgs& a, cudaStream_t st);
+int launch_wgrad(const WgradArgs& a, cudaStream_t st);         // CUDA-core fallback (train_conv.cu)
+int launch_wgrad_tc(const WgradArgs& a, int B, cudaStream_t st);  // tcgen05, MN-major operands (wgrad_tc.cu); needs a.hw = pixels per image
 struct DwBwdArgs {
   const bf16* dz = nullptr; const bf16* x = nullptr; const bf16* w = nullptr;  // w: bf16 [k*k][C]
   bf16* dx = nullptr; float* dw = nullptr;                                      // dw: fp32 [C][k*k], accumulated

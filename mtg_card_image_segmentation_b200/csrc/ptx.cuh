@@ -66,6 +66,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -159,6 +165,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
 // 128B / 64B / 32B swizzled rows; the low half is the 16-byte-granular start address (+ ignored LBO = 1).
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t hi) {
   return static_cast<uint64_t>(((smem_addr & 0x3FFFF) >> 4) | (1u << 16)) | (static_cast<uint64_t>(hi) << 32);
+}
+// MN-major operand (the non-reduction index is contiguous in shared memory, e.g. [pixel][channel] tiles used with the
+// pixel index as the reduction): LBO = bytes between 64-element MN atoms, SBO (in `hi`) = bytes between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t hi) {
+  return static_cast<uint64_t>(((smem_addr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16)) | (static_cast<uint64_t>(hi) << 32);
 }
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, shape M x N.
 __device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {

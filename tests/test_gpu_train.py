@@ -191,18 +191,27 @@ def test_bn_train_fwd_bwd(B, HW, C, act, res, se):
     _chk("bn bwd dbeta", dbet, bet.grad, 1e-3, 1e-3)
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("M,N_,K,taps,H,W,se", [(9600, 160, 960, 1, 0, 0, True), (2 * 19200, 64, 16, 1, 0, 0, False),
-                                                (4 * 300, 128, 960, 9, 20, 15, False), (777, 24, 72, 1, 0, 0, False)])
-def test_wgrad(M, N_, K, taps, H, W, se):
+                                                (4 * 300, 128, 960, 9, 20, 15, False), (777 * 3, 24, 72, 1, 0, 0, False),
+                                                (32 * 300, 960, 160, 1, 0, 0, False), (6 * 1200, 40, 120, 1, 0, 0, True)])
+def test_wgrad(M, N_, K, taps, H, W, se, tc):
     g = torch.Generator().manual_seed(M)
     dz = torch.randn(M, N_, generator=g).bfloat16().cuda(); x = torch.randn(M, K, generator=g).bfloat16().cuda()
-    hw = 300
+    hw = 300 if M % 300 == 0 else (1200 if M % 1200 == 0 else 777)
+    if M % 19200 == 0:
+        hw = 19200
     a_scale = torch.rand(M // hw, K, generator=g).cuda() if se else None
     dw = torch.zeros(N_, K, taps).cuda()
-    N.check(N.load().mtgseg_wgrad(dz.data_ptr(), x.data_ptr(), dw.data_ptr(), N.ptr(a_scale), hw, M, N_, K, taps, H, W, N.stream_ptr()), "wgrad")
+    if tc:  # tensor-core path: the SE gate multiplies the fp32 accumulator (no bf16 rounding of x*s)
+        N.check(N.load().mtgseg_wgrad_tc(dz.data_ptr(), x.data_ptr(), dw.data_ptr(), N.ptr(a_scale), M // hw, hw, N_, K, taps, H, W,
+                                         N.stream_ptr()), "wgrad_tc")
+    else:
+        N.check(N.load().mtgseg_wgrad(dz.data_ptr(), x.data_ptr(), dw.data_ptr(), N.ptr(a_scale), hw, M, N_, K, taps, H, W, N.stream_ptr()), "wgrad")
     xf = x.float()
     if se:
-        xf = (xf.view(-1, hw, K) * a_scale[:, None, :]).bfloat16().float().view(M, K)
+        xf = xf.view(-1, hw, K) * a_scale[:, None, :]
+        xf = (xf if tc else xf.bfloat16().float()).reshape(M, K)
     if taps == 1:
         ref = (dz.float().t() @ xf)[:, :, None]
     else:
