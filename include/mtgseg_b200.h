@@ -183,6 +183,26 @@ int mtgseg_stem_wgrad(const float* x, const void* dz, float* dw, int B, int H, i
 /* transpose of the align_corners=False bilinear upsample: g[B,NC,Hf,Wf] -> out fp32 [B,Hc,Wc,NC] */
 int mtgseg_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int Hc, int Wc, int Hf, int Wf, void* stream);
 
+/* ---- corner-keypoint head of the pose pipeline (BASELINE.json configs[4]) ----------------------------------
+ * HRNetPoseHead.forward in eval mode (train-pose-estimation_custom/model.py:10-77) on a backbone feature map and
+ * LiteHRNet.decode_heatmaps (model.py:133-164).  params = the 28 state_dict entries of HRNetPoseHead in order.
+ *   features  float32 [batch,in_channels,feat_h,feat_w]            (the timm backbone itself is out of scope)
+ *   heatmaps  float32 [batch,num_keypoints,out_h,out_w]            (AdaptiveAvgPool2d target, model.py:52)
+ *   coords    float32 [batch,2*num_keypoints] x0,y0,x1,y1,... in [0,1] (argmax, lowest index on ties), or NULL */
+typedef struct mtgseg_pose_desc {
+  int32_t in_channels; /* backbone feature channels */
+  int32_t feat_h, feat_w;
+  int32_t num_keypoints; /* 4 */
+  int32_t out_h, out_w;  /* 120, 160 */
+} mtgseg_pose_desc;
+int mtgseg_pose_param_count(void);
+size_t mtgseg_pose_packed_bytes(const mtgseg_pose_desc* desc);
+size_t mtgseg_pose_workspace_bytes(const mtgseg_pose_desc* desc, int batch);
+int mtgseg_pose_pack_weights(const mtgseg_pose_desc* desc, const void* const* params, int n_params, void* packed, void* stream);
+int mtgseg_pose_forward(const mtgseg_pose_desc* desc, const float* features, const void* packed, float* heatmaps, float* coords,
+                        void* workspace, size_t workspace_bytes, int batch, void* stream);
+int mtgseg_decode_heatmaps(const float* heatmaps, float* coords, int batch, int num_keypoints, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

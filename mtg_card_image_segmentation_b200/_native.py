@@ -25,6 +25,11 @@ class LayerProf(C.Structure):
                 ("flops", C.c_double)]
 
 
+class PoseDesc(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("feat_h", C.c_int32), ("feat_w", C.c_int32), ("num_keypoints", C.c_int32),
+                ("out_h", C.c_int32), ("out_w", C.c_int32)]
+
+
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_void_p, C.c_size_t
 _ND = C.POINTER(NetDesc)
 
@@ -50,6 +55,12 @@ SIGNATURES = {
     "mtgseg_dw_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mtgseg_stem_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mtgseg_upsample_bwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mtgseg_pose_param_count": (_i, []),
+    "mtgseg_pose_packed_bytes": (_sz, [C.POINTER(PoseDesc)]),
+    "mtgseg_pose_workspace_bytes": (_sz, [C.POINTER(PoseDesc), _i]),
+    "mtgseg_pose_pack_weights": (_i, [C.POINTER(PoseDesc), C.POINTER(_vp), _i, _vp, _vp]),
+    "mtgseg_pose_forward": (_i, [C.POINTER(PoseDesc), _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "mtgseg_decode_heatmaps": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "mtgseg_launch_count": (C.c_ulonglong, []),
     "mtgseg_forward_infer_profiled": (_i, [_ND, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp, C.POINTER(LayerProf), _i,
                                            C.POINTER(_i)]),

@@ -54,8 +54,9 @@ struct GemmKParams {
   int hw;
   int res_slabs;  // 0 or ceil(BN/obox)
   int obox;       // output / residual slab width in channels: 64 / 32 / 16 <-> 128B / 64B / 32B swizzled rows
-  // 3x3 geometry
+  // multi-tap (3x3 / transposed-conv parity) geometry: A boxes {64 ch, W, HB rows, NB images} shifted by (dx, dy) per tap
   int B, H, W, HB, NB, h_tiles;
+  signed char tap_dy[9], tap_dx[9];
 };
 
 template <bool kConv3x3, bool kAScale>
@@ -137,7 +138,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_arrive_expect_tx(&full[s], stage_bytes);
           if (kConv3x3) {
             const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
-            ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kc * BK, tap % 3 - 1, y0 + tap / 3 - 1, n0);
+            ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kc * BK, p.tap_dx[tap], y0 + p.tap_dy[tap], n0);
             ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], tap * p.K + kc * BK, n_tile * p.BN);
           } else {
             ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, m_tile * BM);
@@ -473,7 +474,13 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     kp.desc_hi = sbo | (1u << 14) | (layout << 29);                          // bits 32-45 SBO, 46-48 version 1, 61-63 layout
   }
   kp.kb_per_tap = ceil_div(g.K, BK);
-  kp.num_kb = kp.kb_per_tap * (g.conv3x3 ? 9 : 1);
+  const int ntaps = g.conv3x3 ? (g.ntaps > 0 ? g.ntaps : 9) : 1;
+  MTG_REQUIRE(ntaps >= 1 && ntaps <= 9, MTG_ERR_ARG, "conv_gemm: ntaps %d out of range", ntaps);
+  for (int t = 0; t < 9; ++t) {
+    kp.tap_dy[t] = static_cast<signed char>(g.ntaps > 0 ? g.tap_dy[t] : t / 3 - 1);
+    kp.tap_dx[t] = static_cast<signed char>(g.ntaps > 0 ? g.tap_dx[t] : t % 3 - 1);
+  }
+  kp.num_kb = kp.kb_per_tap * ntaps;
   kp.ksteps_last = ceil_div(g.K - (kp.kb_per_tap - 1) * BK, 16);
   kp.scale = g.scale; kp.shift = g.shift; kp.act = g.act;
   kp.residual = g.residual; kp.out = g.out; kp.a_scale = g.a_scale; kp.hw = g.hw;
@@ -507,13 +514,16 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)g.W, (uint32_t)kp.HB, (uint32_t)kp.NB};
     int rc = make_map(&tmA, g.a, 4, dims, strides, box);
     if (rc) return rc;
-    const uint64_t wd[2] = {(uint64_t)g.K * 9, (uint64_t)g.N};
-    const uint64_t ws[1] = {(uint64_t)g.K * 9 * 2};
+    const uint64_t wd[2] = {(uint64_t)g.K * ntaps, (uint64_t)g.N};
+    const uint64_t ws[1] = {(uint64_t)g.K * ntaps * 2};
     const uint32_t wb[2] = {(uint32_t)BK, (uint32_t)kp.BN};
     rc = make_map(&tmB, g.w, 2, wd, ws, wb);
     if (rc) return rc;
+    // output view: dense NHWC by default, or a strided view (transposed-conv parity classes write every other pixel)
+    const uint64_t sx = g.out_sx ? g.out_sx : g.N, sy = g.out_sy ? g.out_sy : (uint64_t)g.W * g.N,
+                   sn = g.out_sn ? g.out_sn : (uint64_t)g.H * g.W * g.N;
     const uint64_t od[4] = {(uint64_t)g.N, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
-    const uint64_t os[3] = {(uint64_t)g.N * 2, (uint64_t)g.W * g.N * 2, (uint64_t)g.H * g.W * g.N * 2};
+    const uint64_t os[3] = {sx * 2, sy * 2, sn * 2};
     const uint32_t ob[4] = {64, (uint32_t)g.W, (uint32_t)kp.HB, (uint32_t)kp.NB};
     rc = make_map(&tmO, g.out, 4, od, os, ob);
     if (rc) return rc;

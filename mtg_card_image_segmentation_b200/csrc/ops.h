@@ -17,8 +17,12 @@ struct ConvGemmArgs {
   const bf16* residual = nullptr;  // [M][N] added after the activation-less projection
   const float* a_scale = nullptr;  // squeeze-excite: [B][K] multiplier applied to A rows of image b
   int hw = 0;                      // rows per image (needed with a_scale)
-  int conv3x3 = 0;                 // 3x3, stride 1, pad 1, dilation 1
-  int B = 0, H = 0, W = 0;         // geometry for conv3x3 (M == B*H*W)
+  int conv3x3 = 0;                 // multi-tap mode: 3x3, stride 1, pad 1 (default taps) or an explicit tap list
+  int B = 0, H = 0, W = 0;         // geometry for the multi-tap mode (M == B*H*W)
+  int ntaps = 0;                   // 0 -> the nine 3x3 taps; else 1..9 explicit (dy, dx) offsets in [-1, 1], weights [N][ntaps][K]
+  int tap_dy[9] = {0}, tap_dx[9] = {0};
+  long long out_sx = 0, out_sy = 0, out_sn = 0;  // output strides in elements (0 -> dense NHWC); lets a parity class of a
+                                                 // stride-2 transposed conv write every other pixel of the full-size tensor
 };
 int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st);
 
