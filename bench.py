@@ -295,6 +295,36 @@ def run_ours(args):
                  "parallelism": f"data parallel x{world}, per-replica BatchNorm, NCCL all-reduce of 16.8 MB fp32 grads after backward"}
         del tmodel, opt
 
+    # ---------------- pose head forward (configs[4], second half): tensor-bound 256-channel convs at 160x120 --------
+    pose = None
+    if not args.no_pose:
+        from mtg_card_image_segmentation_b200.pose import HRNetPoseHead
+        PB = args.pose_batch
+        head = HRNetPoseHead(512).to(dev).eval()
+        feat = torch.randn(PB, 512, 40, 30, device=dev)
+        with torch.no_grad():
+            for _ in range(3):
+                head(feat, return_coords=True)
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            psteps = max(5, args.steps // 2)
+            p0.record()
+            for _ in range(psteps):
+                head(feat, return_coords=True)
+            p1.record()
+            barrier()
+        pt = torch.tensor([p0.elapsed_time(p1)], device=dev)
+        if world > 1:
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        flop_img = 2.0 * (1200 * 4 * 256 * 4 * 512 + 4800 * 4 * 256 * 4 * 256 + 2 * 19200 * 256 * 9 * 256 + 19200 * 8 * 256)
+        _, tf_peak, _ = peaks()
+        ms = pt.item() / psteps
+        pose = {"metric": "pose-head forward images/sec (HRNetPoseHead on a 512x40x30 feature -> 4x120x160 heatmaps + coords)",
+                "value": world * PB / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": PB,
+                "roofline": {"bound": "tensor", "achieved": flop_img * PB / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                             "frac": flop_img * PB / (ms * 1e-3) / 1e12 / tf_peak, "flop_per_image": flop_img}}
+        del head, feat
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -317,7 +347,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "CardSegmentationModel.predict (uint8 mask), pinned host buffers, copy/compute double-buffered"},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "train": train,
+            "roofline": roofline, "cpu_baseline": cpu, "train": train, "pose_head": pose,
         }
         emit(line)
     if world > 1:
@@ -352,6 +382,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--no-pose", action="store_true", help="skip the pose-head leg")
+    ap.add_argument("--pose-batch", type=int, default=16)
     ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step (train/config.py:26)")
     ap.add_argument("--layers-out", default=None, help="write the per-layer profile (JSON) here")
     args = ap.parse_args()

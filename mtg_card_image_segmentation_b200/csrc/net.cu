@@ -82,7 +82,7 @@ int build_plan(const mtgseg_net_desc& d, NetPlan& P) {
     b.cfg = c;
     b.has_expand = c.cexp != c.cin;
     if (b.has_expand) plan_convbn(b.expand, pi, arena, static_cast<size_t>(c.cexp) * c.cin, 2, c.cexp, eps_bb, true, c.cin);
-    plan_convbn(b.dw, pi, arena, static_cast<size_t>(c.cexp) * c.k * c.k, 2, c.cexp, eps_bb);
+    plan_convbn(b.dw, pi, arena, static_cast<size_t>(c.cexp) * c.k * c.k, 2, c.cexp, eps_bb, true);  // + tap-reversed copy (dgrad)
     if (c.se) {
       b.sq = make_divisible8(c.cexp / 4);
       b.fc1_w = pi++; b.fc1_b = pi++; b.fc2_w = pi++; b.fc2_b = pi++;
@@ -127,7 +127,8 @@ int pack_weights(const NetPlan& P, const void* const* params, void* packed, cuda
       RC(launch_pack_transpose_bf16(f(b.expand.w_idx), reinterpret_cast<bf16*>(base + b.expand.wt_off), c.cexp, c.cin, st));
       RC(fold(b.expand));
     }
-    RC(launch_pack_dw(f(b.dw.w_idx), reinterpret_cast<bf16*>(base + b.dw.w_off), c.cexp, c.k * c.k, st));
+    RC(launch_pack_dw(f(b.dw.w_idx), reinterpret_cast<bf16*>(base + b.dw.w_off), reinterpret_cast<bf16*>(base + b.dw.wt_off), c.cexp,
+                      c.k * c.k, st));
     RC(fold(b.dw));
     if (c.se) {
       const size_t n = static_cast<size_t>(b.sq) * c.cexp;

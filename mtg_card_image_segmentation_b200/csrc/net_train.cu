@@ -365,7 +365,16 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
     RC(launch_dw_wgrad(d, st));
     bf16* dy_e = T.g[2];
     d.dx = dy_e;
-    RC(launch_dw_dgrad(d, st));
+    if (d.stride == 1) {
+      // dgrad of a stride-1 depthwise conv is the same conv with the taps reversed: reuse the staged forward kernel
+      DwConvArgs f;
+      f.in = dz_d; f.w = c.wb(b.dw.wt_off); f.out = dy_e; f.scale = T.ones; f.shift = T.zeros; f.act = ACT_NONE;
+      f.B = B; f.H = K.Hin; f.W = K.Win; f.C = cf.cexp; f.k = cf.k; f.stride = 1; f.dil = cf.dil;
+      f.chunks = dwconv_chunks(K.Hin, K.Win, cf.cexp, cf.k, 1, cf.dil, false);
+      RC(launch_dwconv(f, st));
+    } else {
+      RC(launch_dw_dgrad(d, st));
+    }
     bf16* d_inp = T.g[3];
     if (b.has_expand) {
       MTG_REQUIRE(need(b.expand.w_idx), MTG_ERR_ARG, "backward: missing gradient buffers (block %d expand)", i + 1);

@@ -188,7 +188,7 @@ int launch_copy_f32(const float* in, float* out, size_t n, cudaStream_t st);
 // [O][I][kh][kw] fp32 -> [O][kh*kw][I] bf16
 int launch_pack_oihw_to_otapi(const float* in, bf16* out, int O, int I, int taps, cudaStream_t st);
 // depthwise [C][1][k][k] fp32 -> [k*k][C] bf16
-int launch_pack_dw(const float* in, bf16* out, int C, int taps, cudaStream_t st);
+int launch_pack_dw(const float* in, bf16* out, bf16* out_flip, int C, int taps, cudaStream_t st);
 // stem [16][3][3][3] fp32 -> [27][16] fp32
 int launch_pack_stem(const float* in, float* out, cudaStream_t st);
 // scale = gamma / sqrt(var + eps), shift = beta - mean * scale

@@ -24,12 +24,14 @@ __global__ void oihw_to_otapi_kernel(const float* __restrict__ in, bf16* __restr
     out[i] = __float2bfloat16(in[(o * I + ci) * T + t]);
   }
 }
-// in [C][T] -> out [T][C]
-__global__ void pack_dw_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int T) {
+// in [C][T] -> out [T][C] and (optional) the tap-reversed copy used by the stride-1 depthwise dgrad
+__global__ void pack_dw_kernel(const float* __restrict__ in, bf16* __restrict__ out, bf16* __restrict__ out_flip, int C, int T) {
   const int n = C * T;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int c = i % C, t = i / C;
-    out[i] = __float2bfloat16(in[c * T + t]);
+    const bf16 v = __float2bfloat16(in[c * T + t]);
+    out[i] = v;
+    if (out_flip) out_flip[(T - 1 - t) * C + c] = v;
   }
 }
 // in [16][27] -> out [27][16]
@@ -91,8 +93,8 @@ int launch_pack_oihw_to_otapi(const float* in, bf16* out, int O, int I, int taps
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
-int launch_pack_dw(const float* in, bf16* out, int C, int taps, cudaStream_t st) {
-  pack_dw_kernel<<<blocks_for(static_cast<size_t>(C) * taps), 256, 0, st>>>(in, out, C, taps);
+int launch_pack_dw(const float* in, bf16* out, bf16* out_flip, int C, int taps, cudaStream_t st) {
+  pack_dw_kernel<<<blocks_for(static_cast<size_t>(C) * taps), 256, 0, st>>>(in, out, out_flip, C, taps);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -124,21 +124,45 @@ __global__ void __launch_bounds__(1024) se_bwd_kernel(const SeBwdP p) {
 }
 
 // dW[i][j] = sum_n u[n][i] * v[n][j] * vscale ; optional dbias[i] = sum_n u[n][i].   v may be chunked partial sums.
-__global__ void outer_sum_kernel(const float* __restrict__ u, const float* __restrict__ v, int v_chunks, float vscale,
-                                 float* __restrict__ dw, float* __restrict__ dbias, int B, int I, int J) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= I * J) return;
-  const int i = idx / J, j = idx - i * J;
-  float a = 0.f, bsum = 0.f;
-  for (int n = 0; n < B; ++n) {
-    float vv = 0.f;
-    for (int k = 0; k < v_chunks; ++k) vv += v[(static_cast<size_t>(n) * v_chunks + k) * J + j];
-    const float uu = u[static_cast<size_t>(n) * I + i];
-    a = fmaf(uu, vv * vscale, a);
-    bsum += uu;
+// CTA tile: 16 rows (i) x 64 columns (j); u and the chunk-reduced v of up to 64 images are staged in shared memory.
+__global__ void __launch_bounds__(256) outer_sum_kernel(const float* __restrict__ u, const float* __restrict__ v, int v_chunks, float vscale,
+                                                        float* __restrict__ dw, float* __restrict__ dbias, int B, int I, int J) {
+  __shared__ float us[64][16];
+  __shared__ float vs[64][64];
+  const int j0 = blockIdx.x * 64, i0 = blockIdx.y * 16;
+  const int tj = threadIdx.x & 63, ti = threadIdx.x >> 6;  // 4 row lanes
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int nb = 0; nb < B; nb += 64) {
+    const int nn = min(64, B - nb);
+    for (int idx = threadIdx.x; idx < nn * 64; idx += 256) {
+      const int n = idx >> 6, j = j0 + (idx & 63);
+      float t = 0.f;
+      if (j < J)
+        for (int k = 0; k < v_chunks; ++k) t += v[(static_cast<size_t>(nb + n) * v_chunks + k) * J + j];
+      vs[n][idx & 63] = t * vscale;
+    }
+    for (int idx = threadIdx.x; idx < nn * 16; idx += 256) {
+      const int n = idx >> 4, i = i0 + (idx & 15);
+      us[n][idx & 15] = i < I ? u[static_cast<size_t>(nb + n) * I + i] : 0.f;
+    }
+    __syncthreads();
+    for (int n = 0; n < nn; ++n) {
+      const float vv = vs[n][tj];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float uu = us[n][ti + 4 * m];
+        acc[m] = fmaf(uu, vv, acc[m]);
+        bsum[m] += uu;
+      }
+    }
+    __syncthreads();
   }
-  dw[idx] = a;
-  if (dbias && j == 0) dbias[i] = bsum;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int i = i0 + ti + 4 * m, j = j0 + tj;
+    if (i < I && j < J) dw[static_cast<size_t>(i) * J + j] = acc[m];
+    if (dbias && blockIdx.x == 0 && tj == 0 && i < I) dbias[i] = bsum[m];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -339,7 +363,7 @@ int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
 int launch_outer_sum(const float* u, const float* v, int v_chunks, float vscale, float* dw, float* dbias, int B, int I, int J,
                      cudaStream_t st) {
   MTG_REQUIRE(u && v && dw, MTG_ERR_ARG, "outer_sum: null pointer");
-  outer_sum_kernel<<<ceil_div(I * J, 256), 256, 0, st>>>(u, v, v_chunks, vscale, dw, dbias, B, I, J);
+  outer_sum_kernel<<<dim3(ceil_div(J, 64), ceil_div(I, 16)), 256, 0, st>>>(u, v, v_chunks, vscale, dw, dbias, B, I, J);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

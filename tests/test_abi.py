@@ -37,7 +37,7 @@ def test_binding_covers_header_and_basic_queries():
     assert lib.mtgseg_param_count() == 319
     d = N.NetDesc(320, 240, 2, 128)
     packed = lib.mtgseg_packed_bytes(ctypes.byref(d))
-    assert 12_000_000 < packed < 18_000_000  # bf16 weights + their transposed dgrad copies + folded BN constants
+    assert 12_000_000 < packed < 19_000_000  # bf16 weights + their transposed dgrad copies + folded BN constants
     ws1 = lib.mtgseg_workspace_bytes(ctypes.byref(d), 1)
     ws8 = lib.mtgseg_workspace_bytes(ctypes.byref(d), 8)
     assert 16_000_000 < ws1 < 20_000_000 and 7.5 * ws1 < ws8 < 8.5 * ws1  # ~16.6 MB of bf16 activations per image

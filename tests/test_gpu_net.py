@@ -195,3 +195,22 @@ def test_config5_metrics_over_10k_masks():
     for k, v in want.items():
         assert abs(got[k] - v) <= 1e-6, (k, got[k], v)
     assert per_class_metrics(cm) == O.per_class_metrics(cm)
+
+
+def test_model_evaluator_matches_reference_semantics():
+    """evaluate.py:41-137 drop-in: dict keys, integer confusion matrix == oracle over the whole loader, per-class metrics."""
+    from mtg_card_image_segmentation_b200.evaluate import ModelEvaluator
+    x, m = O.synthetic_cards(10, seed=5, height=64, width=48)
+    sd = O.calibrate_running_stats(O.make_weights(9), x)
+    model = _model(sd)
+    loader = [{"image": x[i:i + 4], "mask": m[i:i + 4], "filename": [f"f{j}" for j in range(i, min(i + 4, 10))]} for i in range(0, 10, 4)]
+    res = ModelEvaluator(model, torch.device("cuda"), 2).evaluate_dataset(loader, criterion=M.CombinedLoss(), keep_predictions=True)
+    assert set(res) == {"basic_metrics", "confusion_matrix", "per_class_metrics", "predictions", "targets", "filenames"}
+    with torch.no_grad():
+        z = model(x.cuda()).cpu()
+    want = O.confusion_counts(z, m).reshape(2, 2)
+    assert (torch.from_numpy(res["confusion_matrix"]) == want).all()
+    assert res["per_class_metrics"] == O.per_class_metrics(want)
+    assert len(res["predictions"]) == 10 * 64 * 48 and res["filenames"][-1] == "f9"
+    assert set(res["basic_metrics"]) == {"loss", "iou_background", "iou_card", "mean_iou", "dice_background", "dice_card", "mean_dice",
+                                        "pixel_accuracy"}
