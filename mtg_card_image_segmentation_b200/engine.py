@@ -19,6 +19,7 @@ class SegEngine:
         self._packed = None
         self._packed_sig = None
         self._ws = None
+        self._ws_extra = {}
         self._train_ws = None
         self._stats_dirty = False
         self._desc_cache = {}
@@ -53,17 +54,22 @@ class SegEngine:
         self._packed_sig = sig
         return self._packed
 
-    def workspace(self, d: N.NetDesc, batch: int, device) -> torch.Tensor:
+    def workspace(self, d: N.NetDesc, batch: int, device, slot: int = 0) -> torch.Tensor:
+        """Activation workspace; `slot` > 0 selects an independent buffer (concurrent sub-batches on other streams)."""
         need = self.lib.mtgseg_workspace_bytes(C.byref(d), batch)
         if need == 0:
             raise RuntimeError(f"mtgseg_workspace_bytes failed: {self.lib.mtgseg_last_error().decode()}")
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
+        cur = self._ws if slot == 0 else self._ws_extra.get(slot)
+        if cur is None or cur.numel() < need or cur.device != device:
+            cur = torch.empty(need, dtype=torch.uint8, device=device)
+            if slot == 0:
+                self._ws = cur
+            else:
+                self._ws_extra[slot] = cur
+        return cur
 
     # -- inference ---------------------------------------------------------------------------
-    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None):
+    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None, ws_slot=0, out=None):
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError(f"expected a (B,3,H,W) batch, got {tuple(x.shape)}")
         if x.dtype != torch.float32:
@@ -74,10 +80,10 @@ class SegEngine:
         with torch.cuda.device(dev):
             packed = self.pack(tensors, dev)
             d = self.desc(H, W)
-            ws = self.workspace(d, B, dev)
+            ws = self.workspace(d, B, dev, ws_slot)
             logits = None
             if logits_dtype is not None:
-                logits = torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
+                logits = out if out is not None else torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
             mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_mask else None
             counts = None
             if targets is not None:
@@ -165,23 +171,46 @@ class SegEngine:
 class GraphedInference:
     """CUDA-graph replay of one fixed-shape inference call (launch-bound regimes: ~60 kernels per forward).
 
+    ``splits`` > 1 runs that many sub-batches concurrently on forked streams inside the graph (images are independent
+    units): kernels of different sub-batches fill each other's ramp-up / drain phases.
     ``run(x)`` copies ``x`` into the captured input buffer and replays; outputs are the captured tensors."""
 
-    def __init__(self, model, example, logits_dtype=torch.bfloat16, want_mask=False):
+    def __init__(self, model, example, logits_dtype=torch.bfloat16, want_mask=False, splits=1):
         self.model = model
         self.x = example.clone()
         eng, tensors = model.engine(), model._state_tensors()
-        kw = dict(logits_dtype=logits_dtype, want_mask=want_mask)
+        B = self.x.shape[0]
+        splits = max(1, min(splits, B))
+        bounds = [(i * B) // splits for i in range(splits + 1)]
+        logits = torch.empty((B, eng.num_classes) + tuple(self.x.shape[2:]), dtype=logits_dtype, device=self.x.device)
+
+        def run_all():
+            if splits == 1:
+                return eng.infer(tensors, self.x, logits_dtype=logits_dtype, want_mask=want_mask, out=logits)
+            main = torch.cuda.current_stream()
+            for i in range(splits):
+                st = self._streams[i]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    eng.infer(tensors, self.x[bounds[i]:bounds[i + 1]], logits_dtype=logits_dtype, ws_slot=i,
+                              out=logits[bounds[i]:bounds[i + 1]])
+            for st in self._streams:
+                main.wait_stream(st)
+            return logits
+
+        if splits > 1 and want_mask:
+            raise RuntimeError("GraphedInference: splits > 1 supports logits output only")
+        self._streams = [torch.cuda.Stream() for _ in range(splits)] if splits > 1 else []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up outside capture: packs weights, sizes the workspace, sets func attributes
-            eng.infer(tensors, self.x, **kw)
+        with torch.cuda.stream(side):  # warm-up outside capture: packs weights, sizes the workspaces, sets func attributes
+            run_all()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         before = eng.lib.mtgseg_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = eng.infer(tensors, self.x, **kw)
+            self.out = run_all()
         self.launches_per_replay = int(eng.lib.mtgseg_launch_count() - before)
 
     def replay(self):
