@@ -44,6 +44,7 @@ struct GemmKParams {
   int num_kb, kb_per_tap, ksteps_last;
   int stages, tmem_cols, a_bytes;  // a_bytes: bytes one A TMA box delivers
   int kbox;                        // K elements per stage: 64 / 32 / 16 <-> 128B / 64B / 32B swizzled rows
+  int b_res;                       // weights of this CTA's N tile stay resident in smem (few k-blocks): the ring carries A only
   uint32_t desc_hi;                // upper half of the smem matrix descriptors (SBO, version, swizzle mode)
   const float* scale;
   const float* shift;
@@ -69,9 +70,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int BK = p.kbox;
   const int A_STAGE_BYTES = BM * BK * 2;
   const int b_stage_bytes = p.BN * BK * 2;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + S * A_STAGE_BYTES;
-  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + S * b_stage_bytes) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
+  // B-stationary layout: [resident B: num_kb tiles][A ring] ; streaming layout: [A ring][B ring]
+  const int b_res_bytes = p.b_res ? ((p.num_kb * b_stage_bytes + 1023) & ~1023) : 0;
+  uint8_t* sBres = smem;
+  uint8_t* sA = smem + b_res_bytes;
+  uint8_t* sB = sA + S * A_STAGE_BYTES;
+  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + (p.b_res ? 0 : S * b_stage_bytes)) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
   const int SLAB_BYTES = BM * p.obox * 2;
   uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // 2 x res_slabs slabs
   float* sScale = reinterpret_cast<float*>(sRes + 2 * p.res_slabs * SLAB_BYTES);
@@ -83,7 +87,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = bars + 3 * MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* resbar = tempty + 2;  // [2]: the residual tile is double buffered and prefetched one tile ahead
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + 2);
+  uint64_t* bfull = resbar + 2;   // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +105,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     ptx::mbar_init(&resbar[0], 1);
     ptx::mbar_init(&resbar[1], 1);
+    ptx::mbar_init(bfull, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -123,7 +129,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t stage_bytes = p.a_bytes + b_stage_bytes;
+      const uint32_t stage_bytes = p.a_bytes + (p.b_res ? 0 : b_stage_bytes);
+      if (p.b_res && static_cast<int>(blockIdx.x) < total_tiles) {
+        // gridDim.x is a multiple of n_tiles, so this CTA's N tile never changes: fetch its weights once
+        const int n_tile = blockIdx.x % p.n_tiles;
+        ptx::mbar_arrive_expect_tx(bfull, p.num_kb * b_stage_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          ptx::tma_load_2d(sBres + kb * b_stage_bytes, &tmB, bfull, kb * BK, n_tile * p.BN);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int n0 = 0, y0 = 0;
@@ -142,7 +155,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], tap * p.K + kc * BK, n_tile * p.BN);
           } else {
             ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, m_tile * BM);
-            ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], kb * BK, n_tile * p.BN);
+            if (!p.b_res) ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], kb * BK, n_tile * p.BN);
           }
         }
       }
@@ -152,6 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.BN);
       uint32_t it = 0, tc = 0;
+      if (p.b_res && static_cast<int>(blockIdx.x) < total_tiles) ptx::mbar_wait(bfull, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
         const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
         ptx::mbar_wait(&tempty[buf], aph ^ 1);
@@ -165,7 +179,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int kc = kb % p.kb_per_tap;
           const int ksteps = (kc == p.kb_per_tap - 1) ? p.ksteps_last : (BK / 16);
           const uint64_t adesc = ptx::umma_desc_kmajor(ptx::smem_u32(sA + s * A_STAGE_BYTES), p.desc_hi);
-          const uint64_t bdesc = ptx::umma_desc_kmajor(ptx::smem_u32(sB + s * b_stage_bytes), p.desc_hi);
+          const uint64_t bdesc = ptx::umma_desc_kmajor(ptx::smem_u32(p.b_res ? sBres + kb * b_stage_bytes : sB + s * b_stage_bytes), p.desc_hi);
           for (int k = 0; k < ksteps; ++k)  // +32 B along K inside the swizzle row == +2 in the address field
             ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
@@ -432,6 +446,10 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const long long total_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = static_cast<int>(total_tiles);
+  if (kp.b_res) {  // resident weights: a CTA must keep one N tile for its whole life -> grid is a multiple of n_tiles
+    grid = grid / kp.n_tiles * kp.n_tiles;
+    if (grid < kp.n_tiles) grid = kp.n_tiles;
+  }
   conv_gemm_kernel<C3, AS><<<grid, threads, smem, st>>>(tmA, tmB, tmO, tmR, kp);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
@@ -553,9 +571,15 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     }
   }
 
-  const int stage_bytes = A_STAGE_BYTES + kp.BN * BK * 2;
+  // B-stationary: with few k-blocks the weights of one N tile fit in shared memory next to the A ring; every CTA then
+  // streams only activations (the weight tile would otherwise be re-fetched from L2 for every 128-pixel tile)
+  const size_t b_tile_bytes = static_cast<size_t>(kp.BN) * BK * 2;
+  const long long all_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles;
+  kp.b_res = (!g.conv3x3 && kp.num_kb <= 4 && kp.num_kb * b_tile_bytes <= 100 * 1024 && all_tiles >= 4LL * num_sms()) ? 1 : 0;
+  const size_t b_res_bytes = kp.b_res ? align_up(kp.num_kb * b_tile_bytes, 1024) : 0;
+  const int stage_bytes = A_STAGE_BYTES + (kp.b_res ? 0 : kp.BN * BK * 2);
   const size_t slab_bytes = static_cast<size_t>(BM) * kp.obox * 2;
-  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * slab_bytes + 2 * static_cast<size_t>(kp.res_slabs) * slab_bytes + SS_BYTES + BAR_BYTES;
+  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * slab_bytes + 2 * static_cast<size_t>(kp.res_slabs) * slab_bytes + SS_BYTES + BAR_BYTES + b_res_bytes;
   // ring depth: enough stages that two co-resident CTAs keep >= ~64 KB of loads in flight per SM (HBM latency x bandwidth)
   int stages = kp.num_kb >= 8 ? 6 : 4;
   if (stage_bytes <= 16 * 1024) stages = 8;

@@ -174,6 +174,7 @@ class CardSegmentationModel(nn.Module):
         self.num_classes = num_classes
         self.model = _LRASPP(num_classes, inter_channels=128)
         self._engine = None
+        self._state_cache = None
         self.last_flat_grad = None
 
     # -- engine plumbing ---------------------------------------------------------------------
@@ -183,7 +184,22 @@ class CardSegmentationModel(nn.Module):
         return self._engine
 
     def _state_tensors(self):
-        return list(self.state_dict(keep_vars=True).values())
+        """The 319 state tensors in reference order (cached: building a state_dict costs ~0.3 ms per call).  Module
+        surgery that adds/removes parameters (e.g. torch.nn.utils.prune) must call ``invalidate_cache()``."""
+        if self._state_cache is None:
+            self._state_cache = list(self.state_dict(keep_vars=True).values())
+        return self._state_cache
+
+    def invalidate_cache(self):
+        self._state_cache = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._state_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._state_cache = None
+        return super().load_state_dict(*args, **kwargs)
 
     def forward(self, x):
         """x float32 (B,3,H,W) -> logits (B,num_classes,H,W) (train/model.py:79-89)."""
