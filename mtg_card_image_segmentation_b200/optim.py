@@ -19,8 +19,7 @@ class FusedAdamW(torch.optim.Optimizer):
                         foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True)
         super().__init__(params, defaults)
         self._lib = N.load()
-        self._table_key = None
-        self._table = None
+        self._tables = {}
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -49,16 +48,18 @@ class FusedAdamW(torch.optim.Optimizer):
             # the chunk table only depends on pointers; the caching allocator hands the same gradient block back every
             # step, so in steady state the device copy is reused
             key = (gi, tuple(p.grad.data_ptr() for p in params), tuple(p.data_ptr() for p in params))
-            if key != self._table_key:
+            if key not in self._tables:  # (the flat gradient buffer alternates between two allocator blocks)
+                if len(self._tables) >= 8:
+                    self._tables.clear()
                 recs = []
                 for p in params:
                     st = self.state[p]
                     n, base = p.numel(), (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr())
                     for off in range(0, n, _CHUNK):
                         recs.append((base[0] + 4 * off, base[1] + 4 * off, base[2] + 4 * off, base[3] + 4 * off, min(_CHUNK, n - off), 0))
-                self._table = (torch.from_numpy(np.array(recs, dtype=_REC).view(np.uint8).copy()).to(dev), len(recs))
-                self._table_key = key
-            table, nrec = self._table
+                host = torch.from_numpy(np.array(recs, dtype=_REC).view(np.uint8).copy()).pin_memory()
+                self._tables[key] = (host.to(dev, non_blocking=True), len(recs), host)
+            table, nrec, _ = self._tables[key]
             b1, b2 = group["betas"]
             with torch.cuda.device(dev):
                 N.check(self._lib.mtgseg_adamw_step(table.data_ptr(), nrec, float(group["lr"]), float(b1), float(b2),
