@@ -255,16 +255,17 @@ def run_ours(args):
                 with open(args.layers_out, "w") as f:
                     json.dump({"batch": B, "layers": layers, "families": roofline["families"]}, f, indent=1)
 
-    # ---------------- training step (configs[2]/[3]): fwd + CombinedLoss + bwd (+ grad all-reduce) + AdamW ----------
-    train = None
-    if not args.no_train:
+    # ---------------- training step: fwd + CombinedLoss + bwd (+ grad all-reduce) + AdamW --------------------------
+    # configs[2]: batch 32 per GPU (train/config.py:26); configs[3]: data parallel at GLOBAL batch 256 (256/N per GPU)
+    def train_leg(TB, label):
         from mtg_card_image_segmentation_b200.optim import FusedAdamW
         from mtg_card_image_segmentation_b200.parallel import average_gradients
-        TB = args.train_batch
         tmodel = M.create_model(2, pretrained=False).to(dev).train()
         opt = FusedAdamW(tmodel.parameters(), lr=1e-3, weight_decay=1e-4)  # train/config.py:28-29
         crit = M.CombinedLoss(0.5, 0.5)
-        xt, mt = x[:TB].contiguous(), m_host[:TB].to(dev)
+        reps = (TB + B - 1) // B
+        xt = x.repeat(reps, 1, 1, 1)[:TB].contiguous() if TB > B else x[:TB].contiguous()
+        mt = (m_host.repeat(reps, 1, 1)[:TB] if TB > B else m_host[:TB]).to(dev)
 
         def train_step():
             opt.zero_grad(set_to_none=True)
@@ -280,7 +281,7 @@ def run_ours(args):
         barrier()
         l0 = lib.mtgseg_launch_count()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tsteps = max(5, args.steps // 2)
+        tsteps = max(5, args.steps // 4)
         t0e.record()
         for _ in range(tsteps):
             last = train_step()
@@ -289,11 +290,20 @@ def run_ours(args):
         tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        train = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "value": world * TB * tsteps / (tt.item() * 1e-3),
-                 "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps, "batch_per_gpu": TB, "global_batch": TB * world,
-                 "loss": float(last.item()), "gpu_launches_per_step": int((lib.mtgseg_launch_count() - l0) // tsteps),
-                 "parallelism": f"data parallel x{world}, per-replica BatchNorm, NCCL all-reduce of 16.8 MB fp32 grads after backward"}
+        res = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "workload": label,
+               "value": world * TB * tsteps / (tt.item() * 1e-3), "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps,
+               "batch_per_gpu": TB, "global_batch": TB * world, "loss": float(last.item()),
+               "gpu_launches_per_step": int((lib.mtgseg_launch_count() - l0) // tsteps),
+               "parallelism": f"data parallel x{world}, per-replica BatchNorm, one NCCL all-reduce of the 16.8 MB flat fp32 gradient"}
         del tmodel, opt
+        torch.cuda.empty_cache()
+        return res
+
+    train = train_dp = None
+    if not args.no_train:
+        train = train_leg(args.train_batch, "configs[2]: train/train.py step, batch 32 per GPU")
+        if 256 % world == 0:
+            train_dp = train_leg(256 // world, f"configs[3]: data-parallel step, global batch 256 = {256 // world} per GPU")
 
     # ---------------- pose head forward (configs[4], second half): tensor-bound 256-channel convs at 160x120 --------
     pose = None
@@ -330,8 +340,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         ips, ms = cpu_reference_forward(32, 3, 1, threads)
+        ips1, ms1 = cpu_reference_forward(1, 20, 5, threads)  # configs[0]: batch 1, fp32, config.py resolution
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "3 steps x B=32 fp32 eval forward at 320x240, oracle port (torch oneDNN), 1 warm-up"}
+               "sample": "3 steps x B=32 fp32 eval forward at 320x240, oracle port (torch oneDNN), 1 warm-up",
+               "config0_batch1": {"value": ips1, "unit": UNIT, "ms_per_image": ms1, "sample": "20 x B=1 fp32 eval forward, 5 warm-up"}}
 
     if rank == 0:
         line = {
@@ -347,7 +359,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "CardSegmentationModel.predict (uint8 mask), pinned host buffers, copy/compute double-buffered"},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "train": train, "pose_head": pose,
+            "roofline": roofline, "cpu_baseline": cpu, "train": train, "train_global256": train_dp, "pose_head": pose,
         }
         emit(line)
     if world > 1:
