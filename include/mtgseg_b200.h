@@ -100,6 +100,13 @@ int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* pac
 int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int step, const float* inv_scale, const float* found_inf, void* stream);
 
+/* Same, fed with the RAW image batch: uint8 [batch,in_h,in_w,3] (HWC, what cv2 / the camera delivers, train/dataset.py:66-70);
+ * A.Normalize's (v/255 - mean)/std with the ImageNet constants (train/dataset.py:182-185) is fused into the stem's load, so the
+ * host->device copy is 4x smaller and no normalised fp32 tensor is ever materialised. */
+int mtgseg_forward_infer_u8(const mtgseg_net_desc* desc, const uint8_t* x_hwc, const void* packed, void* logits, int logits_dtype,
+                            uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
+                            int batch, void* stream);
+
 /* Measurement aids (bench.py): kernels launched by this library so far in this process, and one forward with
  * CUDA events around every kernel launch (synchronises `stream`; algorithmic bytes/flops per launch as in
  * each input read once, each output written once). */

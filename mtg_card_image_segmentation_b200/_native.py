@@ -64,6 +64,7 @@ SIGNATURES = {
     "mtgseg_launch_count": (C.c_ulonglong, []),
     "mtgseg_forward_infer_profiled": (_i, [_ND, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp, C.POINTER(LayerProf), _i,
                                            C.POINTER(_i)]),
+    "mtgseg_forward_infer_u8": (_i, [_ND, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "mtgseg_metric_counts": (_i, [_vp, _i, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "mtgseg_loss_scratch_bytes": (_sz, []),
     "mtgseg_loss_fwd_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _i, C.c_float, C.c_float, C.c_float, _vp]),

@@ -47,26 +47,38 @@ int mtgseg_pack_weights(const mtgseg_net_desc* desc, const void* const* params, 
   return pack_weights(P, params, packed, S(stream));
 }
 
-int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits, int logits_dtype,
-                         uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
-                         int batch, void* stream) {
+static int forward_infer_impl(const mtgseg_net_desc* desc, const float* x, const uint8_t* x_u8, const void* packed, void* logits,
+                              int logits_dtype, uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace,
+                              size_t workspace_bytes, int batch, void* stream) {
   NetPlan P;
   int rc = plan_for(desc, P);
   if (rc) return rc;
-  MTG_REQUIRE(x && packed && workspace, MTG_ERR_ARG, "forward_infer: null pointer");
+  MTG_REQUIRE((x || x_u8) && packed && workspace, MTG_ERR_ARG, "forward_infer: null pointer");
   MTG_REQUIRE(batch > 0, MTG_ERR_ARG, "forward_infer: batch must be positive");
   MTG_REQUIRE(logits || mask || counts4, MTG_ERR_ARG, "forward_infer: no output requested");
   MTG_REQUIRE(!logits || (logits_dtype >= LOGITS_F32 && logits_dtype <= LOGITS_F16), MTG_ERR_ARG, "forward_infer: bad logits dtype %d", logits_dtype);
   MTG_REQUIRE(!counts4 || targets, MTG_ERR_ARG, "forward_infer: counts4 needs targets");
   MTG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MTG_ERR_ARG, "forward_infer: workspace must be 256-byte aligned");
   InferIO io;
-  io.x = x; io.packed = packed; io.logits = logits; io.logits_dtype = logits_dtype; io.mask = mask;
+  io.x = x; io.x_u8 = x_u8; io.packed = packed; io.logits = logits; io.logits_dtype = logits_dtype; io.mask = mask;
   io.counts4 = counts4; io.targets = targets; io.batch = batch;
   size_t need = 0;
   rc = run_infer(P, io, nullptr, 0, &need, nullptr);
   if (rc) return rc;
   MTG_REQUIRE(need <= workspace_bytes, MTG_ERR_WORKSPACE, "forward_infer: workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   return run_infer(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, nullptr, S(stream));
+}
+
+int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits, int logits_dtype,
+                         uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
+                         int batch, void* stream) {
+  return forward_infer_impl(desc, x, nullptr, packed, logits, logits_dtype, mask, counts4, targets, workspace, workspace_bytes, batch, stream);
+}
+
+int mtgseg_forward_infer_u8(const mtgseg_net_desc* desc, const uint8_t* x_hwc, const void* packed, void* logits, int logits_dtype,
+                            uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
+                            int batch, void* stream) {
+  return forward_infer_impl(desc, nullptr, x_hwc, packed, logits, logits_dtype, mask, counts4, targets, workspace, workspace_bytes, batch, stream);
 }
 
 size_t mtgseg_train_workspace_bytes(const mtgseg_net_desc* desc, int batch) {

@@ -186,7 +186,7 @@ int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes,
   bf16* t = act_buf(static_cast<size_t>(B) * H * W * 16);
   if (!dry) {
     StemArgs a;
-    a.x = io.x; a.w = wf(P.stem.w_off); a.scale = wf(P.stem.scale_off); a.shift = wf(P.stem.shift_off);
+    a.x = io.x; a.x_u8 = io.x_u8; a.w = wf(P.stem.w_off); a.scale = wf(P.stem.scale_off); a.shift = wf(P.stem.shift_off);
     a.out = t; a.B = B; a.H = P.desc.in_h; a.W = P.desc.in_w;
     snprintf(nm, sizeof(nm), "stem");
     PROF("stem", (double)B * (3.0 * P.desc.in_h * P.desc.in_w * 4 + (double)H * W * 16 * 2), 2.0 * B * H * W * 16 * 27, launch_stem(a, st));

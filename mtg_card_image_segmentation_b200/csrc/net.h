@@ -39,6 +39,7 @@ struct NetPlan {
 
 struct InferIO {
   const float* x = nullptr;
+  const uint8_t* x_u8 = nullptr;  // alternative input: raw uint8 HWC pixels
   const void* packed = nullptr;
   void* logits = nullptr;
   int logits_dtype = LOGITS_F32;

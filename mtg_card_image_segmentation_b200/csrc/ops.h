@@ -42,7 +42,9 @@ int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st);
 
 struct StemArgs {
-  const float* x = nullptr;  // [B][3][H][W] fp32 NCHW (the reference's data contract)
+  const float* x = nullptr;  // [B][3][H][W] fp32 NCHW (the reference's data contract), or
+  const uint8_t* x_u8 = nullptr;  // [B][H][W][3] raw uint8 pixels, normalised on load with mean/std below
+  float mean[3] = {0.485f, 0.456f, 0.406f}, std[3] = {0.229f, 0.224f, 0.225f};  // train/dataset.py:182-185
   const float* w = nullptr;  // [27][16] fp32, index (ci*9 + ky*3 + kx)
   const float* scale = nullptr;
   const float* shift = nullptr;

@@ -9,7 +9,11 @@
 namespace mtgseg {
 namespace {
 
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// kU8: the batch is raw uint8 HWC camera/dataset pixels; (v/255 - mean)/std (train/dataset.py:182-185) is applied on load,
+// so the host never materialises the 4x larger normalised fp32 NCHW tensor.  Zero padding lives in the normalised domain.
+template <bool kU8>
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xu8, float3 nmul,
+                                                   float3 nadd, const float* __restrict__ w,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int act) {
   __shared__ float4 sw[27 * 4];
@@ -26,17 +30,32 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     const int n = static_cast<int>(t / Ho);
     // gather the 27 taps first (predicated, no branches between them: all loads are in flight together)
     float xin[27];
-    const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
+    if (kU8) {
+      const uint8_t* xn = xu8 + static_cast<size_t>(n) * H * W * 3;
+      const float mul[3] = {nmul.x, nmul.y, nmul.z}, add[3] = {nadd.x, nadd.y, nadd.z};
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
           const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-          xin[ci * 9 + ky * 3 + kx] = ok ? __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix) : 0.f;
+          const uint8_t* px = xn + (static_cast<size_t>(ok ? iy : 0) * W + (ok ? ix : 0)) * 3;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) xin[ci * 9 + ky * 3 + kx] = ok ? fmaf(static_cast<float>(__ldg(px + ci)), mul[ci], add[ci]) : 0.f;
         }
+    } else {
+      const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+            xin[ci * 9 + ky * 3 + kx] = ok ? __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix) : 0.f;
+          }
+    }
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -68,12 +87,16 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 }  // namespace
 
 int launch_stem(const StemArgs& a, cudaStream_t st) {
-  MTG_REQUIRE(a.x && a.w && a.scale && a.shift && a.out, MTG_ERR_ARG, "stem: null pointer");
+  MTG_REQUIRE((a.x || a.x_u8) && a.w && a.scale && a.shift && a.out, MTG_ERR_ARG, "stem: null pointer");
   const int Ho = (a.H + 2 - 3) / 2 + 1, Wo = (a.W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(a.B) * Ho * Wo;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stem_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(a.x, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act);
+  // v/255 normalised: (v/255 - mean)/std = v * 1/(255 std) - mean/std
+  const float3 nmul = make_float3(1.f / (255.f * a.std[0]), 1.f / (255.f * a.std[1]), 1.f / (255.f * a.std[2]));
+  const float3 nadd = make_float3(-a.mean[0] / a.std[0], -a.mean[1] / a.std[1], -a.mean[2] / a.std[2]);
+  if (a.x_u8) stem_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(nullptr, a.x_u8, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act);
+  else stem_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(a.x, nullptr, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

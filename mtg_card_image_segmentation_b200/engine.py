@@ -70,13 +70,21 @@ class SegEngine:
 
     # -- inference ---------------------------------------------------------------------------
     def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None, ws_slot=0, out=None):
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise RuntimeError(f"expected a (B,3,H,W) batch, got {tuple(x.shape)}")
-        if x.dtype != torch.float32:
-            x = x.float()
-        x = x.contiguous()
-        B, _, H, W = x.shape
+        u8 = x.dtype == torch.uint8
+        if u8:  # raw HWC pixels: normalisation is fused into the stem kernel
+            if x.dim() != 4 or x.shape[3] != 3:
+                raise RuntimeError(f"uint8 input must be (B,H,W,3) raw pixels, got {tuple(x.shape)}")
+            x = x.contiguous()
+            B, H, W, _ = x.shape
+        else:
+            if x.dim() != 4 or x.shape[1] != 3:
+                raise RuntimeError(f"expected a (B,3,H,W) batch, got {tuple(x.shape)}")
+            if x.dtype != torch.float32:
+                x = x.float()
+            x = x.contiguous()
+            B, _, H, W = x.shape
         dev = x.device
+        fwd = self.lib.mtgseg_forward_infer_u8 if u8 else self.lib.mtgseg_forward_infer
         with torch.cuda.device(dev):
             packed = self.pack(tensors, dev)
             d = self.desc(H, W)
@@ -91,7 +99,7 @@ class SegEngine:
                     raise RuntimeError("targets must be an int64 (B,H,W) tensor on the input's device")
                 targets = targets.contiguous()
                 counts = torch.zeros(4, dtype=torch.int64, device=dev)
-            rc = self.lib.mtgseg_forward_infer(
+            rc = fwd(
                 C.byref(d), x.data_ptr(), packed.data_ptr(), N.ptr(logits),
                 _TORCH_TO_LOGITS.get(logits_dtype, N.LOGITS_NONE), N.ptr(mask), N.ptr(counts), N.ptr(targets),
                 ws.data_ptr(), ws.numel(), B, N.stream_ptr())

@@ -214,3 +214,20 @@ def test_model_evaluator_matches_reference_semantics():
     assert len(res["predictions"]) == 10 * 64 * 48 and res["filenames"][-1] == "f9"
     assert set(res["basic_metrics"]) == {"loss", "iou_background", "iou_card", "mean_iou", "dice_background", "dice_card", "mean_dice",
                                         "pixel_accuracy"}
+
+
+def test_uint8_input_path_matches_normalised_fp32_path():
+    """raw uint8 HWC pixels in, (v/255 - mean)/std fused into the stem (train/dataset.py:182-185)."""
+    g = torch.Generator().manual_seed(12)
+    raw = torch.randint(0, 256, (3, 320, 240, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]); std = torch.tensor([0.229, 0.224, 0.225])
+    xf = ((raw.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    sd = O.calibrate_running_stats(O.make_weights(31), xf)
+    model = _model(sd)
+    with torch.no_grad():
+        a = model.engine().infer(model._state_tensors(), raw.cuda(), torch.float32)
+        b = model(xf.cuda())
+        m_u8 = model.predict(raw.cuda())["mask"]
+    # identical maths except the order of the normalisation arithmetic before the bf16 stem output
+    assert D.report("uint8 path vs fp32 path", a.cpu(), b.cpu())[0] <= 1e-2
+    assert (m_u8.long() == torch.argmax(a, 1)).all()
