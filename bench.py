@@ -255,6 +255,15 @@ def run_ours(args):
                                          "TFLOP/s": v["flops"] / (v["ms"] * 1e-3) / 1e12, "launches": v["launches"]}
                                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
                         "whole_step_algorithmic_GB/s": sum(v["bytes"] for v in agg.values()) / (total_ms * 1e-3) / 1e9}
+            # dram read+write per launch of the dominant family, from the committed `ncu --set full` capture of one forward
+            # (profiles/r1_traffic.json, written by tools/forward_full_summary.py); null when no capture is committed or
+            # it was taken at another batch size.
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if os.path.exists(tpath) and B == 256:
+                tf = json.load(open(tpath))["families"].get(dom)
+                if tf and tf["launches"] == a["launches"]:
+                    roofline["traffic"] = tf["traffic_bytes_per_launch"]
+                    roofline["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, B=256, caches flushed per kernel)"
             if args.layers_out:
                 os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
                 with open(args.layers_out, "w") as f:
@@ -293,11 +302,22 @@ def run_ours(args):
         t1e.record()
         barrier()
         tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+        # Host time to ENQUEUE one step, measured outside the timed region on steps that start from an idle, synchronised
+        # device (inside a free-running loop the launch queue fills and the host time converges to the device time).
+        host_ms = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            h0 = time.perf_counter()
+            train_step()
+            host_ms.append(1e3 * (time.perf_counter() - h0))
+        torch.cuda.synchronize()
+        host_ms = min(host_ms)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         res = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "workload": label,
                "value": world * TB * tsteps / (tt.item() * 1e-3), "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps,
                "batch_per_gpu": TB, "global_batch": TB * world, "loss": float(last.item()),
+               "host_enqueue_ms_per_step": host_ms,  # >= ms_per_step would mean the step is host-launch bound on this box
                "gpu_launches_per_step": int((lib.mtgseg_launch_count() - l0) // tsteps),
                "parallelism": f"data parallel x{world}, per-replica BatchNorm, one NCCL all-reduce of the 16.8 MB flat fp32 gradient"}
         del tmodel, opt
