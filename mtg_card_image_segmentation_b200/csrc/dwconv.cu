@@ -9,11 +9,17 @@
 //
 // Replaces the depthwise Conv2dNormActivation of tv:models/mobilenetv3.py:83-95 (+ the AdaptiveAvgPool2d
 // of tv:ops/misc.py:252-253).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "ops.h"
+#include "ptx.cuh"
 
 namespace mtgseg {
+
+int make_tma_map_bf16(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides_bytes, const unsigned* box, int kbox);  // gemm_tc.cu
+
 namespace {
 
 struct DwP {
@@ -138,6 +144,7 @@ struct DwS {
   const float* scale; const float* shift;
   float* gap;
   int act, H, W, C, Ho, Wo, pad, CV, CVc, PL, strips, band, bands, R, Wp;
+  int xoff;  // offset of the input tile inside the dynamic buffer, in uint4 (weights first, padded to 128 bytes for TMA)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
@@ -146,38 +153,76 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
 }
 
-template <int KS, int STRIDE, int DIL, int TW>
-__global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const DwS p) {
-  extern __shared__ uint4 dsm[];
-  __shared__ float red[256 * 8];
+// acc[0..7] += x[0..7] * w[0..7]; F2 issues the four channel pairs as packed fp32x2 FMAs (FFMA2 on sm_100).
+template <bool F2>
+__device__ __forceinline__ void fma8(float (&acc)[8], const float (&x)[8], const float (&w)[8]) {
+  if constexpr (F2) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint64_t a, xv, wv;
+      asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(acc[j]), "f"(acc[j + 1]));
+      asm("mov.b64 %0, {%1,%2};" : "=l"(xv) : "f"(x[j]), "f"(x[j + 1]));
+      asm("mov.b64 %0, {%1,%2};" : "=l"(wv) : "f"(w[j]), "f"(w[j + 1]));
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xv), "l"(wv));
+      asm("mov.b64 {%0,%1}, %2;" : "=f"(acc[j]), "=f"(acc[j + 1]) : "l"(a));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], w[j], acc[j]);
+  }
+}
+
+// TMA: phase 1 is ONE 4-D box load of the band's input rows (out-of-bounds rows / columns / channels are zero filled by
+// the TMA unit = the convolution padding) plus one 2-D box load of the weights, issued by thread 0 and awaited on an
+// mbarrier; no per-thread address arithmetic.  !TMA: the same tile gathered with 16-byte cp.async (kept for A/B).
+template <int KS, int STRIDE, int DIL, int TW, bool TMA, bool F2>
+__global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
+                                                              const DwS p) {
+  extern __shared__ __align__(128) uint4 dsm[];
+  __shared__ uint64_t bar;
   constexpr int NI = (TW - 1) * STRIDE + (KS - 1) * DIL + 1;
-  uint4* sw = dsm;                      // [KS*KS][CVc]
-  uint4* sx = dsm + KS * KS * p.CVc;    // [R][Wp][CVc]
+  uint4* sw = dsm;              // [KS*KS][CVc]
+  uint4* sx = dsm + p.xoff;     // [R][Wp][CVc]
+  float* red = reinterpret_cast<float*>(dsm);  // SE pool partials reuse the buffer after phase 2 (<= 8 KB)
   const int tid = threadIdx.x;
   const int n = blockIdx.z, band = blockIdx.x;
   const int v0 = blockIdx.y * p.CVc;
   const int nv = min(p.CVc, p.CV - v0);  // vectors of this group that exist
   const int oy0 = band * p.band, oy1 = min(p.Ho, oy0 + p.band);
   const int iy_base = oy0 * STRIDE - p.pad;
-  const int rows = (oy1 - oy0 - 1) * STRIDE + (KS - 1) * DIL + 1;
   // ---- phase 1: stage ----
-  const bf16* in_n = p.in + static_cast<size_t>(n) * p.H * p.W * p.C + v0 * 8;
-  const int per_row = p.Wp * p.CVc;
-  for (int i = tid; i < rows * per_row; i += 256) {
-    const int r = i / per_row, rem = i - r * per_row;
-    const int xp = rem / p.CVc, vl = rem - xp * p.CVc;
-    const int iy = iy_base + r, ix = xp - p.pad;
-    const bool ok = vl < nv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-    const bf16* src = ok ? in_n + (static_cast<size_t>(iy) * p.W + ix) * p.C + vl * 8 : p.in;
-    cp_async16(sx + i, src, ok);
+  if constexpr (TMA) {
+    if (tid == 0) {
+      ptx::mbar_init(&bar, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>((KS * KS + p.R * p.Wp) * p.CVc) * 16u);
+      ptx::tma_load_2d(sw, &tmw, &bar, v0 * 8, 0);
+      ptx::tma_load_4d(sx, &tmx, &bar, v0 * 8, -p.pad, iy_base, n);
+    }
+    ptx::mbar_wait(&bar, 0);
+  } else {
+    const int rows = (oy1 - oy0 - 1) * STRIDE + (KS - 1) * DIL + 1;
+    const bf16* in_n = p.in + static_cast<size_t>(n) * p.H * p.W * p.C + v0 * 8;
+    const int per_row = p.Wp * p.CVc;
+    for (int i = tid; i < rows * per_row; i += 256) {
+      const int r = i / per_row, rem = i - r * per_row;
+      const int xp = rem / p.CVc, vl = rem - xp * p.CVc;
+      const int iy = iy_base + r, ix = xp - p.pad;
+      const bool ok = vl < nv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      const bf16* src = ok ? in_n + (static_cast<size_t>(iy) * p.W + ix) * p.C + vl * 8 : p.in;
+      cp_async16(sx + i, src, ok);
+    }
+    for (int i = tid; i < KS * KS * p.CVc; i += 256) {
+      const int t = i / p.CVc, vl = i - t * p.CVc;
+      const bool ok = vl < nv;
+      cp_async16(sw + i, ok ? p.w + t * p.C + (v0 + vl) * 8 : p.w, ok);
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
-  for (int i = tid; i < KS * KS * p.CVc; i += 256) {
-    const int t = i / p.CVc, vl = i - t * p.CVc;
-    const bool ok = vl < nv;
-    cp_async16(sw + i, ok ? p.w + t * p.C + (v0 + vl) * 8 : p.w, ok);
-  }
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
   // ---- phase 2: compute ----
   const int vl = tid % p.CVc, pl = tid / p.CVc;
   const bool active = pl < p.PL && vl < nv;
@@ -216,33 +261,38 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const DwS p) {
 #pragma unroll
           for (int kx = 0; kx < KS; ++kx) {
             const int t = xi - kx * DIL;  // compile-time after unrolling
-            if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) {
+            if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) fma8<F2>(acc[t / STRIDE], xf, wv[kx]);
+          }
+        }
+      }
+      // the activation is uniform over the launch: pick it once per strip, not once per element
+      auto finish = [&](auto actf) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[t / STRIDE][j] = fmaf(xf[j], wv[kx][j], acc[t / STRIDE][j]);
+        for (int t = 0; t < TW; ++t) {
+          if (ox0 + t < p.Wo) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = actf(fmaf(acc[t][j], sc[j], sh[j]));
+            const uint4 packed = pack8(o);
+            *reinterpret_cast<uint4*>(out_n + (static_cast<size_t>(oy0 + ry) * p.Wo + ox0 + t) * p.C) = packed;
+            if (p.gap) {
+              float rf[8];
+              unpack8(packed, rf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc_gap[j] += rf[j];
             }
           }
         }
-      }
-#pragma unroll
-      for (int t = 0; t < TW; ++t) {
-        if (ox0 + t < p.Wo) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = apply_act(fmaf(acc[t][j], sc[j], sh[j]), p.act);
-          const uint4 packed = pack8(o);
-          *reinterpret_cast<uint4*>(out_n + (static_cast<size_t>(oy0 + ry) * p.Wo + ox0 + t) * p.C) = packed;
-          if (p.gap) {
-            float rf[8];
-            unpack8(packed, rf);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc_gap[j] += rf[j];
-          }
-        }
-      }
+      };
+      if (p.act == ACT_HSWISH) finish([](float v) { return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f); });
+      else if (p.act == ACT_RELU) finish([](float v) { return fmaxf(v, 0.f); });
+      else if (p.act == ACT_NONE) finish([](float v) { return v; });
+      else finish([&](float v) { return apply_act(v, p.act); });
     }
   }
   if (p.gap) {
     const int cw = p.CVc * 8;
+    __syncthreads();  // every thread is done with the staged tile: its first 8 KB become the reduction buffer
     if (pl < p.PL) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) red[(pl * p.CVc + vl) * 8 + j] = active ? acc_gap[j] : 0.f;
@@ -259,7 +309,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const DwS p) {
   }
 }
 
-// MTGSEG_DW_VARIANT: 0 (default) shared-memory staged kernel; 2 legacy direct kernel, narrow strips; 1 legacy, wide strips
+// MTGSEG_DW_VARIANT (A/B switch): 0 (default) staged kernel, TMA box fill, packed fp32x2 FMAs; 4 = 0 with scalar FMAs; 3 staged kernel,
+// cp.async gather fill, scalar FMAs; 5 = 3 with packed FMAs (all four bit-identical; B=256 family time 1.57 / 1.58 / 2.03 / 2.03 ms); 2 legacy direct kernel, narrow strips; 1 legacy direct kernel, wide strips
 int dw_variant() {
   static int v = -1;
   if (v < 0) {
@@ -283,7 +334,7 @@ int group_vectors(int CV) {
   return best;
 }
 
-struct DwPlan { int pad, Ho, Wo, CV, CVc, PL, TW, strips, band, bands, R, Wp; size_t smem; bool ok; };
+struct DwPlan { int pad, Ho, Wo, CV, CVc, PL, TW, strips, band, bands, R, Wp, xoff; size_t smem; bool ok; };
 
 DwPlan dw_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
   DwPlan q{};
@@ -297,8 +348,11 @@ DwPlan dw_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
   const int NI = (q.TW - 1) * stride + (k - 1) * dil + 1;
   q.Wp = (q.strips - 1) * q.TW * stride + NI;
   if (q.Wp < W + 2 * q.pad) q.Wp = W + 2 * q.pad;
+  // two CTAs per SM: 2 x (108 KB + 1 KB reserved) fits the 227 KB of an SM (the kernel has no static shared memory
+  // besides one mbarrier; the SE-pool reduction reuses the tile)
   const size_t budget = 108 * 1024;
-  const size_t wbytes = static_cast<size_t>(k) * k * q.CVc * 16;
+  q.xoff = (k * k * q.CVc + 7) / 8 * 8;  // weights first, the input tile starts 128-byte aligned (TMA destination)
+  const size_t wbytes = static_cast<size_t>(q.xoff) * 16;
   auto bytes = [&](int band) { return (static_cast<size_t>((band - 1) * stride + (k - 1) * dil + 1) * q.Wp * q.CVc) * 16 + wbytes; };
   q.ok = bytes(1) <= budget;
   int band = 1;
@@ -309,7 +363,7 @@ DwPlan dw_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
   band = ceil_div(q.Ho, bands);  // even bands
   q.band = band; q.bands = ceil_div(q.Ho, band);
   q.R = (band - 1) * stride + (k - 1) * dil + 1;
-  q.smem = bytes(band);
+  q.smem = bytes(band) < 8192 ? 8192 : bytes(band);  // >= the 8 KB reduction buffer
   return q;
 }
 
@@ -326,16 +380,44 @@ int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap
   return dw_plan(H, W, C, k, stride, dil, need_gap).bands;
 }
 
-template <int KS, int STRIDE, int DIL, int TW>
-int launch_smem(const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
+template <int KS, int STRIDE, int DIL, int TW, bool TMA, bool F2>
+int launch_smem2(const CUtensorMap& tmx, const CUtensorMap& tmw, const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    MTG_CUDA(cudaFuncSetAttribute(dwconv_smem_kernel<KS, STRIDE, DIL, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    MTG_CUDA(cudaFuncSetAttribute(dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  dwconv_smem_kernel<KS, STRIDE, DIL, TW><<<grid, 256, smem, st>>>(p);
+  dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2><<<grid, 256, smem, st>>>(tmx, tmw, p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
+}
+
+template <int KS, int STRIDE, int DIL, int TW>
+int launch_smem(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
+  const int v = dw_variant();
+  CUtensorMap tmx{}, tmw{};
+  if (v == 0 || v == 4) {
+    // input [B][H][W][C] bf16 as a 4-D tensor, box = (group channels, padded row, band rows + halo, 1 image);
+    // weights [k*k][C] as a 2-D tensor, box = (group channels, all taps).  No swizzle: the tile is read as stored.
+    const unsigned long long xd[4] = {static_cast<unsigned long long>(a.C), static_cast<unsigned long long>(a.W),
+                                      static_cast<unsigned long long>(a.H), static_cast<unsigned long long>(a.B)};
+    const unsigned long long xs[3] = {xd[0] * 2, xd[0] * xd[1] * 2, xd[0] * xd[1] * xd[2] * 2};
+    const unsigned xb[4] = {static_cast<unsigned>(p.CVc * 8), static_cast<unsigned>(p.Wp), static_cast<unsigned>(p.R), 1u};
+    MTG_REQUIRE(xb[1] <= 256 && xb[2] <= 256, MTG_ERR_UNSUPPORTED, "dwconv: tile %ux%u exceeds the TMA box limit", xb[1], xb[2]);
+    int rc = make_tma_map_bf16(&tmx, a.in, 4, xd, xs, xb, 0);
+    if (rc != MTG_OK) return rc;
+    const unsigned long long wd[2] = {static_cast<unsigned long long>(a.C), static_cast<unsigned long long>(KS * KS)};
+    const unsigned long long ws[1] = {wd[0] * 2};
+    const unsigned wb[2] = {static_cast<unsigned>(p.CVc * 8), static_cast<unsigned>(KS * KS)};
+    rc = make_tma_map_bf16(&tmw, a.w, 2, wd, ws, wb, 0);
+    if (rc != MTG_OK) return rc;
+  }
+  switch (v) {
+    case 0: return launch_smem2<KS, STRIDE, DIL, TW, true, true>(tmx, tmw, p, grid, smem, st);
+    case 4: return launch_smem2<KS, STRIDE, DIL, TW, true, false>(tmx, tmw, p, grid, smem, st);
+    case 5: return launch_smem2<KS, STRIDE, DIL, TW, false, true>(tmx, tmw, p, grid, smem, st);
+    default: return launch_smem2<KS, STRIDE, DIL, TW, false, false>(tmx, tmw, p, grid, smem, st);
+  }
 }
 
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
@@ -346,14 +428,14 @@ int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
     MTG_REQUIRE(q.ok, MTG_ERR_UNSUPPORTED, "dwconv: feature map %dx%d (C=%d, k=%d) does not fit the shared-memory tiling", a.H, a.W, a.C, a.k);
     MTG_REQUIRE(!a.gap_partial || a.chunks == q.bands, MTG_ERR_ARG, "dwconv: gap_partial must have mtgseg_dwconv_chunks() = %d chunks, got %d", q.bands, a.chunks);
     DwS s{a.in, a.w, a.out, a.scale, a.shift, a.gap_partial, a.act, a.H, a.W, a.C, q.Ho, q.Wo, q.pad, q.CV, q.CVc, q.PL, q.strips,
-          q.band, q.bands, q.R, q.Wp};
+          q.band, q.bands, q.R, q.Wp, q.xoff};
     dim3 grid(q.bands, ceil_div(q.CV, q.CVc), a.B);
     switch (a.k * 100 + a.stride * 10 + a.dil) {
-      case 311: return launch_smem<3, 1, 1, 4>(s, grid, q.smem, st);
-      case 321: return launch_smem<3, 2, 1, 2>(s, grid, q.smem, st);
-      case 511: return launch_smem<5, 1, 1, 4>(s, grid, q.smem, st);
-      case 521: return launch_smem<5, 2, 1, 2>(s, grid, q.smem, st);
-      case 512: return launch_smem<5, 1, 2, 4>(s, grid, q.smem, st);
+      case 311: return launch_smem<3, 1, 1, 4>(a, s, grid, q.smem, st);
+      case 321: return launch_smem<3, 2, 1, 2>(a, s, grid, q.smem, st);
+      case 511: return launch_smem<5, 1, 1, 4>(a, s, grid, q.smem, st);
+      case 521: return launch_smem<5, 2, 1, 2>(a, s, grid, q.smem, st);
+      case 512: return launch_smem<5, 1, 2, 4>(a, s, grid, q.smem, st);
       default:
         MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: (k=%d, stride=%d, dilation=%d) is not one of the MobileNetV3 shapes", a.k, a.stride, a.dil);
     }

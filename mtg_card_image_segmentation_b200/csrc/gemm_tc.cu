@@ -375,7 +375,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes for dims 1..
+// bf16 tensor map, zero OOB fill; swizzle by kbox: 64 -> 128 B, 32 -> 64 B, 16 -> 32 B, 0 -> none (dense box, used by the
+// depthwise tiles).  dims/strides innermost first; strides in bytes for dims 1..
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box, int kbox = 64) {
   EncodeTiledFn fn = get_encode_fn();
@@ -391,7 +392,8 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  kbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                  kbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                             : (kbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (kbox == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MTG_REQUIRE(r == CUDA_SUCCESS, MTG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu)",
@@ -401,7 +403,7 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
 
 }  // namespace
 
-// shared with wgrad_tc.cu
+// shared with wgrad_tc.cu and dwconv.cu
 int make_tma_map_bf16(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
                       const unsigned long long* strides_bytes, const unsigned* box, int kbox) {
   uint64_t d[5], s[4];
