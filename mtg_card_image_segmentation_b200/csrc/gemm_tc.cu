@@ -22,6 +22,8 @@
 // tv:models/mobilenetv3.py:71-80,101-105,179-187 and the head's 3x3 (train/model.py:110), with the
 // eval-mode BatchNorm + activation (+ residual, tv:models/mobilenetv3.py:111-115) fused in the epilogue.
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -59,6 +61,19 @@ struct GemmKParams {
   int B, H, W, HB, NB, h_tiles;
   signed char tap_dy[9], tap_dx[9];
 };
+
+// acc[0..7] = x[0..7] * w[0..7] + acc[0..7] as four packed fp32x2 FMAs (FFMA2)
+__device__ __forceinline__ void fma8_f2(float (&acc)[8], const float (&x)[8], const float (&w)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    uint64_t a, xv, wv;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(acc[j]), "f"(acc[j + 1]));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(xv) : "f"(x[j]), "f"(x[j + 1]));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(wv) : "f"(w[j]), "f"(w[j + 1]));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xv), "l"(wv));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(acc[j]), "=f"(acc[j + 1]) : "l"(a));
+  }
+}
 
 template <bool kConv3x3, bool kAScale>
 __global__ void __launch_bounds__(kAScale ? 448 : 320, kAScale ? 1 : 2)
@@ -245,31 +260,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tmem_ld16(taddr + sl * OB + half * 32, v[0]);
           if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * OB + half * 32 + 16, v[1]);
           ptx::tmem_ld_wait();
+          // the activation is uniform over the launch: dispatch once per slab, not once per element
+          auto convert = [&](auto actf) {
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            if (half * 32 + cc * 16 < cols) {
+            for (int cc = 0; cc < 2; ++cc) {
+              if (half * 32 + cc * 16 < cols) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the slab row
-                const int c = sl * OB + chunk * 8;             // column inside the N tile
-                const int phys = (chunk ^ rx) * 16;            // TMA swizzle of the staging slab
-                const float4 s0 = *reinterpret_cast<const float4*>(sScale + c), s1 = *reinterpret_cast<const float4*>(sScale + c + 4);
-                const float4 h0 = *reinterpret_cast<const float4*>(sShift + c), h1 = *reinterpret_cast<const float4*>(sShift + c + 4);
-                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                float f[8];
+                for (int h = 0; h < 2; ++h) {
+                  const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the slab row
+                  const int c = sl * OB + chunk * 8;             // column inside the N tile
+                  const int phys = (chunk ^ rx) * 16;            // TMA swizzle of the staging slab
+                  const float4 s0 = *reinterpret_cast<const float4*>(sScale + c), s1 = *reinterpret_cast<const float4*>(sScale + c + 4);
+                  const float4 h0 = *reinterpret_cast<const float4*>(sShift + c), h1 = *reinterpret_cast<const float4*>(sShift + c + 4);
+                  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                  float f[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                  float a[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = apply_act(fmaf(__uint_as_float(v[cc][h * 8 + e]), sc[e], sh[e]), p.act);
-                if (p.res_slabs) {
-                  float rf[8];
-                  unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
+                  for (int e = 0; e < 8; ++e) a[e] = __uint_as_float(v[cc][h * 8 + e]);
+                  fma8_f2(f, a, sc);  // f = acc * scale + shift, four packed fp32x2 FMAs
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                  for (int e = 0; e < 8; ++e) f[e] = actf(f[e]);
+                  if (p.res_slabs) {
+                    float rf[8];
+                    unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                  }
+                  *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
                 }
-                *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
               }
             }
-          }
+          };
+          // hardswish as z * sat(z/6 + 1/2): one FFMA.SAT + one FMUL instead of add / max / min / mul / mul
+          if (p.act == ACT_HSWISH) convert([](float z) { return z * __saturatef(fmaf(z, 1.f / 6.f, 0.5f)); });
+          else if (p.act == ACT_RELU) convert([](float z) { return fmaxf(z, 0.f); });
+          else if (p.act == ACT_NONE) convert([](float z) { return z; });
+          else convert([&](float z) { return apply_act(z, p.act); });
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -434,9 +460,22 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     configured = true;
   }
   const int threads = AS ? 448 : 320;
-  // co-resident CTAs per SM: what registers + shared memory allow, capped so that all TMEM allocations fit
-  int per_sm = 1;
-  MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_gemm_kernel<C3, AS>, threads, need));
+  // co-resident CTAs per SM from the kernel's own resource use: registers (allocated in units of 8 per thread), shared
+  // memory (+1 KB reserved per CTA), threads, and TMEM columns (all allocations must fit the 512 columns of an SM).
+  // cudaOccupancyMaxActiveBlocksPerMultiprocessor is NOT used: on this driver it answers 1 for this kernel for every
+  // block size / shared-memory request (measured on a B200, even 256 threads and 0 bytes), while two CTAs do run
+  // concurrently (29-31 % warps active under ncu with a 296-CTA grid).
+  static int regs_per_thread = 0;  // per template instantiation
+  if (regs_per_thread == 0) {
+    cudaFuncAttributes fa{};
+    MTG_CUDA(cudaFuncGetAttributes(&fa, conv_gemm_kernel<C3, AS>));
+    regs_per_thread = fa.numRegs > 0 ? (fa.numRegs + 7) / 8 * 8 : 128;
+  }
+  int per_sm = 65536 / (regs_per_thread * threads);
+  const int by_smem = static_cast<int>((227 * 1024) / (need + 1024));
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  const int occ_raw = per_sm;
   if (per_sm > 512 / kp.tmem_cols) per_sm = 512 / kp.tmem_cols;
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
@@ -452,6 +491,17 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     grid = grid / kp.n_tiles * kp.n_tiles;
     if (grid < kp.n_tiles) grid = kp.n_tiles;
   }
+  static const bool debug = getenv("MTGSEG_GEMM_DEBUG") != nullptr;
+  if (debug) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, conv_gemm_kernel<C3, AS>);
+    fprintf(stderr, "[conv_gemm<%d,%d>] occ_raw=%d regs=%d static_smem=%zu local=%zu max_threads=%d max_dyn=%d\n", int(C3), int(AS), occ_raw,
+            fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
+  }
+  if (debug)
+    fprintf(stderr, "[conv_gemm<%d,%d>] M=%d N=%d K=%d BN=%d kbox=%d obox=%d num_kb=%d stages=%d b_res=%d res_slabs=%d tmem=%d need=%zu smem=%zu per_sm=%d grid=%d tiles=%lld\n",
+            int(C3), int(AS), kp.M, kp.N, kp.K, kp.BN, kp.kbox, kp.obox, kp.num_kb, kp.stages, kp.b_res, kp.res_slabs, kp.tmem_cols, need, smem,
+            per_sm, grid, total_tiles);
   conv_gemm_kernel<C3, AS><<<grid, threads, smem, st>>>(tmA, tmB, tmO, tmR, kp);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
