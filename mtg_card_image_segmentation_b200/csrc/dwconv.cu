@@ -319,6 +319,7 @@ int dw_variant() {
   }
   return v;
 }
+// 8-wide strips for the stride-1 5x5 layers were measured and rejected: 128 registers spill (b14 213 -> 317 us)
 inline int strip_width(int stride) { return dw_variant() != 1 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
 
 }  // namespace

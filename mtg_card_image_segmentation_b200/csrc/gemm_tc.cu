@@ -56,6 +56,7 @@ struct GemmKParams {
   const float* a_scale;
   int hw;
   int res_slabs;  // 0 or ceil(BN/obox)
+  int res_bufs;   // 2: residual tile prefetched one tile ahead; 1: single buffer, reloaded after the epilogue has read it (long mainloops)
   int obox;       // output / residual slab width in channels: 64 / 32 / 16 <-> 128B / 64B / 32B swizzled rows
   // multi-tap (3x3 / transposed-conv parity) geometry: A boxes {64 ch, W, HB rows, NB images} shifted by (dx, dy) per tap
   int B, H, W, HB, NB, h_tiles;
@@ -92,8 +93,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = sA + S * A_STAGE_BYTES;
   uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + (p.b_res ? 0 : S * b_stage_bytes)) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
   const int SLAB_BYTES = BM * p.obox * 2;
-  uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // 2 x res_slabs slabs
-  float* sScale = reinterpret_cast<float*>(sRes + 2 * p.res_slabs * SLAB_BYTES);
+  uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // res_bufs x res_slabs slabs
+  float* sScale = reinterpret_cast<float*>(sRes + p.res_bufs * p.res_slabs * SLAB_BYTES);
   float* sShift = sScale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + SS_BYTES);
   uint64_t* full = bars;
@@ -229,10 +230,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         oc2 = (m_tile % p.h_tiles) * p.HB;
         oc3 = (m_tile / p.h_tiles) * p.NB;
       }
-      const uint32_t rb = tc & 1;
+      const uint32_t rb = p.res_bufs == 2 ? (tc & 1) : 0;
       // prefetch the NEXT tile's residual into the other buffer (its last readers finished before the final
       // bar.sync of the previous iteration)
-      if (p.res_slabs && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, rb ^ 1);
+      if (p.res_slabs && p.res_bufs == 2 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, rb ^ 1);
       if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
         cur_ntile = n_tile;
         for (int c = et; c < p.BN; c += 256) {
@@ -243,7 +244,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       ptx::mbar_wait(&tfull[buf], aph);
       ptx::tc_fence_after();
-      if (p.res_slabs) ptx::mbar_wait(&resbar[rb], (tc >> 1) & 1);
+      if (p.res_slabs) ptx::mbar_wait(&resbar[rb], p.res_bufs == 2 ? ((tc >> 1) & 1) : (tc & 1));
       const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
       for (int sl = 0; sl < slabs; ++sl, ++store_no) {
         uint8_t* sbuf = sOut + (store_no & 1) * SLAB_BYTES;
@@ -306,6 +307,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::bulk_commit();
         }
       }
+      // single residual buffer: every epilogue thread passed the last bar.sync after its final read of the tile (and
+      // executed fence.proxy.async before it), so the buffer may be refilled now; the next mainloop hides the load
+      if (p.res_slabs && p.res_bufs == 1 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, 0);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[buf]);
     }
@@ -314,26 +318,53 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== squeeze-excite prologue on the A tile ===============================
     const int t = threadIdx.x - 320;
     const int chunk = t & 7;  // physical 16-byte chunk inside the 128-byte row
+    // this thread's 16-byte chunk holds the same 8 logical channels in every row it touches (rows differ by 16, the
+    // swizzle only looks at row % 8), and a 128-row tile spans at most two images when hw >= 128: the (at most two)
+    // gate vectors of a stage are fetched ONE STAGE AHEAD into registers, so their global-load latency is hidden behind
+    // the previous stage instead of sitting between "A tile landed" and "MMA may start"
+    const int kofs = (chunk ^ ((t >> 3) & 7)) << 3;
+    const bool fast = p.hw >= BM;
+    float na[8], nb[8];
+    int nsplit = 0;  // rows are indexed in 32 bits here: M is an int and a tile starts below M
+    auto fetch = [&](int tile, int kb) {
+      const int k = kb * BK + kofs;
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int img0 = m0 / p.hw;
+      nsplit = (img0 + 1) * p.hw;  // first row index of the next image
+      if (fast && k < p.K) {
+        const float* sp = p.a_scale + static_cast<size_t>(img0) * p.K + k;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sp)), a1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+        na[0] = a0.x; na[1] = a0.y; na[2] = a0.z; na[3] = a0.w; na[4] = a1.x; na[5] = a1.y; na[6] = a1.z; na[7] = a1.w;
+        const bool two = nsplit < m0 + BM && nsplit < p.M;
+        const float* sq = two ? sp + p.K : sp;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(sq)), b1 = __ldg(reinterpret_cast<const float4*>(sq + 4));
+        nb[0] = b0.x; nb[1] = b0.y; nb[2] = b0.z; nb[3] = b0.w; nb[4] = b1.x; nb[5] = b1.y; nb[6] = b1.z; nb[7] = b1.w;
+      }
+    };
+    if (static_cast<int>(blockIdx.x) < total_tiles) fetch(blockIdx.x, 0);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
+      const int m0 = m_tile * BM;
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
+        float sa[8], sb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sa[e] = na[e]; sb[e] = nb[e]; }
+        const int split = nsplit;
+        {
+          int ntile = tile, nkb = kb + 1;
+          if (nkb == p.num_kb) { nkb = 0; ntile = tile + gridDim.x; }
+          if (ntile < total_tiles) fetch(ntile, nkb);
+        }
         ptx::mbar_wait(&full[s], ph);
         uint8_t* base = sA + s * A_STAGE_BYTES;
-        // this thread's 16-byte chunk holds the same 8 logical channels in every row it touches (rows differ by 16,
-        // the swizzle only looks at row % 8), and a 128-row tile spans at most two images when hw >= 128: fetch the
-        // (at most two) gate vectors once per stage, then the row loop is pure shared-memory work
-        const int k = kb * BK + ((chunk ^ ((t >> 3) & 7)) << 3);
-        const long long m0 = static_cast<long long>(m_tile) * BM;
-        const int img0 = static_cast<int>(m0 / p.hw);
-        const long long split = static_cast<long long>(img0 + 1) * p.hw;  // first row index of the next image
-        float sa[8], sb[8];
-        if (k < p.K && p.hw < BM) {  // tiny feature maps (tests): a tile may span many images, fetch the gate per row
+        const int k = kb * BK + kofs;
+        if (k < p.K && !fast) {  // tiny feature maps (tests): a tile may span many images, fetch the gate per row
           for (int j = 0; j < 8; ++j) {
             const int row = (t >> 3) + 16 * j;
-            const long long m = m0 + row;
+            const int m = m0 + row;
             if (m < p.M) {
               const float* sp = p.a_scale + static_cast<size_t>(m / p.hw) * p.K + k;
               uint4* ptr = reinterpret_cast<uint4*>(base + row * 128 + chunk * 16);
@@ -345,17 +376,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else if (k < p.K) {
-          const float* sp = p.a_scale + static_cast<size_t>(img0) * p.K + k;
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(sp)), a1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
-          sa[0] = a0.x; sa[1] = a0.y; sa[2] = a0.z; sa[3] = a0.w; sa[4] = a1.x; sa[5] = a1.y; sa[6] = a1.z; sa[7] = a1.w;
-          const bool two = split < m0 + BM && split < p.M;
-          const float* sq = two ? sp + p.K : sp;
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(sq)), b1 = __ldg(reinterpret_cast<const float4*>(sq + 4));
-          sb[0] = b0.x; sb[1] = b0.y; sb[2] = b0.z; sb[3] = b0.w; sb[4] = b1.x; sb[5] = b1.y; sb[6] = b1.z; sb[7] = b1.w;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int row = (t >> 3) + 16 * j;
-            const long long m = m0 + row;
+            const int m = m0 + row;
             if (m < p.M) {
               uint4* ptr = reinterpret_cast<uint4*>(base + row * 128 + chunk * 16);
               float f[8];
@@ -499,8 +523,8 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
             fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
   }
   if (debug)
-    fprintf(stderr, "[conv_gemm<%d,%d>] M=%d N=%d K=%d BN=%d kbox=%d obox=%d num_kb=%d stages=%d b_res=%d res_slabs=%d tmem=%d need=%zu smem=%zu per_sm=%d grid=%d tiles=%lld\n",
-            int(C3), int(AS), kp.M, kp.N, kp.K, kp.BN, kp.kbox, kp.obox, kp.num_kb, kp.stages, kp.b_res, kp.res_slabs, kp.tmem_cols, need, smem,
+    fprintf(stderr, "[conv_gemm<%d,%d>] M=%d N=%d K=%d BN=%d kbox=%d obox=%d num_kb=%d stages=%d b_res=%d res_slabs=%d res_bufs=%d tmem=%d need=%zu smem=%zu per_sm=%d grid=%d tiles=%lld\n",
+            int(C3), int(AS), kp.M, kp.N, kp.K, kp.BN, kp.kbox, kp.obox, kp.num_kb, kp.stages, kp.b_res, kp.res_slabs, kp.res_bufs, kp.tmem_cols, need, smem,
             per_sm, grid, total_tiles);
   conv_gemm_kernel<C3, AS><<<grid, threads, smem, st>>>(tmA, tmB, tmO, tmR, kp);
   MTG_LAUNCH_CHECK();
@@ -631,7 +655,9 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   const size_t b_res_bytes = kp.b_res ? align_up(kp.num_kb * b_tile_bytes, 1024) : 0;
   const int stage_bytes = A_STAGE_BYTES + (kp.b_res ? 0 : kp.BN * BK * 2);
   const size_t slab_bytes = static_cast<size_t>(BM) * kp.obox * 2;
-  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * slab_bytes + 2 * static_cast<size_t>(kp.res_slabs) * slab_bytes + SS_BYTES + BAR_BYTES + b_res_bytes;
+  // a long mainloop (>= 6 k-blocks) hides the reload of a single residual buffer; the 48-96 KB saved become ring stages
+  kp.res_bufs = (kp.res_slabs && kp.num_kb >= 6) ? 1 : 2;
+  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * slab_bytes + static_cast<size_t>(kp.res_bufs) * kp.res_slabs * slab_bytes + SS_BYTES + BAR_BYTES + b_res_bytes;
   // ring depth: enough stages that two co-resident CTAs keep >= ~64 KB of loads in flight per SM (HBM latency x bandwidth)
   int stages = kp.num_kb >= 8 ? 6 : 4;
   if (stage_bytes <= 16 * 1024) stages = 8;

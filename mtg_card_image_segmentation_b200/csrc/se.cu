@@ -3,6 +3,8 @@
 // head's scale branch (train/model.py:115-119: GAP -> 1x1 conv (no bias) -> Sigmoid).
 // These are latency-bound (a few hundred kFLOP per image); the design goal is few launches and no
 // re-read of the big activation: the depthwise kernel already produced the channel sums.
+#include <stdlib.h>
+
 #include "ops.h"
 
 namespace mtgseg {
@@ -111,6 +113,105 @@ __global__ void __launch_bounds__(256) fc_batched_kernel(const FcP p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused squeeze-excite MLP: one launch per SE block.  A CTA owns SE_IMGS images: it sums the depthwise kernel's pool
+// partials into shared memory, computes hidden = act1(W1 mean + b1) into shared memory and gate = act2(W2 hidden + b2)
+// into global memory.  Warp-per-output-group with coalesced 16-byte weight loads, as in fc_batched_kernel; the
+// weights (<= 460 KB per layer) are served by L2 to the B/SE_IMGS CTAs.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SE_IMGS = 4;
+constexpr int SE_THREADS = 512;
+
+struct SeP {
+  const float* sums; int chunks; float in_scale;  // [B][chunks][C]
+  int B, C, SQ;
+  const bf16* w1; const float* b1; int act1;  // [SQ][C]
+  const bf16* w2; const float* b2; int act2;  // [C][SQ] or null (single-layer form: out is [B][SQ])
+  float* out; float* hidden;                  // hidden [B][SQ] optional copy for the training backward
+};
+
+// y[i][o] = act(sum_c w[o][c] * x[i][c] + bias[o]) for the CTA's SE_IMGS images; x in shared memory [SE_IMGS][I]
+template <typename Store>
+__device__ __forceinline__ void se_fc(const float* x, int I, const bf16* __restrict__ w, const float* __restrict__ bias, int O, int act,
+                                      Store store) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = SE_THREADS / 32;
+  for (int o0 = warp * 4; o0 < O; o0 += nwarps * 4) {
+    float acc[4][SE_IMGS];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int i = 0; i < SE_IMGS; ++i) acc[a][i] = 0.f;
+    for (int c = lane * 8; c < I; c += 256) {
+      float wf[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (o0 + a < O) unpack8(ldg16(w + static_cast<size_t>(o0 + a) * I + c), wf[a]);
+        else
+#pragma unroll
+          for (int e = 0; e < 8; ++e) wf[a][e] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < SE_IMGS; ++i) {
+        const float4 x0 = *reinterpret_cast<const float4*>(x + i * I + c);
+        const float4 x1 = *reinterpret_cast<const float4*>(x + i * I + c + 4);
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[a][i] = fmaf(wf[a][e], xv[e], acc[a][i]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int i = 0; i < SE_IMGS; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[a][i] += __shfl_xor_sync(0xffffffffu, acc[a][i], o);
+    // lane (a * SE_IMGS + i) finishes output a of image i
+    const int a_sel = lane / SE_IMGS, i_sel = lane % SE_IMGS;
+    float v = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int i = 0; i < SE_IMGS; ++i)
+        if (a == a_sel && i == i_sel) v = acc[a][i];
+    if (lane < 4 * SE_IMGS && o0 + a_sel < O) store(i_sel, o0 + a_sel, apply_act(v + (bias ? bias[o0 + a_sel] : 0.f), act));
+  }
+}
+
+__global__ void __launch_bounds__(SE_THREADS) se_fused_kernel(const SeP p) {
+  extern __shared__ float se_smem[];
+  float* xin = se_smem;                   // [SE_IMGS][C]
+  float* hid = se_smem + SE_IMGS * p.C;   // [SE_IMGS][SQ]
+  const int n0 = blockIdx.x * SE_IMGS;
+  for (int i = 0; i < SE_IMGS; ++i) {
+    const bool ok = n0 + i < p.B;
+    const float* src = p.sums + static_cast<size_t>(ok ? n0 + i : 0) * p.chunks * p.C;
+    for (int c = threadIdx.x; c < p.C; c += SE_THREADS) {
+      float s = 0.f;
+      if (ok)
+        for (int k = 0; k < p.chunks; ++k) s += src[k * p.C + c];
+      xin[i * p.C + c] = s * p.in_scale;
+    }
+  }
+  __syncthreads();
+  if (p.w2) {
+    se_fc(xin, p.C, p.w1, p.b1, p.SQ, p.act1, [&](int i, int o, float v) {
+      hid[i * p.SQ + o] = v;
+      if (p.hidden && n0 + i < p.B) p.hidden[static_cast<size_t>(n0 + i) * p.SQ + o] = v;
+    });
+    __syncthreads();
+    se_fc(hid, p.SQ, p.w2, p.b2, p.C, p.act2, [&](int i, int o, float v) {
+      if (n0 + i < p.B) p.out[static_cast<size_t>(n0 + i) * p.C + o] = v;
+    });
+  } else {
+    se_fc(xin, p.C, p.w1, p.b1, p.SQ, p.act1, [&](int i, int o, float v) {
+      if (n0 + i < p.B) p.out[static_cast<size_t>(n0 + i) * p.SQ + o] = v;
+    });
+  }
+}
+
 }  // namespace
 
 int launch_gap(const bf16* in, float* out, int B, int HW, int C, cudaStream_t st) {
@@ -127,6 +228,14 @@ int launch_se_mlp(const SeMlpArgs& a, cudaStream_t st) {
   MTG_REQUIRE(!a.w2 || a.hidden, MTG_ERR_ARG, "se_mlp: the two-layer form needs a hidden scratch buffer [B][SQ]");
   const int cmax = a.C > a.SQ ? a.C : a.SQ;
   MTG_REQUIRE(static_cast<size_t>(FC_IMGS) * cmax * sizeof(float) <= 48 * 1024, MTG_ERR_UNSUPPORTED, "se_mlp: C too large");
+  static const bool two_launch = getenv("MTGSEG_SE_VARIANT") && atoi(getenv("MTGSEG_SE_VARIANT")) == 1;  // A/B switch
+  const size_t fused_smem = static_cast<size_t>(SE_IMGS) * (a.C + a.SQ) * sizeof(float);
+  if (!two_launch && fused_smem <= 48 * 1024) {
+    SeP sp{a.sums, a.chunks, 1.0f / static_cast<float>(a.HW), a.B, a.C, a.SQ, a.w1, a.b1, a.act1, a.w2, a.b2, a.act2, a.out, a.w2 ? a.hidden : nullptr};
+    se_fused_kernel<<<ceil_div(a.B, SE_IMGS), SE_THREADS, fused_smem, st>>>(sp);
+    MTG_LAUNCH_CHECK();
+    return MTG_OK;
+  }
   FcP l1{a.sums, a.chunks, 1.0f / static_cast<float>(a.HW), a.B, a.C, a.SQ, a.w1, a.b1, a.act1, a.w2 ? a.hidden : a.out};
   dim3 g1(ceil_div(a.SQ, FC_OUTS), ceil_div(a.B, FC_IMGS));
   fc_batched_kernel<<<g1, 256, static_cast<size_t>(FC_IMGS) * a.C * sizeof(float), st>>>(l1);
