@@ -1,8 +1,8 @@
 // Stem: dense 3x3 stride-2 convolution 3 -> 16 channels + folded BatchNorm + Hardswish, reading the
 // reference's fp32 NCHW batch (train/dataset.py:84-88 contract) and writing NHWC bf16.
 // K = 27 is far too small for the tensor cores to matter; the layer is bound by reading the image
-// (12 B/pixel) and writing 32 B per output pixel, so it is a direct convolution: one thread per output
-// pixel, all 16 output channels in registers, weights broadcast from shared memory.
+// (12 B/pixel) and writing 32 B per output pixel, so it is a direct convolution: one thread per pair of output
+// pixels, all 16 output channels of both in registers, weights broadcast from shared memory.
 // Replaces features[0] of tv:models/mobilenetv3.py:160-170.
 #include "ops.h"
 
@@ -21,27 +21,33 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   for (int i = threadIdx.x; i < 27 * 4; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
   if (threadIdx.x < 16) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
-  const long long total = static_cast<long long>(B) * Ho * Wo;
+  // one thread = two horizontally adjacent output pixels: the 3x3 stride-2 windows share a column (45 instead of 54
+  // input values) and every weight quad read from shared memory feeds both pixels; the FMAs are issued as packed
+  // fp32x2 over output-channel pairs (FFMA2), the input value broadcast into both halves.
+  const int Wp = (Wo + 1) >> 1;  // pixel pairs per output row
+  const long long total = static_cast<long long>(B) * Ho * Wp;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ox = static_cast<int>(idx % Wo);
-    const long long t = idx / Wo;
+    const int oxp = static_cast<int>(idx % Wp);
+    const long long t = idx / Wp;
     const int oy = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
-    // gather the 27 taps first (predicated, no branches between them: all loads are in flight together)
-    float xin[27];
+    const int ox = oxp * 2;
+    const bool second = ox + 1 < Wo;
+    // gather the 45 taps first (predicated, no branches between them: all loads are in flight together)
+    float xin[3][3][5];
     if (kU8) {
       const uint8_t* xn = xu8 + static_cast<size_t>(n) * H * W * 3;
       const float mul[3] = {nmul.x, nmul.y, nmul.z}, add[3] = {nadd.x, nadd.y, nadd.z};
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+        for (int c = 0; c < 5; ++c) {
+          const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + c;
           const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
           const uint8_t* px = xn + (static_cast<size_t>(ok ? iy : 0) * W + (ok ? ix : 0)) * 3;
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) xin[ci * 9 + ky * 3 + kx] = ok ? fmaf(static_cast<float>(__ldg(px + ci)), mul[ci], add[ci]) : 0.f;
+          for (int ci = 0; ci < 3; ++ci) xin[ci][ky][c] = ok ? fmaf(static_cast<float>(__ldg(px + ci)), mul[ci], add[ci]) : 0.f;
         }
     } else {
       const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
@@ -50,37 +56,66 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+          for (int c = 0; c < 5; ++c) {
+            const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + c;
             const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-            xin[ci * 9 + ky * 3 + kx] = ok ? __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix) : 0.f;
+            xin[ci][ky][c] = ok ? __ldg(xn + (static_cast<size_t>(ci) * H + iy) * W + ix) : 0.f;
           }
     }
-    float acc[16];
+    uint64_t acc[2][8];  // [pixel][channel pair] packed fp32x2
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int p = 0; p < 2; ++p)
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const float xv = xin[t];
-      const float4* wp = &sw[t * 4];
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0ull;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 wv = wp[q];
-        acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4* wp = &sw[(ci * 9 + ky * 3 + kx) * 4];
+          uint64_t xx[2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const float xv = xin[ci][ky][kx + 2 * p];
+            asm("mov.b64 %0, {%1,%1};" : "=l"(xx[p]) : "f"(xv));
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = wp[q];
+            uint64_t w01, w23;
+            asm("mov.b64 %0, {%1,%2};" : "=l"(w01) : "f"(wv.x), "f"(wv.y));
+            asm("mov.b64 %0, {%1,%2};" : "=l"(w23) : "f"(wv.z), "f"(wv.w));
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[p][2 * q]) : "l"(xx[p]), "l"(w01));
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[p][2 * q + 1]) : "l"(xx[p]), "l"(w23));
+            }
+          }
+        }
+    // the activation is uniform over the launch: dispatch once per thread, not once per element
+    auto emit = [&](auto actf) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        if (p == 1 && !second) break;
+        float o0[8], o1[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a0, a1, b0, b1;
+          asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc[p][j]));
+          asm("mov.b64 {%0,%1}, %2;" : "=f"(b0), "=f"(b1) : "l"(acc[p][4 + j]));
+          o0[2 * j] = actf(fmaf(a0, ssc[2 * j], ssh[2 * j]));
+          o0[2 * j + 1] = actf(fmaf(a1, ssc[2 * j + 1], ssh[2 * j + 1]));
+          o1[2 * j] = actf(fmaf(b0, ssc[8 + 2 * j], ssh[8 + 2 * j]));
+          o1[2 * j + 1] = actf(fmaf(b1, ssc[8 + 2 * j + 1], ssh[8 + 2 * j + 1]));
+        }
+        uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox + p) * 16);
+        op[0] = pack8(o0);
+        op[1] = pack8(o1);
       }
-    }
-    float o0[8], o1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o0[j] = apply_act(fmaf(acc[j], ssc[j], ssh[j]), act);
-      o1[j] = apply_act(fmaf(acc[8 + j], ssc[8 + j], ssh[8 + j]), act);
-    }
-    uint4* op = reinterpret_cast<uint4*>(out + idx * 16);
-    op[0] = pack8(o0);
-    op[1] = pack8(o1);
+    };
+    if (act == ACT_HSWISH) emit([](float z) { return z * __saturatef(fmaf(z, 1.f / 6.f, 0.5f)); });
+    else emit([&](float z) { return apply_act(z, act); });
   }
 }
 
@@ -89,7 +124,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 int launch_stem(const StemArgs& a, cudaStream_t st) {
   MTG_REQUIRE((a.x || a.x_u8) && a.w && a.scale && a.shift && a.out, MTG_ERR_ARG, "stem: null pointer");
   const int Ho = (a.H + 2 - 3) / 2 + 1, Wo = (a.W + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(a.B) * Ho * Wo;
+  const long long total = static_cast<long long>(a.B) * Ho * ((Wo + 1) / 2);  // threads: one per pair of output pixels
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   // v/255 normalised: (v/255 - mean)/std = v * 1/(255 std) - mean/std

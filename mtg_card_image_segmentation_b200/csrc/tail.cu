@@ -110,6 +110,8 @@ struct UpP {
   int Hl, Wl, H, W, NC, rows_per_cta;
 };
 
+// CMAX: compile-time class capacity (2 for the card/background network: no dead predicated code for 6 absent classes)
+template <int CMAX>
 __global__ void __launch_bounds__(256) upsample_out_kernel(const UpP p) {
   extern __shared__ float lo[];  // [Hl*Wl][NC]
   __shared__ unsigned long long scount[4];
@@ -130,24 +132,39 @@ __global__ void __launch_bounds__(256) upsample_out_kernel(const UpP p) {
     int y0, y1;
     float ly;
     src_index(y, sy, p.Hl, y0, y1, ly);
-    float val[MAX_NC][4];
+    float val[CMAX][4];
+    int x0[4], x1[4];
+    float lx[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      int x0, x1;
-      float lx;
-      src_index(min(xb + e, p.W - 1), sx, p.Wl, x0, x1, lx);
+    for (int e = 0; e < 4; ++e) src_index(min(xb + e, p.W - 1), sx, p.Wl, x0[e], x1[e], lx[e]);
+    if (x0[0] == x0[3] && x1[0] == x1[3]) {
+      // the four pixels interpolate inside the same source cell (always true for an aligned group of 4 at the x8 upsampling
+      // of the network): fetch the four corners once, the per-pixel arithmetic is unchanged (bit-identical results)
 #pragma unroll
-      for (int c = 0; c < MAX_NC; ++c)
+      for (int c = 0; c < CMAX; ++c)
         if (c < p.NC) {
-          const float v00 = lo[(y0 * p.Wl + x0) * p.NC + c], v01 = lo[(y0 * p.Wl + x1) * p.NC + c];
-          const float v10 = lo[(y1 * p.Wl + x0) * p.NC + c], v11 = lo[(y1 * p.Wl + x1) * p.NC + c];
-          val[c][e] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+          const float v00 = lo[(y0 * p.Wl + x0[0]) * p.NC + c], v01 = lo[(y0 * p.Wl + x1[0]) * p.NC + c];
+          const float v10 = lo[(y1 * p.Wl + x0[0]) * p.NC + c], v11 = lo[(y1 * p.Wl + x1[0]) * p.NC + c];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            val[c][e] = (1.f - ly) * ((1.f - lx[e]) * v00 + lx[e] * v01) + ly * ((1.f - lx[e]) * v10 + lx[e] * v11);
         }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < p.NC) {
+            const float v00 = lo[(y0 * p.Wl + x0[e]) * p.NC + c], v01 = lo[(y0 * p.Wl + x1[e]) * p.NC + c];
+            const float v10 = lo[(y1 * p.Wl + x0[e]) * p.NC + c], v11 = lo[(y1 * p.Wl + x1[e]) * p.NC + c];
+            val[c][e] = (1.f - ly) * ((1.f - lx[e]) * v00 + lx[e] * v01) + ly * ((1.f - lx[e]) * v10 + lx[e] * v11);
+          }
+      }
     }
     const size_t pix0 = static_cast<size_t>(y) * p.W + xb;
     if (p.logits) {
 #pragma unroll
-      for (int c = 0; c < MAX_NC; ++c)
+      for (int c = 0; c < CMAX; ++c)
         if (c < p.NC) {
           const size_t off = (static_cast<size_t>(b) * p.NC + c) * plane + pix0;
           if (p.dtype == LOGITS_F32) {
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(256) upsample_out_kernel(const UpP p) {
         int best = 0;
         float bv = val[0][e];
 #pragma unroll
-        for (int c = 1; c < MAX_NC; ++c)
+        for (int c = 1; c < CMAX; ++c)
           if (c < p.NC && val[c][e] > bv) { bv = val[c][e]; best = c; }  // strict '>' : ties -> lowest class (torch.argmax)
         m4 |= static_cast<uint32_t>(best) << (8 * e);
         if (p.counts && xb + e < p.W) {
@@ -227,14 +244,16 @@ int launch_upsample_out(const UpsampleOutArgs& a, cudaStream_t st) {
   MTG_REQUIRE(smem <= 200 * 1024, MTG_ERR_UNSUPPORTED, "upsample_out: low-res map too large (%zu B)", smem);
   static bool configured = false;
   if (!configured) {
-    MTG_CUDA(cudaFuncSetAttribute(upsample_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MTG_CUDA(cudaFuncSetAttribute(upsample_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MTG_CUDA(cudaFuncSetAttribute(upsample_out_kernel<MAX_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   // ~8 CTAs per image keeps the smem staging of the low-res map (<= 10 KB) negligible vs the rows written
   int row_blocks = ceil_div(a.H, 40);
   p.rows_per_cta = ceil_div(a.H, row_blocks);
   dim3 grid(row_blocks, a.B);
-  upsample_out_kernel<<<grid, 256, smem, st>>>(p);
+  if (a.NC <= 2) upsample_out_kernel<2><<<grid, 256, smem, st>>>(p);
+  else upsample_out_kernel<MAX_NC><<<grid, 256, smem, st>>>(p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
