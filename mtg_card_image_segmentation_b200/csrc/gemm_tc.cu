@@ -36,7 +36,7 @@ namespace {
 
 constexpr int BM = 128;           // UMMA M
 constexpr int MAX_STAGES = 8;
-constexpr int BAR_BYTES = 256;               // mbarriers + TMEM slot
+constexpr int BAR_BYTES = 320;               // mbarriers + TMEM slot
 constexpr int OUT_BUFS = 2;                  // double-buffered output staging
 constexpr int SS_BYTES = 2 * 256 * 4;        // scale / shift of the current N tile
 
@@ -57,6 +57,10 @@ struct GemmKParams {
   int hw;
   int res_slabs;  // 0 or ceil(BN/obox)
   int res_bufs;   // 2: residual tile prefetched one tile ahead; 1: single buffer, reloaded after the epilogue has read it (long mainloops)
+  int epi_mode;   // 1: per-warp epilogue (pointwise path): the two sets of 4 epilogue warps take alternate tiles, every warp stages and
+                  //    TMA-stores its own 32-row sub-slab, no CTA-wide barrier; 0: all 8 warps share one slab at a time (3x3 / fallback)
+  int wbufs;      // staging buffers per epilogue warp in mode 1 (1 or 2)
+  int out_bytes;  // bytes of output staging in front of the residual buffers
   int obox;       // output / residual slab width in channels: 64 / 32 / 16 <-> 128B / 64B / 32B swizzled rows
   // multi-tap (3x3 / transposed-conv parity) geometry: A boxes {64 ch, W, HB rows, NB images} shifted by (dx, dy) per tap
   int B, H, W, HB, NB, h_tiles;
@@ -93,7 +97,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = sA + S * A_STAGE_BYTES;
   uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + (p.b_res ? 0 : S * b_stage_bytes)) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
   const int SLAB_BYTES = BM * p.obox * 2;
-  uint8_t* sRes = sOut + OUT_BUFS * SLAB_BYTES;        // res_bufs x res_slabs slabs
+  uint8_t* sRes = sOut + p.out_bytes;                  // res_bufs x res_slabs slabs
   float* sScale = reinterpret_cast<float*>(sRes + p.res_bufs * p.res_slabs * SLAB_BYTES);
   float* sShift = sScale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + SS_BYTES);
@@ -104,7 +108,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint64_t* resbar = tempty + 2;  // [2]: the residual tile is double buffered and prefetched one tile ahead
   uint64_t* bfull = resbar + 2;   // resident weights have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  uint64_t* res_free = bfull + 1; // [2] (mode 1): epilogue set s has finished reading the residual of its current tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,7 +122,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull[b], 1);
-      ptx::mbar_init(&tempty[b], 256);
+      ptx::mbar_init(&tempty[b], p.epi_mode ? 128 : 256);
+      ptx::mbar_init(&res_free[b], 128);
     }
     ptx::mbar_init(&resbar[0], 1);
     ptx::mbar_init(&resbar[1], 1);
@@ -153,7 +159,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb)
           ptx::tma_load_2d(sBres + kb * b_stage_bytes, &tmB, bfull, kb * BK, n_tile * p.BN);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // mode 1: the producer also fetches the residual tiles (the epilogue sets run decoupled, there is no leader thread).
+      // Residual loads never block the A/B ring: they are issued from `pump` whenever their buffer has been released.
+      const int r_slabs = p.res_slabs, r_slab_bytes = BM * p.obox * 2;
+      uint32_t tcr = 0;        // residual tiles issued so far (per-CTA tile counter)
+      int rtile = blockIdx.x;  // tile index of the next residual to issue
+      // Barriers are indexed by the epilogue SET (= tile-counter parity), not by the buffer: each barrier then has exactly
+      // one sequential consumer, so the usual (use count & 1) parity is unambiguous even when one buffer serves both sets.
+      auto pump = [&](uint32_t upto) {  // issue pending residual loads of tiles with counter <= upto whose buffer is free
+        while (rtile < total_tiles && tcr <= upto) {
+          const uint32_t rb = p.res_bufs == 2 ? (tcr & 1) : 0;
+          // the buffer was last read for tile tcr - res_bufs, by set (tcr - res_bufs) & 1, as that set's ((tcr - res_bufs) >> 1)-th tile
+          if (tcr >= static_cast<uint32_t>(p.res_bufs)) {
+            const uint32_t prev = tcr - p.res_bufs;
+            if (!ptx::mbar_try_wait(&res_free[prev & 1], (prev >> 1) & 1)) return false;
+          }
+          const int mt = rtile / p.n_tiles, nt = rtile - mt * p.n_tiles;
+          ptx::mbar_arrive_expect_tx(&resbar[tcr & 1], r_slabs * r_slab_bytes);
+          for (int sl = 0; sl < r_slabs; ++sl)
+            ptx::tma_load_2d(sRes + (rb * r_slabs + sl) * r_slab_bytes, &tmR, &resbar[tcr & 1], nt * p.BN + sl * p.obox, mt * BM);
+          ++tcr;
+          rtile += gridDim.x;
+        }
+        return true;
+      };
+      const bool pump_res = p.epi_mode == 1 && p.res_slabs > 0;
+      uint32_t tcp = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcp) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int n0 = 0, y0 = 0;
         if (kConv3x3) {
@@ -163,7 +195,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+          if (pump_res) {
+            pump(tcp);
+            while (!ptx::mbar_try_wait(&empty[s], ph ^ 1)) pump(tcp);
+          } else {
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+          }
           ptx::mbar_arrive_expect_tx(&full[s], stage_bytes);
           if (kConv3x3) {
             const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
@@ -173,6 +210,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, m_tile * BM);
             if (!p.b_res) ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], kb * BK, n_tile * p.BN);
           }
+        }
+      }
+      if (pump_res) {  // drain: the remaining residual tiles, now with blocking waits (bounded like every mbarrier wait here)
+        const long long t0 = clock64();
+        while (!pump(0xffffffffu)) {
+          if (clock64() - t0 > 8000000000LL) __trap();
         }
       }
     }
@@ -204,116 +247,171 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp < 10) {
-    // =============================== epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) ===============================
+    // =============================== epilogue (8 warps) ===============================
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // which 32 of the 64 slab columns this warp converts
+    const int wset = (warp - 2) >> 2;        // mode 0: which 32 of the 64 slab columns; mode 1: which tiles (alternate)
     const int r = q * 32 + lane;             // accumulator row of this thread
     const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
     const bool leader = et == 0;
     const int OB = p.obox, opitch = OB * 2;  // slab columns, slab row pitch in bytes
     const int slabs = (p.BN + OB - 1) / OB;
-    uint32_t tc = 0, store_no = 0;
-    int cur_ntile = -1;
-    auto load_residual = [&](int t, uint32_t rb) {  // leader only: residual tile of `t` -> buffer rb by TMA
-      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
-      ptx::mbar_arrive_expect_tx(&resbar[rb], slabs * SLAB_BYTES);
-      for (int sl = 0; sl < slabs; ++sl)
-        ptx::tma_load_2d(sRes + (rb * slabs + sl) * SLAB_BYTES, &tmR, &resbar[rb], nt * p.BN + sl * OB, mt * BM);
+    // swizzle XOR term of this row: 128B rows: row % 8 ; 64B rows: (row / 2) % 4 ; 32B rows: (row / 4) % 2
+    const int rx = OB == 64 ? (r & 7) : (OB == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+    // 32 accumulator columns [sl * OB + half * 32, +32) of this thread's row: one TMEM round trip, folded BN, activation,
+    // residual, bf16, into the swizzled staging row `srow` (rrow: the same row of the residual slab)
+    auto convert_half = [&](uint32_t taddr, int sl, int half, int cols, uint8_t* srow, const uint8_t* rrow) {
+      uint32_t v[2][16];
+      ptx::tmem_ld16(taddr + sl * OB + half * 32, v[0]);
+      if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * OB + half * 32 + 16, v[1]);
+      ptx::tmem_ld_wait();
+      // the activation is uniform over the launch: dispatch once per call, not once per element
+      auto convert = [&](auto actf) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (half * 32 + cc * 16 < cols) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the slab row
+              const int c = sl * OB + chunk * 8;             // column inside the N tile
+              const int phys = (chunk ^ rx) * 16;            // TMA swizzle of the staging slab
+              const float4 s0 = *reinterpret_cast<const float4*>(sScale + c), s1 = *reinterpret_cast<const float4*>(sScale + c + 4);
+              const float4 h0 = *reinterpret_cast<const float4*>(sShift + c), h1 = *reinterpret_cast<const float4*>(sShift + c + 4);
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              float f[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = __uint_as_float(v[cc][h * 8 + e]);
+              fma8_f2(f, a, sc);  // f = acc * scale + shift, four packed fp32x2 FMAs
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = actf(f[e]);
+              if (p.res_slabs) {
+                float rf[8];
+                unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += rf[e];
+              }
+              *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
+            }
+          }
+        }
+      };
+      // hardswish as z * sat(z/6 + 1/2): one FFMA.SAT + one FMUL instead of add / max / min / mul / mul
+      if (p.act == ACT_HSWISH) convert([](float z) { return z * __saturatef(fmaf(z, 1.f / 6.f, 0.5f)); });
+      else if (p.act == ACT_RELU) convert([](float z) { return fmaxf(z, 0.f); });
+      else if (p.act == ACT_NONE) convert([](float z) { return z; });
+      else convert([&](float z) { return apply_act(z, p.act); });
     };
-    if (p.res_slabs && leader && static_cast<int>(blockIdx.x) < total_tiles) load_residual(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
-      int oc1 = m_tile * BM, oc2 = 0, oc3 = 0;  // output coordinates after the channel coordinate
-      if (kConv3x3) {
-        oc1 = 0;
-        oc2 = (m_tile % p.h_tiles) * p.HB;
-        oc3 = (m_tile / p.h_tiles) * p.NB;
-      }
-      const uint32_t rb = p.res_bufs == 2 ? (tc & 1) : 0;
-      // prefetch the NEXT tile's residual into the other buffer (its last readers finished before the final
-      // bar.sync of the previous iteration)
-      if (p.res_slabs && p.res_bufs == 2 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, rb ^ 1);
-      if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
-        cur_ntile = n_tile;
+    if (!kConv3x3 && p.epi_mode == 1) {
+      // ---- mode 1: decoupled warps.  Set `wset` owns the tiles with (tile counter & 1) == wset and the TMEM buffer of the
+      // same index, so two tiles are in their epilogue at once; each warp converts its 32 rows of every slab into its own
+      // staging buffer and stores it with its own TMA instruction ({OB channels, 32 rows} box): only __syncwarp inside.
+      const int WSLAB = 32 * opitch;
+      uint8_t* wbuf = sOut + (warp - 2) * p.wbufs * WSLAB;
+      {  // folded-BN constants of this CTA's N tile (fixed for its whole life: one N tile, or resident weights)
+        const int n_tile = blockIdx.x % p.n_tiles;
         for (int c = et; c < p.BN; c += 256) {
           const int n = n_tile * p.BN + c;
           sScale[c] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.f;
           sShift[c] = (p.shift && n < p.N) ? __ldg(p.shift + n) : 0.f;
         }
-      }
-      ptx::mbar_wait(&tfull[buf], aph);
-      ptx::tc_fence_after();
-      if (p.res_slabs) ptx::mbar_wait(&resbar[rb], p.res_bufs == 2 ? ((tc >> 1) & 1) : (tc & 1));
-      const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
-      for (int sl = 0; sl < slabs; ++sl, ++store_no) {
-        uint8_t* sbuf = sOut + (store_no & 1) * SLAB_BYTES;
-        // the TMA store that used this buffer two slabs ago must have finished reading it
-        if (leader) ptx::bulk_wait_read<OUT_BUFS - 1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int cols = min(OB, p.BN - sl * OB);  // multiple of 16
-        uint8_t* srow = sbuf + r * opitch;
-        const uint8_t* rrow = sRes + (rb * slabs + sl) * SLAB_BYTES + r * opitch;
-        // swizzle XOR term of this row: 128B rows: row % 8 ; 64B rows: (row / 2) % 4 ; 32B rows: (row / 4) % 2
-        const int rx = OB == 64 ? (r & 7) : (OB == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
-        if (half * 32 < cols) {  // this warp's 32 accumulator columns: one TMEM round trip
-          uint32_t v[2][16];
-          ptx::tmem_ld16(taddr + sl * OB + half * 32, v[0]);
-          if (half * 32 + 16 < cols) ptx::tmem_ld16(taddr + sl * OB + half * 32 + 16, v[1]);
-          ptx::tmem_ld_wait();
-          // the activation is uniform over the launch: dispatch once per slab, not once per element
-          auto convert = [&](auto actf) {
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              if (half * 32 + cc * 16 < cols) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int chunk = half * 4 + cc * 2 + h;       // 16-byte chunk inside the slab row
-                  const int c = sl * OB + chunk * 8;             // column inside the N tile
-                  const int phys = (chunk ^ rx) * 16;            // TMA swizzle of the staging slab
-                  const float4 s0 = *reinterpret_cast<const float4*>(sScale + c), s1 = *reinterpret_cast<const float4*>(sScale + c + 4);
-                  const float4 h0 = *reinterpret_cast<const float4*>(sShift + c), h1 = *reinterpret_cast<const float4*>(sShift + c + 4);
-                  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                  float f[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                  float a[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) a[e] = __uint_as_float(v[cc][h * 8 + e]);
-                  fma8_f2(f, a, sc);  // f = acc * scale + shift, four packed fp32x2 FMAs
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = actf(f[e]);
-                  if (p.res_slabs) {
-                    float rf[8];
-                    unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] += rf[e];
-                  }
-                  *reinterpret_cast<uint4*>(srow + phys) = pack8(f);
-                }
-              }
-            }
-          };
-          // hardswish as z * sat(z/6 + 1/2): one FFMA.SAT + one FMUL instead of add / max / min / mul / mul
-          if (p.act == ACT_HSWISH) convert([](float z) { return z * __saturatef(fmaf(z, 1.f / 6.f, 0.5f)); });
-          else if (p.act == ACT_RELU) convert([](float z) { return fmaxf(z, 0.f); });
-          else if (p.act == ACT_NONE) convert([](float z) { return z; });
-          else convert([&](float z) { return apply_act(z, p.act); });
-        }
-        ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader) {
-          const int c0 = n_tile * p.BN + sl * OB;
-          if (kConv3x3) ptx::tma_store_4d(&tmO, sbuf, c0, oc1, oc2, oc3);
-          else ptx::tma_store_2d(&tmO, sbuf, c0, oc1);
-          ptx::bulk_commit();
-        }
       }
-      // single residual buffer: every epilogue thread passed the last bar.sync after its final read of the tile (and
-      // executed fence.proxy.async before it), so the buffer may be refilled now; the next mainloop hides the load
-      if (p.res_slabs && p.res_bufs == 1 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, 0);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[buf]);
+      uint32_t tc = 0, wstore = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+        if (static_cast<int>(tc & 1) != wset) continue;
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
+        const uint32_t rb = p.res_bufs == 2 ? (tc & 1) : 0;
+        ptx::mbar_wait(&tfull[buf], aph);
+        ptx::tc_fence_after();
+        if (p.res_slabs) ptx::mbar_wait(&resbar[wset], (tc >> 1) & 1);  // per-set barrier: this set's (tc >> 1)-th residual tile
+        const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+        for (int sl = 0; sl < slabs; ++sl, ++wstore) {
+          uint8_t* sbuf = wbuf + (p.wbufs == 2 ? (wstore & 1) : 0) * WSLAB;
+          if (lane == 0) {  // the store that used this buffer before must have finished reading it
+            if (p.wbufs == 2) ptx::bulk_wait_read<1>();
+            else ptx::bulk_wait_read<0>();
+          }
+          __syncwarp();
+          const int cols = min(OB, p.BN - sl * OB);  // multiple of 16
+          uint8_t* srow = sbuf + lane * opitch;
+          const uint8_t* rrow = sRes + (rb * slabs + sl) * SLAB_BYTES + r * opitch;
+          convert_half(taddr, sl, 0, cols, srow, rrow);
+          if (32 < cols) convert_half(taddr, sl, 1, cols, srow, rrow);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmO, sbuf, n_tile * p.BN + sl * OB, m_tile * BM + q * 32);
+            ptx::bulk_commit();
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty[buf]);
+        if (p.res_slabs) ptx::mbar_arrive(&res_free[wset]);
+      }
+      if (lane == 0) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
+    } else {
+      // ---- mode 0: all 8 warps work on one slab at a time (4 lane quarters x 2 column halves), one leader thread stores
+      const int half = wset;
+      uint32_t tc = 0, store_no = 0;
+      int cur_ntile = -1;
+      auto load_residual = [&](int t, uint32_t rb) {  // leader only: residual tile of `t` -> buffer rb by TMA
+        const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+        ptx::mbar_arrive_expect_tx(&resbar[rb], slabs * SLAB_BYTES);
+        for (int sl = 0; sl < slabs; ++sl)
+          ptx::tma_load_2d(sRes + (rb * slabs + sl) * SLAB_BYTES, &tmR, &resbar[rb], nt * p.BN + sl * OB, mt * BM);
+      };
+      if (p.res_slabs && leader && static_cast<int>(blockIdx.x) < total_tiles) load_residual(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
+        int oc1 = m_tile * BM, oc2 = 0, oc3 = 0;  // output coordinates after the channel coordinate
+        if (kConv3x3) {
+          oc1 = 0;
+          oc2 = (m_tile % p.h_tiles) * p.HB;
+          oc3 = (m_tile / p.h_tiles) * p.NB;
+        }
+        const uint32_t rb = p.res_bufs == 2 ? (tc & 1) : 0;
+        // prefetch the NEXT tile's residual into the other buffer (its last readers finished before the final
+        // bar.sync of the previous iteration)
+        if (p.res_slabs && p.res_bufs == 2 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, rb ^ 1);
+        if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
+          cur_ntile = n_tile;
+          for (int c = et; c < p.BN; c += 256) {
+            const int n = n_tile * p.BN + c;
+            sScale[c] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.f;
+            sShift[c] = (p.shift && n < p.N) ? __ldg(p.shift + n) : 0.f;
+          }
+        }
+        ptx::mbar_wait(&tfull[buf], aph);
+        ptx::tc_fence_after();
+        if (p.res_slabs) ptx::mbar_wait(&resbar[rb], p.res_bufs == 2 ? ((tc >> 1) & 1) : (tc & 1));
+        const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+        for (int sl = 0; sl < slabs; ++sl, ++store_no) {
+          uint8_t* sbuf = sOut + (store_no & 1) * SLAB_BYTES;
+          // the TMA store that used this buffer two slabs ago must have finished reading it
+          if (leader) ptx::bulk_wait_read<OUT_BUFS - 1>();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int cols = min(OB, p.BN - sl * OB);  // multiple of 16
+          if (half * 32 < cols)
+            convert_half(taddr, sl, half, cols, sbuf + r * opitch, sRes + (rb * slabs + sl) * SLAB_BYTES + r * opitch);
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (leader) {
+            const int c0 = n_tile * p.BN + sl * OB;
+            if (kConv3x3) ptx::tma_store_4d(&tmO, sbuf, c0, oc1, oc2, oc3);
+            else ptx::tma_store_2d(&tmO, sbuf, c0, oc1);
+            ptx::bulk_commit();
+          }
+        }
+        // single residual buffer: every epilogue thread passed the last bar.sync after its final read of the tile (and
+        // executed fence.proxy.async before it), so the buffer may be refilled now; the next mainloop hides the load
+        if (p.res_slabs && p.res_bufs == 1 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, 0);
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty[buf]);
+      }
+      if (leader) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
     }
-    if (leader) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
   } else if (kAScale) {
     // =============================== squeeze-excite prologue on the A tile ===============================
     const int t = threadIdx.x - 320;
@@ -523,8 +621,8 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
             fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
   }
   if (debug)
-    fprintf(stderr, "[conv_gemm<%d,%d>] M=%d N=%d K=%d BN=%d kbox=%d obox=%d num_kb=%d stages=%d b_res=%d res_slabs=%d res_bufs=%d tmem=%d need=%zu smem=%zu per_sm=%d grid=%d tiles=%lld\n",
-            int(C3), int(AS), kp.M, kp.N, kp.K, kp.BN, kp.kbox, kp.obox, kp.num_kb, kp.stages, kp.b_res, kp.res_slabs, kp.res_bufs, kp.tmem_cols, need, smem,
+    fprintf(stderr, "[conv_gemm<%d,%d>] M=%d N=%d K=%d BN=%d kbox=%d obox=%d num_kb=%d stages=%d b_res=%d res_slabs=%d res_bufs=%d epi=%d wbufs=%d tmem=%d need=%zu smem=%zu per_sm=%d grid=%d tiles=%lld\n",
+            int(C3), int(AS), kp.M, kp.N, kp.K, kp.BN, kp.kbox, kp.obox, kp.num_kb, kp.stages, kp.b_res, kp.res_slabs, kp.res_bufs, kp.epi_mode, kp.wbufs, kp.tmem_cols, need, smem,
             per_sm, grid, total_tiles);
   conv_gemm_kernel<C3, AS><<<grid, threads, smem, st>>>(tmA, tmB, tmO, tmR, kp);
   MTG_LAUNCH_CHECK();
@@ -585,6 +683,19 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   kp.obox = (g.conv3x3 || kp.BN > 32) ? 64 : (kp.BN > 16 ? 32 : 16);  // narrow layers stage narrow slabs: more CTAs per SM
   kp.res_slabs = g.residual ? ceil_div(kp.BN, kp.obox) : 0;
   MTG_REQUIRE(!(g.conv3x3 && g.residual), MTG_ERR_UNSUPPORTED, "conv_gemm: residual with conv3x3 is not supported");
+  // B-stationary: with few k-blocks the weights of one N tile fit in shared memory next to the A ring; every CTA then
+  // streams only activations (the weight tile would otherwise be re-fetched from L2 for every 128-pixel tile)
+  kp.m_tiles = g.conv3x3 ? 0 : ceil_div(g.M, BM);
+  const size_t b_tile_bytes = static_cast<size_t>(kp.BN) * BK * 2;
+  kp.b_res = (!g.conv3x3 && kp.num_kb <= 4 && kp.num_kb * b_tile_bytes <= 100 * 1024 &&
+              static_cast<long long>(kp.m_tiles) * kp.n_tiles >= 4LL * num_sms()) ? 1 : 0;
+  // per-warp epilogue (mode 1) needs the folded-BN constants of ONE N tile per CTA: a single N tile or resident weights
+  static const bool legacy_epi = getenv("MTGSEG_GEMM_EPI") && atoi(getenv("MTGSEG_GEMM_EPI")) == 0;  // A/B switch
+  // ... and enough tiles per CTA to keep both warp sets busy: with ~4 tiles per CTA (the 600-tile layers at 20x15) halving the
+  // warps per tile costs more than the missing barriers save (measured: b9.expand 23 -> 34 us), from ~8 tiles on it wins
+  // (b2.expand 198 -> 167 us, b3.expand 79 -> 71 us)
+  const bool many_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles >= 8LL * num_sms();
+  kp.epi_mode = (!g.conv3x3 && !legacy_epi && many_tiles && (kp.n_tiles == 1 || kp.b_res)) ? 1 : 0;
   CUtensorMap tmA, tmB, tmO, tmR;
   if (g.conv3x3) {
     MTG_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && static_cast<long long>(g.B) * g.H * g.W == g.M, MTG_ERR_ARG,
@@ -638,7 +749,8 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     const uint64_t od[2] = {(uint64_t)g.N, (uint64_t)g.M};
     const uint64_t os[1] = {(uint64_t)g.N * 2};
     const uint32_t ob[2] = {(uint32_t)kp.obox, BM};
-    rc = make_map(&tmO, g.out, 2, od, os, ob, kp.obox);
+    const uint32_t ob_warp[2] = {(uint32_t)kp.obox, 32};  // mode 1: every epilogue warp stores its own 32 rows
+    rc = make_map(&tmO, g.out, 2, od, os, kp.epi_mode ? ob_warp : ob, kp.obox);
     if (rc) return rc;
     tmR = tmO;
     if (g.residual) {
@@ -647,27 +759,44 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
     }
   }
 
-  // B-stationary: with few k-blocks the weights of one N tile fit in shared memory next to the A ring; every CTA then
-  // streams only activations (the weight tile would otherwise be re-fetched from L2 for every 128-pixel tile)
-  const size_t b_tile_bytes = static_cast<size_t>(kp.BN) * BK * 2;
-  const long long all_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles;
-  kp.b_res = (!g.conv3x3 && kp.num_kb <= 4 && kp.num_kb * b_tile_bytes <= 100 * 1024 && all_tiles >= 4LL * num_sms()) ? 1 : 0;
   const size_t b_res_bytes = kp.b_res ? align_up(kp.num_kb * b_tile_bytes, 1024) : 0;
   const int stage_bytes = A_STAGE_BYTES + (kp.b_res ? 0 : kp.BN * BK * 2);
   const size_t slab_bytes = static_cast<size_t>(BM) * kp.obox * 2;
   // a long mainloop (>= 6 k-blocks) hides the reload of a single residual buffer; the 48-96 KB saved become ring stages
   kp.res_bufs = (kp.res_slabs && kp.num_kb >= 6) ? 1 : 2;
-  const size_t fixed = 2048 /*two 1024-byte alignments*/ + OUT_BUFS * slab_bytes + static_cast<size_t>(kp.res_bufs) * kp.res_slabs * slab_bytes + SS_BYTES + BAR_BYTES + b_res_bytes;
-  // ring depth: enough stages that two co-resident CTAs keep >= ~64 KB of loads in flight per SM (HBM latency x bandwidth)
-  int stages = kp.num_kb >= 8 ? 6 : 4;
-  if (stage_bytes <= 16 * 1024) stages = 8;
-  while (stages > 2 && stages * static_cast<size_t>(stage_bytes) + fixed > 227 * 1024) --stages;
-  // prefer two co-resident CTAs (8 epilogue warps per SM) over a deeper ring when that is what it costs
-  if (stages > 3 && 2 * (3 * static_cast<size_t>(stage_bytes) + fixed) <= 227 * 1024 &&
-      2 * (stages * static_cast<size_t>(stage_bytes) + fixed) > 227 * 1024)
-    stages = 3;
+  // ring depth for a given amount of output staging: enough stages that two co-resident CTAs keep >= ~64 KB of loads in
+  // flight per SM (HBM latency x bandwidth); prefer two co-resident CTAs over a deeper ring when that is what it costs
+  auto plan = [&](size_t out_bytes, int& stages_out, size_t& need_out) {
+    const size_t fixed = 2048 /*two 1024-byte alignments*/ + out_bytes + static_cast<size_t>(kp.res_bufs) * kp.res_slabs * slab_bytes + SS_BYTES + BAR_BYTES + b_res_bytes;
+    int stages = kp.num_kb >= 8 ? 6 : 4;
+    if (stage_bytes <= 16 * 1024) stages = 8;
+    while (stages > 2 && stages * static_cast<size_t>(stage_bytes) + fixed > 227 * 1024) --stages;
+    if (stages > 3 && 2 * (3 * static_cast<size_t>(stage_bytes) + fixed) <= 227 * 1024 &&
+        2 * (stages * static_cast<size_t>(stage_bytes) + fixed) > 227 * 1024)
+      stages = 3;
+    stages_out = stages;
+    need_out = static_cast<size_t>(stages) * stage_bytes + fixed;
+  };
+  int stages = 0;
+  size_t need = 0;
+  if (kp.epi_mode) {
+    // 8 warps x 32 rows = two slabs' worth of staging per buffer; take the second buffer per warp only when it costs
+    // neither a co-resident CTA nor ring stages below 4
+    int st1, st2;
+    size_t need1, need2;
+    plan(2 * slab_bytes, st1, need1);
+    plan(4 * slab_bytes, st2, need2);
+    const bool two_ok = need2 <= 227 * 1024 && ((227 * 1024) / (need2 + 1024) >= 2) == ((227 * 1024) / (need1 + 1024) >= 2) && (st2 >= 4 || st2 == st1);
+    kp.wbufs = two_ok ? 2 : 1;
+    kp.out_bytes = static_cast<int>((two_ok ? 4 : 2) * slab_bytes);
+    stages = two_ok ? st2 : st1;
+    need = two_ok ? need2 : need1;
+  } else {
+    kp.wbufs = 0;
+    kp.out_bytes = static_cast<int>(OUT_BUFS * slab_bytes);
+    plan(OUT_BUFS * slab_bytes, stages, need);
+  }
   kp.stages = stages;
-  const size_t need = static_cast<size_t>(stages) * stage_bytes + fixed;
   MTG_REQUIRE(need <= 227 * 1024, MTG_ERR_UNSUPPORTED, "conv_gemm: tile needs %zu B shared memory", need);
   if (g.conv3x3) return launch_variant<true, false>(tmA, tmB, tmO, tmR, kp, need, st);
   if (g.a_scale) return launch_variant<false, true>(tmA, tmB, tmO, tmR, kp, need, st);

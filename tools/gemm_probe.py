@@ -27,7 +27,10 @@ dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 res = {"batch": B, "layers": {}}
 total = 0.0
+only = os.environ.get("GEMM_ONLY")
 for (name, hw, K, N, act, has_res, has_se) in L:
+    if only and name not in only.split(","):
+        continue
     M = B * hw
     nbuf = 3
     xs = [torch.randn(M, K, device=dev, generator=g).bfloat16() for _ in range(nbuf)]
