@@ -108,7 +108,7 @@ int build_plan(const mtgseg_net_desc& d, NetPlan& P) {
   return MTG_OK;
 }
 
-int pack_weights(const NetPlan& P, const void* const* params, void* packed, cudaStream_t st) {
+static int pack_weights_impl(const NetPlan& P, const void* const* params, void* packed, cudaStream_t st) {
   uint8_t* base = static_cast<uint8_t*>(packed);
   auto f = [&](int idx) { return static_cast<const float*>(params[idx]); };
   auto fold = [&](const ConvBnPlan& c) {
@@ -154,6 +154,17 @@ int pack_weights(const NetPlan& P, const void* const* params, void* packed, cuda
   RC(launch_copy_f32(f(P.high_w), reinterpret_cast<float*>(base + P.high_w_off), static_cast<size_t>(nc) * ic, st));
   RC(launch_copy_f32(f(P.high_b), reinterpret_cast<float*>(base + P.high_b_off), nc, st));
   return MTG_OK;
+}
+
+// every conversion of the ~170 tensors is recorded and executed by ONE kernel (pack.cu)
+int pack_weights(const NetPlan& P, const void* const* params, void* packed, cudaStream_t st) {
+  pack_batch_begin();
+  const int rc = pack_weights_impl(P, params, packed, st);
+  if (rc != MTG_OK) {
+    pack_batch_abort();
+    return rc;
+  }
+  return pack_batch_flush(st);
 }
 
 static inline int conv_out(int in, int k, int stride, int dil) {

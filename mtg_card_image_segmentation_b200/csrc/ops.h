@@ -193,6 +193,10 @@ int launch_pack_oihw_to_otapi(const float* in, bf16* out, int O, int I, int taps
 int launch_pack_dw(const float* in, bf16* out, bf16* out_flip, int C, int taps, cudaStream_t st);
 // stem [16][3][3][3] fp32 -> [27][16] fp32
 int launch_pack_stem(const float* in, float* out, cudaStream_t st);
+// between begin and flush the pack launchers only record their job; flush runs all of them in one kernel (pack.cu)
+void pack_batch_begin();
+int pack_batch_flush(cudaStream_t st);
+void pack_batch_abort();
 // scale = gamma / sqrt(var + eps), shift = beta - mean * scale
 int launch_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
                    float* shift, int C, cudaStream_t st);

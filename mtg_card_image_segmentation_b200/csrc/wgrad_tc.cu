@@ -174,19 +174,24 @@ int launch_wgrad_tc(const WgradArgs& a, int B, cudaStream_t st) {
     p.segs_per_img = ceil_div(a.hw, SEG);
   }
   const int tiles = p.mt_tiles * p.nt_tiles * p.taps;
-  // enough (image, run) splits for ~3 CTAs per SM, at least 2 segments per CTA when possible
-  int runs = ceil_div(148 * 2, tiles * B);
-  if (runs < 1) runs = 1;
-  if (runs > p.segs_per_img) runs = p.segs_per_img;
+  // Every CTA adds its whole partial tile (128 x BNp fp32) to global memory with atomics, and shared memory allows one CTA
+  // per SM: the pixel range is split for ONE wave of CTAs, not more (b14.expand at B=32: 512 CTAs / 10.5 M atomics before,
+  // 128 CTAs / 2.6 M now).  Without a squeeze-excite gate a CTA may walk several images; with one the scale belongs to
+  // the finished per-image accumulator, so those layers keep one image per CTA.
+  int splits = 148 / tiles;
+  if (splits < 1) splits = 1;
+  int runs = 1;
+  p.imgs_per_cta = 1;
+  if (a.a_scale || splits >= B) {
+    runs = splits / B;
+    if (runs < 1) runs = 1;
+    if (runs > p.segs_per_img) runs = p.segs_per_img;
+  } else {
+    p.imgs_per_cta = ceil_div(B, splits);
+  }
   p.segs_per_cta = ceil_div(p.segs_per_img, runs);
   p.runs_per_img = ceil_div(p.segs_per_img, p.segs_per_cta);
   p.B = B;
-  p.imgs_per_cta = 1;
-  if (!a.a_scale && p.runs_per_img == 1) {  // plenty of CTAs already: merge images to cut the atomic traffic
-    p.imgs_per_cta = (tiles * B) / (148 * 2);
-    if (p.imgs_per_cta < 1) p.imgs_per_cta = 1;
-    if (p.imgs_per_cta > B) p.imgs_per_cta = B;
-  }
 
   CUtensorMap tmDz, tmX;
   int rc;
