@@ -36,6 +36,12 @@ def _check(name, got, ref, tol_max=1e-2, tol_l2=4e-3):
     (600, 184, 80, 2, False, False),
     (1, 16, 16, 0, False, False),        # smallest
     (148 * 128 * 9 + 5, 72, 24, 1, False, False),  # many tiles per persistent CTA
+    # >= 8 tiles per SM: the decoupled per-warp epilogue (alternate tiles per warp set, per-warp TMA stores) ...
+    (148 * 128 * 10, 16, 16, 0, True, False),   # ... with the residual tile double buffered and fetched by the producer (b1.project)
+    (300 * 600, 160, 960, 0, True, True),       # ... with ONE residual buffer shared by both warp sets (15 k-blocks), SE gate prefetch
+    (1200 * 160, 40, 120, 0, True, True),       # ... SE project at 40x30 (b5/b6)
+    (148 * 128 * 9, 240, 40, 2, False, False),  # ... four 64-column slabs per tile (b7.expand)
+    (300 * 512, 960, 160, 2, False, False),     # ... resident weights with five N tiles (b14.expand)
 ])
 def test_conv1x1(M, N, K, act, res, se):
     g = torch.Generator().manual_seed(M + N + K)
