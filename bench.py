@@ -187,15 +187,24 @@ def run_ours(args):
         value = world * B * args.steps / (ms_total * 1e-3)
 
         # ---------------- e2e: public API from pinned host memory, double-buffered --------------------------
-        def e2e_leg(host_batch):
+        def e2e_leg(host_batch, graphed):
             # three streams: H2D of batch i+1, forward of batch i and D2H of mask i-1 overlap (the read-back must not sit on the
-            # compute stream, or every step pays its 19.7 MB PCIe transfer between two forwards)
+            # compute stream, or every step pays its 19.7 MB PCIe transfer between two forwards).
+            # graphed: the forward is engine.GraphedInference (CUDA-graph replay, static input / mask buffers, two instances for
+            # double buffering): the host enqueues 1 launch per step instead of ~60 + their tensor-map encodes.
+            # eager:   the forward is model.predict, every kernel launched by the host each step.
             copy_s, comp_s, back_s = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-            xbuf = [torch.empty(host_batch.shape, dtype=host_batch.dtype, device=dev) for _ in range(2)]
             mask_host = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
             ready = [torch.cuda.Event(), torch.cuda.Event()]
             done = [torch.cuda.Event(), torch.cuda.Event()]
             computed = [torch.cuda.Event(), torch.cuda.Event()]
+            read_back = [torch.cuda.Event(), torch.cuda.Event()]
+            if graphed:
+                example = torch.zeros(host_batch.shape, dtype=host_batch.dtype, device=dev)
+                graphs = [GraphedInference(model, example, logits_dtype=None, want_mask=True) for _ in range(2)]
+                xbuf = [gi.x for gi in graphs]
+            else:
+                xbuf = [torch.empty(host_batch.shape, dtype=host_batch.dtype, device=dev) for _ in range(2)]
 
             def e2e_steps(n):
                 for i in range(n):
@@ -206,17 +215,24 @@ def run_ours(args):
                         ready[k].record(copy_s)
                     with torch.cuda.stream(comp_s):
                         comp_s.wait_event(ready[k])
-                        out = model.predict(xbuf[k])  # public API: uint8 argmax mask (train/evaluate.py:66-78)
+                        if graphed:
+                            comp_s.wait_event(read_back[k])  # the static mask of instance k has been copied out
+                            mask = graphs[k].replay()["mask"]
+                        else:
+                            mask = model.predict(xbuf[k])["mask"]  # public API: uint8 argmax mask (train/evaluate.py:66-78)
                         done[k].record(comp_s)
                         computed[k].record(comp_s)
                     with torch.cuda.stream(back_s):
                         back_s.wait_event(computed[k])
-                        mask_host[k].copy_(out["mask"], non_blocking=True)  # in-order on back_s: slot k is free again two steps later
-                        out["mask"].record_stream(back_s)
+                        mask_host[k].copy_(mask, non_blocking=True)  # in-order on back_s: slot k is free again two steps later
+                        read_back[k].record(back_s)
+                        if not graphed:
+                            mask.record_stream(back_s)
                 copy_s.synchronize(); comp_s.synchronize(); back_s.synchronize()
 
             for k in range(2):
                 done[k].record(comp_s)
+                read_back[k].record(back_s)
             e2e_steps(max(3, args.warmup))
             barrier()
             t0 = time.perf_counter()
@@ -227,12 +243,14 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return world * B * args.steps / t.item(), host_batch.numel() * host_batch.element_size()
 
-        e2e_value, h2d = e2e_leg(x_host)
+        e2e_value, h2d = e2e_leg(x_host, True)
+        e2e_eager, _ = e2e_leg(x_host, False)
         d2h = B * H * W
         # the same call fed with the raw uint8 HWC frames (normalisation fused into the stem): 4x less PCIe traffic
         mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1); std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
         raw_host = ((x_host * std + mean) * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
-        e2e_u8_value, h2d_u8 = e2e_leg(raw_host)
+        e2e_u8_value, h2d_u8 = e2e_leg(raw_host, True)
+        e2e_u8_eager, _ = e2e_leg(raw_host, False)
 
         # ---------------- roofline of the dominant kernel family, timed live ------------------------------
         roofline, layers = None, []
@@ -390,9 +408,13 @@ def run_ours(args):
                        "cuda_graph": not args.no_graph, "concurrent_sub_batches": args.splits},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "CardSegmentationModel.predict (uint8 mask), pinned host buffers, H2D / forward / D2H on three streams, double-buffered",
+                    "api": "engine.GraphedInference(model, example, logits_dtype=None, want_mask=True).replay() (uint8 mask), pinned host "
+                           "buffers, H2D / forward / D2H on three streams, double-buffered",
+                    "eager_predict": {"value": e2e_eager, "unit": UNIT,
+                                      "api": "CardSegmentationModel.predict: same pipeline, every kernel launched by the host each step"},
                     "uint8_input": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
-                                    "note": "same call fed raw uint8 HWC frames; (v/255-mean)/std fused into the stem kernel"}},
+                                    "eager_predict": {"value": e2e_u8_eager, "unit": UNIT},
+                                    "note": "same calls fed raw uint8 HWC frames; (v/255-mean)/std fused into the stem kernel"}},
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "train": train, "train_global256": train_dp, "pose_head": pose,
         }

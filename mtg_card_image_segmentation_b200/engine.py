@@ -190,7 +190,9 @@ class GraphedInference:
         B = self.x.shape[0]
         splits = max(1, min(splits, B))
         bounds = [(i * B) // splits for i in range(splits + 1)]
-        logits = torch.empty((B, eng.num_classes) + tuple(self.x.shape[2:]), dtype=logits_dtype, device=self.x.device)
+        # spatial size of the input: (B,3,H,W) float batches or (B,H,W,3) uint8 frames; logits_dtype None = mask / counts only
+        hw = tuple(self.x.shape[1:3]) if self.x.dtype == torch.uint8 else tuple(self.x.shape[2:])
+        logits = None if logits_dtype is None else torch.empty((B, eng.num_classes) + hw, dtype=logits_dtype, device=self.x.device)
 
         def run_all():
             if splits == 1:
@@ -206,7 +208,7 @@ class GraphedInference:
                 main.wait_stream(st)
             return logits
 
-        if splits > 1 and want_mask:
+        if splits > 1 and (want_mask or logits is None):
             raise RuntimeError("GraphedInference: splits > 1 supports logits output only")
         self._streams = [torch.cuda.Stream() for _ in range(splits)] if splits > 1 else []
         side = torch.cuda.Stream()
