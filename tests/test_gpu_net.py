@@ -231,3 +231,25 @@ def test_uint8_input_path_matches_normalised_fp32_path():
     # identical maths except the order of the normalisation arithmetic before the bf16 stem output
     assert D.report("uint8 path vs fp32 path", a.cpu(), b.cpu())[0] <= 1e-2
     assert (m_u8.long() == torch.argmax(a, 1)).all()
+
+
+def test_graphed_inference_mask_only_matches_predict():
+    """engine.GraphedInference(logits_dtype=None, want_mask=True): the CUDA-graph replay the e2e bench leg uses must give the
+    mask of model.predict bit for bit, for normalised fp32 NCHW batches and for raw uint8 HWC frames, across replays."""
+    from mtg_card_image_segmentation_b200.engine import GraphedInference
+    g = torch.Generator().manual_seed(21)
+    raw = torch.randint(0, 256, (4, 320, 240, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]); std = torch.tensor([0.229, 0.224, 0.225])
+    xf = ((raw.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    model = _model(O.calibrate_running_stats(O.make_weights(32), xf))
+    with torch.no_grad():
+        for batch in (xf.cuda(), raw.cuda()):
+            want = model.predict(batch)["mask"].clone()
+            gi = GraphedInference(model, torch.zeros_like(batch), logits_dtype=None, want_mask=True)
+            out = gi.run(batch)
+            assert out["logits"] is None
+            assert torch.equal(out["mask"], want)
+            # a second input through the same captured graph, then the first again: static buffers, no stale state
+            other = torch.flip(batch, dims=[0])
+            assert torch.equal(gi.run(other)["mask"], torch.flip(want, dims=[0]))
+            assert torch.equal(gi.run(batch)["mask"], want)
