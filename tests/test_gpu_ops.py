@@ -8,6 +8,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 import devops as D  # noqa: E402
+from mtg_card_image_segmentation_b200 import _native as N_  # noqa: E402
 
 DEV = "cuda"
 torch.backends.cudnn.allow_tf32 = False  # the references below must be true fp32
@@ -165,3 +166,74 @@ def test_head_tail(NC, H, W):
     _check("upsample_out bf16", lb, ref, tol_max=1e-2, tol_l2=4e-3)
     lh, _, _ = D.upsample_out(lowres, H, W, torch.float16)
     _check("upsample_out f16", lh, ref, tol_max=2e-3, tol_l2=1e-3)
+
+
+def _guarded(shape, dtype, guard=4096):
+    """A tensor of `shape` carved out of a larger buffer whose margins hold a sentinel: (view, check())."""
+    n = 1
+    for s in shape:
+        n *= s
+    sentinel = 0x5A if dtype == torch.uint8 else 12345.0
+    buf = torch.full((n + 2 * guard,), sentinel, dtype=dtype, device=DEV)
+    view = buf[guard:guard + n].view(*shape)
+
+    def check():
+        assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n:] == sentinel).all()), "write outside the output tensor"
+    return view, check
+
+
+@pytest.mark.parametrize("M,N,K,res", [
+    (148 * 128 * 9 + 77, 16, 16, True),    # per-warp epilogue, ragged last M tile, N below the slab width
+    (148 * 128 * 8 + 1, 200, 80, False),   # per-warp epilogue, N = 200 padded to 208 columns, one valid row in the last tile
+    (777, 24, 72, True),                   # CTA-wide epilogue (few tiles), N = 24 padded to 32
+])
+def test_conv1x1_writes_stay_inside_the_output(M, N, K, res):
+    """compute-sanitizer is not available on the GPU pool: guard bands around the output instead (the TMA stores clip
+    against the tensor map, ragged tiles and padded N columns must never touch memory past [M][N])."""
+    g = torch.Generator().manual_seed(M)
+    a = _rand(M, K, gen=g).bfloat16().to(DEV)
+    w = _rand(N, K, gen=g, scale=K ** -0.5).bfloat16().to(DEV)
+    residual = _rand(M, N, gen=g).bfloat16().to(DEV) if res else None
+    out, check = _guarded((M, N), torch.bfloat16)
+    lib = N_.load()
+    N_.check(lib.mtgseg_conv1x1(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, None, None, 0, N_.ptr(residual), None, 0,
+                                N_.stream_ptr()), "conv1x1")
+    torch.cuda.synchronize()
+    check()
+    ref = a.float() @ w.float().t() + (residual.float() if res else 0)
+    _check(f"guarded conv1x1 M{M} N{N} K{K}", out, ref)
+
+
+@pytest.mark.parametrize("B,H,W,C,k,s,d", [(3, 20, 15, 184, 3, 1, 1), (2, 40, 30, 120, 5, 1, 1), (2, 21, 17, 72, 5, 2, 1), (2, 20, 15, 672, 5, 1, 2)])
+def test_dwconv_writes_stay_inside_the_output(B, H, W, C, k, s, d):
+    g = torch.Generator().manual_seed(C + k)
+    x = _rand(B, H, W, C, gen=g).bfloat16().to(DEV)
+    w = _rand(k * k, C, gen=g, scale=0.2).bfloat16().to(DEV)
+    sc = (torch.rand(C, generator=g) + 0.5).to(DEV); sh = _rand(C, gen=g, scale=0.1).to(DEV)
+    pad = (k - 1) // 2 * d
+    Ho = (H + 2 * pad - d * (k - 1) - 1) // s + 1; Wo = (W + 2 * pad - d * (k - 1) - 1) // s + 1
+    out, check = _guarded((B, Ho, Wo, C), torch.bfloat16)
+    lib = N_.load()
+    chunks = lib.mtgseg_dwconv_chunks(H, W, C, k, s, d, 1)
+    gap, check_gap = _guarded((B, chunks, C), torch.float32)
+    N_.check(lib.mtgseg_dwconv(x.data_ptr(), w.data_ptr(), out.data_ptr(), B, H, W, C, k, s, d, sc.data_ptr(), sh.data_ptr(), 1,
+                               gap.data_ptr(), chunks, N_.stream_ptr()), "dwconv")
+    torch.cuda.synchronize()
+    check(); check_gap()
+    want, want_gap = D.dwconv(x, w, sc, sh, 1, k, s, d, True)
+    assert torch.equal(out, want) and torch.equal(gap, want_gap)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 46, 46), (1, 33, 21), (2, 320, 240)])
+def test_stem_writes_stay_inside_the_output(B, H, W):
+    """Two output pixels per thread: an odd output width leaves the second pixel of the last pair without a home."""
+    g = torch.Generator().manual_seed(H * W)
+    x = _rand(B, 3, H, W, gen=g).to(DEV)
+    w = _rand(27, 16, gen=g, scale=0.3).to(DEV)
+    sc = (torch.rand(16, generator=g) + 0.5).to(DEV); sh = _rand(16, gen=g, scale=0.1).to(DEV)
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out, check = _guarded((B, Ho, Wo, 16), torch.bfloat16)
+    N_.check(N_.load().mtgseg_stem(x.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), B, H, W, N_.stream_ptr()), "stem")
+    torch.cuda.synchronize()
+    check()
+    assert torch.equal(out, D.stem(x, w, sc, sh))
