@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgP p) {
 struct DwBwdP {
   const bf16* dz; const bf16* x; const bf16* w; bf16* dx; float* dw;
   int H, W, C, Ho, Wo, k, stride, dil, pad, CV, CVc, PL, rows_per_chunk, chunks;
+  int B, imgs_per_cta;  // wgrad: a CTA accumulates over several images before its block reduction + atomics
 };
 
 // dx[n,iy,ix,c] = sum_taps w[tap][c] * dz[n,(iy+pad-ky*d)/s,(ix+pad-kx*d)/s,c]   (grid: chunks, groups, B)
@@ -144,14 +145,16 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const DwBwdP p) {
 }
 
 // dW[c][ky][kx] += sum dz[n,oy,ox,c] * x[n,oy*s-pad+ky*d,ox*s-pad+kx*d,c]; one kernel row (ky) per CTA:
-// grid (chunks*KS, groups, B)
+// grid (chunks*KS, groups, ceil(B / imgs_per_cta)): the per-CTA cost is the block reduction + cw*KS atomics at the end, so a
+// CTA walks imgs_per_cta images of its (pixel chunk, kernel row) first (B=32, 20x15, C=960: 3840 CTAs of <= 8 pixels per
+// thread before, ~600 now)
 template <int KS>
 __global__ void __launch_bounds__(256) dw_wgrad_kernel(const DwBwdP p) {
   __shared__ float red[256 * 8];
   const int vl = threadIdx.x % p.CVc, pl = threadIdx.x / p.CVc;
   const int v = blockIdx.y * p.CVc + vl;
   const bool active = pl < p.PL && v < p.CV;
-  const int c0 = (active ? v : 0) * 8, n = blockIdx.z;
+  const int c0 = (active ? v : 0) * 8;
   const int chunk = blockIdx.x / KS, ky = blockIdx.x % KS;
   float acc[KS][8];
 #pragma unroll
@@ -161,22 +164,25 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const DwBwdP p) {
   if (active) {
     const int npix = p.Ho * p.Wo;
     const int r0 = chunk * p.rows_per_chunk, r1 = min(npix, r0 + p.rows_per_chunk);
-    const bf16* dz_n = p.dz + static_cast<size_t>(n) * npix * p.C + c0;
-    const bf16* x_n = p.x + static_cast<size_t>(n) * p.H * p.W * p.C + c0;
-    for (int pix = r0 + pl; pix < r1; pix += p.PL) {
-      const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
-      const int iy = oy * p.stride - p.pad + ky * p.dil;
-      if (iy < 0 || iy >= p.H) continue;
-      float g[8];
-      unpack8(ldg16(dz_n + static_cast<size_t>(pix) * p.C), g);
+    const int n_begin = blockIdx.z * p.imgs_per_cta, n_end = min(p.B, n_begin + p.imgs_per_cta);
+    for (int n = n_begin; n < n_end; ++n) {
+      const bf16* dz_n = p.dz + static_cast<size_t>(n) * npix * p.C + c0;
+      const bf16* x_n = p.x + static_cast<size_t>(n) * p.H * p.W * p.C + c0;
+      for (int pix = r0 + pl; pix < r1; pix += p.PL) {
+        const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+        const int iy = oy * p.stride - p.pad + ky * p.dil;
+        if (iy < 0 || iy >= p.H) continue;
+        float g[8];
+        unpack8(ldg16(dz_n + static_cast<size_t>(pix) * p.C), g);
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        const int ix = ox * p.stride - p.pad + kx * p.dil;
-        if (ix < 0 || ix >= p.W) continue;
-        float xf[8];
-        unpack8(ldg16(x_n + (static_cast<size_t>(iy) * p.W + ix) * p.C), xf);
+        for (int kx = 0; kx < KS; ++kx) {
+          const int ix = ox * p.stride - p.pad + kx * p.dil;
+          if (ix < 0 || ix >= p.W) continue;
+          float xf[8];
+          unpack8(ldg16(x_n + (static_cast<size_t>(iy) * p.W + ix) * p.C), xf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], xf[j], acc[kx][j]);
+          for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], xf[j], acc[kx][j]);
+        }
       }
     }
   }
@@ -206,31 +212,35 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const DwBwdP p) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(448) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz,
                                                          float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
-                                                         long long pix_per_cta) {
+                                                         int pix_per_cta) {
   __shared__ float sp[64][28];
   __shared__ float sg[64][16];
-  const long long total = static_cast<long long>(B) * Ho * Wo;
-  const long long p_begin = blockIdx.x * pix_per_cta, p_end = min(total, p_begin + pix_per_cta);
+  // 32-bit pixel indices (the launcher checks B*Ho*Wo < 2^31): the staging loop decomposes one index per gathered element,
+  // and three 64-bit divisions per element made that arithmetic the whole kernel (233 us for 49 MB of input at B=32)
+  const int total = B * Ho * Wo;
+  const int p_begin = blockIdx.x * pix_per_cta, p_end = min(total, p_begin + pix_per_cta);
   const int t = threadIdx.x;
   const int o = t / 27, q = t % 27;  // weight (o, q) with q = ci*9 + ky*3 + kx
+  const int plane = Ho * Wo;
   float acc = 0.f;
-  for (long long p0 = p_begin; p0 < p_end; p0 += 64) {
+  for (int p0 = p_begin; p0 < p_end; p0 += 64) {
     for (int i = t; i < 64 * 27; i += blockDim.x) {
-      const int pp = i / 27, qq = i % 27;
-      const long long pix = p0 + pp;
+      const int pp = i / 27, qq = i - pp * 27;
+      const int pix = p0 + pp;
       float v = 0.f;
       if (pix < p_end) {
-        const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho), n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
-        const int ci = qq / 9, ky = (qq % 9) / 3, kx = qq % 3;
+        const int n = pix / plane, rem = pix - n * plane;
+        const int oy = rem / Wo, ox = rem - oy * Wo;
+        const int ci = qq / 9, r9 = qq - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
         const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<size_t>(n) * 3 + ci) * H + iy) * W + ix);
       }
       sp[pp][qq] = v;
     }
     for (int i = t; i < 64 * 16; i += blockDim.x) {
-      const int pp = i / 16, oo = i % 16;
-      const long long pix = p0 + pp;
-      sg[pp][oo] = pix < p_end ? __bfloat162float(dz[pix * 16 + oo]) : 0.f;
+      const int pp = i >> 4, oo = i & 15;
+      const int pix = p0 + pp;
+      sg[pp][oo] = pix < p_end ? __bfloat162float(dz[static_cast<size_t>(pix) * 16 + oo]) : 0.f;
     }
     __syncthreads();
     if (t < 432) {
@@ -294,7 +304,12 @@ int launch_dw_wgrad(const DwBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.C % 8 == 0 && (a.k == 3 || a.k == 5), MTG_ERR_UNSUPPORTED, "dw_wgrad: unsupported shape");
   DwBwdP p{};
   fill_dw(a, p, 1);
-  dim3 grid(p.chunks * a.k, ceil_div(p.CV, p.CVc), a.B);
+  p.B = a.B;
+  const int groups = ceil_div(p.CV, p.CVc);
+  p.imgs_per_cta = ceil_div(p.chunks * a.k * groups * a.B, 148 * 4);  // ~4 CTAs per SM in total
+  if (p.imgs_per_cta < 1) p.imgs_per_cta = 1;
+  if (p.imgs_per_cta > a.B) p.imgs_per_cta = a.B;
+  dim3 grid(p.chunks * a.k, groups, ceil_div(a.B, p.imgs_per_cta));
   if (a.k == 3) dw_wgrad_kernel<3><<<grid, 256, 0, st>>>(p);
   else dw_wgrad_kernel<5><<<grid, 256, 0, st>>>(p);
   MTG_LAUNCH_CHECK();
@@ -305,10 +320,11 @@ int launch_stem_wgrad(const float* x, const bf16* dz, float* dw, int B, int H, i
   MTG_REQUIRE(x && dz && dw, MTG_ERR_ARG, "stem_wgrad: null pointer");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo;
+  MTG_REQUIRE(total < (1LL << 31) - 64 * 1024, MTG_ERR_UNSUPPORTED, "stem_wgrad: %lld output pixels exceed the 32-bit index range", total);
   long long ctas = 148 * 4;
   long long per = ((total + ctas - 1) / ctas + 63) / 64 * 64;
   ctas = (total + per - 1) / per;
-  stem_wgrad_kernel<<<static_cast<unsigned>(ctas), 448, 0, st>>>(x, dz, dw, B, H, W, Ho, Wo, per);
+  stem_wgrad_kernel<<<static_cast<unsigned>(ctas), 448, 0, st>>>(x, dz, dw, B, H, W, Ho, Wo, static_cast<int>(per));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
