@@ -145,6 +145,7 @@ struct DwS {
   float* gap;
   int act, H, W, C, Ho, Wo, pad, CV, CVc, PL, strips, band, bands, R, Wp;
   int xoff;  // offset of the input tile inside the dynamic buffer, in uint4 (weights first, padded to 128 bytes for TMA)
+  int dbg;   // MTGSEG_DW_PHASE (timing experiments only): 1 = fill phase only, 2 = compute phase only (reads an unfilled tile)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
@@ -192,17 +193,20 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
   const int iy_base = oy0 * STRIDE - p.pad;
   // ---- phase 1: stage ----
   if constexpr (TMA) {
-    if (tid == 0) {
-      ptx::mbar_init(&bar, 1);
-      ptx::fence_mbar_init();
+    if (p.dbg != 2) {
+      if (tid == 0) {
+        ptx::mbar_init(&bar, 1);
+        ptx::fence_mbar_init();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>((KS * KS + p.R * p.Wp) * p.CVc) * 16u);
+        ptx::tma_load_2d(sw, &tmw, &bar, v0 * 8, 0);
+        ptx::tma_load_4d(sx, &tmx, &bar, v0 * 8, -p.pad, iy_base, n);
+      }
+      ptx::mbar_wait(&bar, 0);
     }
-    __syncthreads();
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>((KS * KS + p.R * p.Wp) * p.CVc) * 16u);
-      ptx::tma_load_2d(sw, &tmw, &bar, v0 * 8, 0);
-      ptx::tma_load_4d(sx, &tmx, &bar, v0 * 8, -p.pad, iy_base, n);
-    }
-    ptx::mbar_wait(&bar, 0);
+    if (p.dbg == 1) return;
   } else {
     const int rows = (oy1 - oy0 - 1) * STRIDE + (KS - 1) * DIL + 1;
     const bf16* in_n = p.in + static_cast<size_t>(n) * p.H * p.W * p.C + v0 * 8;
@@ -309,6 +313,137 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Half-vector variant for the stride-1 5x5 layers: a thread owns FOUR channels (8-byte LDS / STG) and a strip of EIGHT
+// output pixels.  Same 32 accumulators as 8 channels x 4 pixels, but every staged input value now feeds up to 5 taps of 8
+// outputs: per kernel row 16 (dilation 2) or 12 (dilation 1) 8-byte loads and 4-element unpacks for 160 FMAs per lane,
+// instead of 12 / 8 16-byte loads and 8-element unpacks: ~38 % fewer shared-memory bytes and unpack instructions per FMA
+// (the 8-channel kernel sits where shared-memory bandwidth and issue bandwidth meet; 8 pixels x 8 channels spills).
+// Same tile layout and TMA fill as dwconv_smem_kernel; the plan is made with TW = 8.
+// ---------------------------------------------------------------------------------------------------------
+template <int KS, int DIL>
+__global__ void __launch_bounds__(256, 2) dwconv_half_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
+                                                              const DwS p) {
+  constexpr int TW = 8, NI = (TW - 1) + (KS - 1) * DIL + 1;
+  extern __shared__ __align__(128) uint4 dsm[];
+  __shared__ uint64_t bar;
+  const uint2* sw = reinterpret_cast<const uint2*>(dsm);            // [KS*KS][HV]
+  const uint2* sx = reinterpret_cast<const uint2*>(dsm + p.xoff);   // [R][Wp][HV]
+  float* red = reinterpret_cast<float*>(dsm);
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z, band = blockIdx.x;
+  const int v0 = blockIdx.y * p.CVc;
+  const int nv = min(p.CVc, p.CV - v0);
+  const int HV = p.CVc * 2, nvh = nv * 2, PLh = 256 / HV;  // half-vectors per pixel of this group, pixel lanes
+  const int oy0 = band * p.band, oy1 = min(p.Ho, oy0 + p.band);
+  if (tid == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>((KS * KS + p.R * p.Wp) * p.CVc) * 16u);
+    ptx::tma_load_2d(dsm, &tmw, &bar, v0 * 8, 0);
+    ptx::tma_load_4d(dsm + p.xoff, &tmx, &bar, v0 * 8, -p.pad, oy0 - p.pad, n);
+  }
+  ptx::mbar_wait(&bar, 0);
+  const int vl = tid % HV, pl = tid / HV;
+  const bool active = pl < PLh && vl < nvh;
+  const int c0 = v0 * 8 + (active ? vl : 0) * 4;
+  float acc_gap[4] = {0.f, 0.f, 0.f, 0.f};
+  // one bf16x2 word -> (even channel, odd channel) as packed fp32x2
+  auto widen = [](uint32_t w) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xFFFF0000u));
+    return r;
+  };
+  if (active) {
+    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), sh4 = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+    bf16* out_n = p.out + static_cast<size_t>(n) * p.Ho * p.Wo * p.C + c0;
+    const int items = (oy1 - oy0) * p.strips;
+    for (int item = pl; item < items; item += PLh) {
+      const int ry = item / p.strips, sxi = item - ry * p.strips;
+      const int ox0 = sxi * TW;
+      uint64_t acc[TW][2];
+#pragma unroll
+      for (int t = 0; t < TW; ++t) acc[t][0] = acc[t][1] = 0ull;
+#pragma unroll 1
+      for (int ky = 0; ky < KS; ++ky) {
+        uint64_t wv[KS][2];
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const uint2 q = sw[(ky * KS + kx) * HV + vl];
+          wv[kx][0] = widen(q.x); wv[kx][1] = widen(q.y);
+        }
+        const uint2* row = sx + (static_cast<size_t>(ry + ky * DIL) * p.Wp + ox0) * HV + vl;
+#pragma unroll
+        for (int xi = 0; xi < NI; ++xi) {
+          const uint2 q = row[xi * HV];
+          const uint64_t x0 = widen(q.x), x1 = widen(q.y);
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const int t = xi - kx * DIL;  // compile-time after unrolling
+            if (t >= 0 && t < TW) {
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[t][0]) : "l"(x0), "l"(wv[kx][0]));
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[t][1]) : "l"(x1), "l"(wv[kx][1]));
+            }
+          }
+        }
+      }
+      auto finish = [&](auto actf) {
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+          if (ox0 + t < p.Wo) {
+            float a[4];
+            asm("mov.b64 {%0,%1}, %2;" : "=f"(a[0]), "=f"(a[1]) : "l"(acc[t][0]));
+            asm("mov.b64 {%0,%1}, %2;" : "=f"(a[2]), "=f"(a[3]) : "l"(acc[t][1]));
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = actf(fmaf(a[j], sc[j], sh[j]));
+            const uint2 packed = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+            *reinterpret_cast<uint2*>(out_n + (static_cast<size_t>(oy0 + ry) * p.Wo + ox0 + t) * p.C) = packed;
+            if (p.gap) {
+              acc_gap[0] += __uint_as_float(packed.x << 16); acc_gap[1] += __uint_as_float(packed.x & 0xFFFF0000u);
+              acc_gap[2] += __uint_as_float(packed.y << 16); acc_gap[3] += __uint_as_float(packed.y & 0xFFFF0000u);
+            }
+          }
+        }
+      };
+      if (p.act == ACT_HSWISH) finish([](float v) { return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f); });
+      else if (p.act == ACT_RELU) finish([](float v) { return fmaxf(v, 0.f); });
+      else if (p.act == ACT_NONE) finish([](float v) { return v; });
+      else finish([&](float v) { return apply_act(v, p.act); });
+    }
+  }
+  if (p.gap) {
+    const int cw = p.CVc * 8;
+    __syncthreads();  // every thread is done with the staged tile: its first bytes become the reduction buffer (PLh * cw floats <= 4 KB)
+    if (pl < PLh) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(pl * HV + vl) * 4 + j] = active ? acc_gap[j] : 0.f;
+    }
+    __syncthreads();
+    for (int cl = tid; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < p.C) {
+        float s = 0.f;
+        for (int l = 0; l < PLh; ++l) s += red[l * cw + cl];
+        p.gap[(static_cast<size_t>(n) * p.bands + band) * p.C + c] = s;
+      }
+    }
+  }
+}
+
+int dw_phase() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTGSEG_DW_PHASE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 // MTGSEG_DW_VARIANT (A/B switch): 0 (default) staged kernel, TMA box fill, packed fp32x2 FMAs; 4 = 0 with scalar FMAs; 3 staged kernel,
 // cp.async gather fill, scalar FMAs; 5 = 3 with packed FMAs (all four bit-identical; B=256 family time 1.57 / 1.58 / 2.03 / 2.03 ms); 2 legacy direct kernel, narrow strips; 1 legacy direct kernel, wide strips
 int dw_variant() {
@@ -319,8 +454,20 @@ int dw_variant() {
   }
   return v;
 }
-// 8-wide strips for the stride-1 5x5 layers were measured and rejected: 128 registers spill (b14 213 -> 317 us)
-inline int strip_width(int stride) { return dw_variant() != 1 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4); }
+// 8-wide strips at 8 channels per thread were measured and rejected: 128 registers spill (b14 213 -> 317 us).
+// Half-vector kernel + 8-vector channel groups: default for the dilated stride-1 5x5 layers (b13-b15).  Measured per layer at
+// B=256 (tools/dw_probe.py, outputs bit-identical): 8 ch/thread with 15-vector groups 159 / 214 / 214 us (31 % of the
+// shared-memory load wavefronts are bank-conflict replays: a warp's 16-byte lanes straddle 240-byte runs), half vectors with
+// 8-vector groups (every half-warp reads one aligned 128-byte run) 154 / 196 / 197 us; the undilated 5x5 layers (b5, b6) are
+// faster with the 8-channel kernel (105 vs 113 us).  Variant 7 forces the half kernel on every stride-1 5x5 layer.
+inline bool use_half(int k, int stride, int dil) {
+  if (k != 5 || stride != 1) return false;
+  return dw_variant() == 7 || (dw_variant() == 0 && dil == 2);
+}
+inline int strip_width(int stride, int k = 3, int dil = 1) {
+  if (use_half(k, stride, dil)) return 8;
+  return dw_variant() != 1 ? (stride == 1 ? 4 : 2) : (stride == 1 ? 8 : 4);
+}
 
 }  // namespace
 
@@ -342,8 +489,10 @@ DwPlan dw_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
   q.pad = (k - 1) / 2 * dil;
   q.Ho = (H + 2 * q.pad - dil * (k - 1) - 1) / stride + 1;
   q.Wo = (W + 2 * q.pad - dil * (k - 1) - 1) / stride + 1;
-  q.CV = C / 8; q.CVc = group_vectors(q.CV); q.PL = 256 / q.CVc;
-  q.TW = strip_width(stride);
+  q.CV = C / 8; q.CVc = group_vectors(q.CV);
+  if (use_half(k, stride, dil) && q.CVc > 8) q.CVc = 8;  // 16 half-vectors = one aligned 128-byte run per half-warp
+  q.PL = 256 / q.CVc;
+  q.TW = strip_width(stride, k, dil);
   q.strips = ceil_div(q.Wo, q.TW);
   // padded row: every strip (including the ragged last one) may read NI inputs from its first column
   const int NI = (q.TW - 1) * stride + (k - 1) * dil + 1;
@@ -397,7 +546,7 @@ template <int KS, int STRIDE, int DIL, int TW>
 int launch_smem(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
   const int v = dw_variant();
   CUtensorMap tmx{}, tmw{};
-  if (v == 0 || v == 4) {
+  if (v == 0 || v == 4 || v == 7) {
     // input [B][H][W][C] bf16 as a 4-D tensor, box = (group channels, padded row, band rows + halo, 1 image);
     // weights [k*k][C] as a 2-D tensor, box = (group channels, all taps).  No swizzle: the tile is read as stored.
     const unsigned long long xd[4] = {static_cast<unsigned long long>(a.C), static_cast<unsigned long long>(a.W),
@@ -414,11 +563,36 @@ int launch_smem(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaS
     if (rc != MTG_OK) return rc;
   }
   switch (v) {
-    case 0: return launch_smem2<KS, STRIDE, DIL, TW, true, true>(tmx, tmw, p, grid, smem, st);
+    case 0: case 7: return launch_smem2<KS, STRIDE, DIL, TW, true, true>(tmx, tmw, p, grid, smem, st);
     case 4: return launch_smem2<KS, STRIDE, DIL, TW, true, false>(tmx, tmw, p, grid, smem, st);
     case 5: return launch_smem2<KS, STRIDE, DIL, TW, false, true>(tmx, tmw, p, grid, smem, st);
     default: return launch_smem2<KS, STRIDE, DIL, TW, false, false>(tmx, tmw, p, grid, smem, st);
   }
+}
+
+template <int KS, int DIL>
+int launch_half(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
+  CUtensorMap tmx{}, tmw{};
+  const unsigned long long xd[4] = {static_cast<unsigned long long>(a.C), static_cast<unsigned long long>(a.W),
+                                    static_cast<unsigned long long>(a.H), static_cast<unsigned long long>(a.B)};
+  const unsigned long long xs[3] = {xd[0] * 2, xd[0] * xd[1] * 2, xd[0] * xd[1] * xd[2] * 2};
+  const unsigned xb[4] = {static_cast<unsigned>(p.CVc * 8), static_cast<unsigned>(p.Wp), static_cast<unsigned>(p.R), 1u};
+  MTG_REQUIRE(xb[1] <= 256 && xb[2] <= 256, MTG_ERR_UNSUPPORTED, "dwconv: tile %ux%u exceeds the TMA box limit", xb[1], xb[2]);
+  int rc = make_tma_map_bf16(&tmx, a.in, 4, xd, xs, xb, 0);
+  if (rc != MTG_OK) return rc;
+  const unsigned long long wd[2] = {static_cast<unsigned long long>(a.C), static_cast<unsigned long long>(KS * KS)};
+  const unsigned long long ws[1] = {wd[0] * 2};
+  const unsigned wb[2] = {static_cast<unsigned>(p.CVc * 8), static_cast<unsigned>(KS * KS)};
+  rc = make_tma_map_bf16(&tmw, a.w, 2, wd, ws, wb, 0);
+  if (rc != MTG_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MTG_CUDA(cudaFuncSetAttribute(dwconv_half_kernel<KS, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    configured = true;
+  }
+  dwconv_half_kernel<KS, DIL><<<grid, 256, smem, st>>>(tmx, tmw, p);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
 }
 
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
@@ -429,14 +603,14 @@ int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
     MTG_REQUIRE(q.ok, MTG_ERR_UNSUPPORTED, "dwconv: feature map %dx%d (C=%d, k=%d) does not fit the shared-memory tiling", a.H, a.W, a.C, a.k);
     MTG_REQUIRE(!a.gap_partial || a.chunks == q.bands, MTG_ERR_ARG, "dwconv: gap_partial must have mtgseg_dwconv_chunks() = %d chunks, got %d", q.bands, a.chunks);
     DwS s{a.in, a.w, a.out, a.scale, a.shift, a.gap_partial, a.act, a.H, a.W, a.C, q.Ho, q.Wo, q.pad, q.CV, q.CVc, q.PL, q.strips,
-          q.band, q.bands, q.R, q.Wp, q.xoff};
+          q.band, q.bands, q.R, q.Wp, q.xoff, dw_phase()};
     dim3 grid(q.bands, ceil_div(q.CV, q.CVc), a.B);
     switch (a.k * 100 + a.stride * 10 + a.dil) {
       case 311: return launch_smem<3, 1, 1, 4>(a, s, grid, q.smem, st);
       case 321: return launch_smem<3, 2, 1, 2>(a, s, grid, q.smem, st);
-      case 511: return launch_smem<5, 1, 1, 4>(a, s, grid, q.smem, st);
+      case 511: return use_half(5, 1, 1) ? launch_half<5, 1>(a, s, grid, q.smem, st) : launch_smem<5, 1, 1, 4>(a, s, grid, q.smem, st);
       case 521: return launch_smem<5, 2, 1, 2>(a, s, grid, q.smem, st);
-      case 512: return launch_smem<5, 1, 2, 4>(a, s, grid, q.smem, st);
+      case 512: return use_half(5, 1, 2) ? launch_half<5, 2>(a, s, grid, q.smem, st) : launch_smem<5, 1, 2, 4>(a, s, grid, q.smem, st);
       default:
         MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: (k=%d, stride=%d, dilation=%d) is not one of the MobileNetV3 shapes", a.k, a.stride, a.dil);
     }
