@@ -12,6 +12,8 @@
 // gradient fused as the epilogue's "residual") or the depthwise dgrad kernel.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "net.h"
 
 namespace mtgseg {
@@ -45,6 +47,7 @@ struct TrainBufs {
   float* ones = nullptr; float* zeros = nullptr;  // [max(B*960, 960)] constants
   // backward scratch
   bf16* g[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // activation-sized gradient buffers
+  bf16* dzpool[4] = {nullptr, nullptr, nullptr, nullptr};  // dz buffers: rotated so that the side-stream wgrad of one layer may still read its dz while the main stream produces the next
   float* c1 = nullptr; float* c2 = nullptr;                    // BN backward coefficients [960]
   float* pooled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [B][16][960] / [B][960] SE backward vectors
   float* d_o = nullptr; float* dh2 = nullptr;
@@ -108,6 +111,8 @@ void layout(const NetPlan& P, int B, uint8_t* ws, TrainBufs& T) {
   T.ones = f32(static_cast<size_t>(B) * 960);
   T.zeros = f32(static_cast<size_t>(B) * 960);
   for (int k = 0; k < 5; ++k) T.g[k] = bf(max_act);
+  T.dzpool[0] = T.g[1];
+  for (int k = 1; k < 4; ++k) T.dzpool[k] = bf(max_act);
   T.c1 = f32(960); T.c2 = f32(960);
   for (int k = 0; k < 5; ++k) T.pooled[k] = f32(static_cast<size_t>(B) * 16 * 960);
   T.d_o = f32(static_cast<size_t>(B) * T.Hl * T.Wl * nc);
@@ -250,6 +255,40 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
   return MTG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradients on a second stream.  At B = 32 the backward chain (BN backward -> dgrad -> BN backward ...) is a
+// sequence of small kernels that leave most SMs idle, and the weight-gradient kernels (tcgen05 wgrad, depthwise wgrad, stem
+// wgrad: ~21 % of the step in the ncu launch list) only need a layer's dz and its saved input; nothing downstream waits for
+// them.  They run on a private non-blocking stream: "dz ready" events main -> side, "dz buffer free" events side -> main (dz
+// rotates through four buffers), and the main stream waits for the side stream before the call returns.
+// MTGSEG_TRAIN_SIDE=0 keeps everything on one stream (A/B).
+// ---------------------------------------------------------------------------------------------------------
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ready[4] = {}, freed[4] = {}, done = nullptr;
+  bool ok = false;
+};
+SideStream* side_stream() {
+  static const bool enabled = [] { const char* e = getenv("MTGSEG_TRAIN_SIDE"); return !(e && e[0] == '0'); }();
+  if (!enabled) return nullptr;
+  static SideStream per_dev[16];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& S = per_dev[dev];
+  if (!S.ok) {
+    if (cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int k = 0; k < 4; ++k) {
+      if (cudaEventCreateWithFlags(&S.ready[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&S.freed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    S.ok = true;
+  }
+  return &S;
+}
+
 int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
   TrainBufs T;
   layout(P, io.batch, ws, T);
@@ -260,6 +299,27 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   const int Hh = T.Hh, Wh = T.Wh, Hl = T.Hl, Wl = T.Wl, Mh = B * Hh * Wh;
   const int H = P.desc.in_h, W = P.desc.in_w;
   auto need = [&](int idx) { return io.grads[idx] != nullptr; };
+  SideStream* side = side_stream();
+  Ctx cs{P, io, T, side ? side->s : st, B};  // context of the weight-gradient launches
+  int dz_next = 0, dz_cur = 0;
+  bool freed_valid[4] = {false, false, false, false};
+  // next dz buffer; the main stream first waits until the side-stream reader of its previous contents is done
+  auto new_dz = [&]() -> bf16* {
+    dz_cur = side ? (dz_next++ & 3) : 0;
+    if (side && freed_valid[dz_cur]) cudaStreamWaitEvent(st, side->freed[dz_cur], 0);
+    return T.dzpool[dz_cur];
+  };
+  // hand the current dz buffer (just produced on the main stream) to the side stream; call before the side launch
+  auto dz_to_side = [&]() {
+    if (!side) return;
+    cudaEventRecord(side->ready[dz_cur], st);
+    cudaStreamWaitEvent(side->s, side->ready[dz_cur], 0);
+  };
+  auto dz_side_done = [&]() {  // call after the side launch that read the current dz buffer
+    if (!side) return;
+    cudaEventRecord(side->freed[dz_cur], side->s);
+    freed_valid[dz_cur] = true;
+  };
   MTG_REQUIRE(need(P.high_w) && need(P.high_b) && need(P.low_w) && need(P.low_b) && need(P.scale_w) && need(P.cbr.w_idx) &&
                   need(P.last.w_idx) && need(P.stem.w_idx), MTG_ERR_ARG, "backward: missing gradient buffers");
 
@@ -291,25 +351,29 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
     RC(launch_outer_sum(dpre_s, T.hsum, 1, 1.f / static_cast<float>(Hh * Wh), c.grad(P.scale_w), nullptr, B, ic, 960, st));
   }
   // cbr: BN(ReLU) backward, wgrad 3x3, dgrad 3x3
-  bf16* dz_cbr = T.g[1];
+  bf16* dz_cbr = new_dz();
   RC(bn_bwd(c, P.cbr, T.cbr, ACT_RELU, dcbr, dz_cbr, nullptr, nullptr));
   {
     WgradArgs w;
     w.dz = dz_cbr; w.x = T.last.y; w.dw = c.grad(P.cbr.w_idx); w.M = Mh; w.N = ic; w.K = 960; w.taps = 9; w.H = Hh; w.W = Wh;
-    RC(wgrad(c, w, Hh * Wh));
+    dz_to_side();
+    RC(wgrad(cs, w, Hh * Wh));
+    dz_side_done();
     ConvGemmArgs g;
     g.a = dz_cbr; g.w = c.wb(P.cbr.wt_off); g.out = T.g[0]; g.M = Mh; g.N = 960; g.K = ic; g.act = ACT_NONE;
     g.conv3x3 = 1; g.B = B; g.H = Hh; g.W = Wh;
     RC(launch_conv_gemm(g, st));
   }
   // last 1x1 (160 -> 960): d high = conv dgrad + broadcast of the pooled gradient of the scale branch
-  bf16* dz_last = T.g[1];
+  bf16* dz_last = new_dz();
   RC(bn_bwd(c, P.last, T.last, ACT_HSWISH, T.g[0], dz_last, T.ones, dgap_high));
   const bf16* last_in = T.blk[kNumBlocks - 1].project.y;
   {
     WgradArgs w;
     w.dz = dz_last; w.x = last_in; w.dw = c.grad(P.last.w_idx); w.M = Mh; w.N = 960; w.K = 160;
-    RC(wgrad(c, w, Hh * Wh));
+    dz_to_side();
+    RC(wgrad(cs, w, Hh * Wh));
+    dz_side_done();
   }
   bf16* d_out = T.g[0];  // gradient w.r.t. the current block's output
   RC(conv1x1_raw(c, dz_last, c.wb(P.last.wt_off), d_out, Mh, 160, 960, nullptr, 0, nullptr));
@@ -327,13 +391,15 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
     if (i == 3) {  // features[4] also feeds the head's low classifier
       RC(launch_add_bf16(d_out, dlow, d_out, static_cast<size_t>(Mo) * cf.cout, st));
     }
-    bf16* dz_p = T.g[1];
+    bf16* dz_p = new_dz();
     RC(bn_bwd(c, b.project, K.project, ACT_NONE, d_out, dz_p, nullptr, nullptr));
     {
       WgradArgs w;
       w.dz = dz_p; w.x = K.dw.y; w.dw = c.grad(b.project.w_idx); w.M = Mo; w.N = cf.cout; w.K = cf.cexp;
       w.a_scale = cf.se ? K.s : nullptr; w.hw = HWo;
-      RC(wgrad(c, w, HWo));
+      dz_to_side();
+      RC(wgrad(cs, w, HWo));
+      dz_side_done();
     }
     bf16* da = T.g[2];
     RC(conv1x1_raw(c, dz_p, c.wb(b.project.wt_off), da, Mo, cf.cexp, cf.cout, nullptr, 0, nullptr));
@@ -356,13 +422,15 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
       se_s = K.s;
       se_dmean = T.pooled[3];
     }
-    bf16* dz_d = T.g[1];
+    bf16* dz_d = new_dz();
     RC(bn_bwd(c, b.dw, K.dw, cf.act, da, dz_d, se_s, se_dmean));
     const bf16* dw_in = b.has_expand ? K.expand.y : inp;
     DwBwdArgs d;
     d.dz = dz_d; d.x = dw_in; d.w = c.wb(b.dw.w_off); d.dw = c.grad(b.dw.w_idx);
     d.B = B; d.H = K.Hin; d.W = K.Win; d.C = cf.cexp; d.k = cf.k; d.stride = cf.dil > 1 ? 1 : cf.stride; d.dil = cf.dil;
-    RC(launch_dw_wgrad(d, st));
+    dz_to_side();
+    RC(launch_dw_wgrad(d, cs.st));
+    dz_side_done();
     bf16* dy_e = T.g[2];
     d.dx = dy_e;
     if (d.stride == 1) {
@@ -378,11 +446,13 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
     bf16* d_inp = T.g[3];
     if (b.has_expand) {
       MTG_REQUIRE(need(b.expand.w_idx), MTG_ERR_ARG, "backward: missing gradient buffers (block %d expand)", i + 1);
-      bf16* dz_e = T.g[1];
+      bf16* dz_e = new_dz();
       RC(bn_bwd(c, b.expand, K.expand, cf.act, dy_e, dz_e, nullptr, nullptr));
       WgradArgs w;
       w.dz = dz_e; w.x = inp; w.dw = c.grad(b.expand.w_idx); w.M = Mi; w.N = cf.cexp; w.K = cf.cin;
-      RC(wgrad(c, w, K.Hin * K.Win));
+      dz_to_side();
+      RC(wgrad(cs, w, K.Hin * K.Win));
+      dz_side_done();
       RC(conv1x1_raw(c, dz_e, c.wb(b.expand.wt_off), d_inp, Mi, cf.cin, cf.cexp, nullptr, 0, res ? d_out : nullptr));
     } else if (res) {
       RC(launch_add_bf16(dy_e, d_out, d_inp, static_cast<size_t>(Mi) * cf.cin, st));
@@ -395,9 +465,15 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
     d_out = T.g[0];
   }
   // ---- stem -----------------------------------------------------------------------------------------
-  bf16* dz_stem = T.g[1];
+  bf16* dz_stem = new_dz();
   RC(bn_bwd(c, P.stem, T.stem, ACT_HSWISH, d_out, dz_stem, nullptr, nullptr));
-  RC(launch_stem_wgrad(io.x, dz_stem, c.grad(P.stem.w_idx), B, H, W, st));
+  dz_to_side();
+  RC(launch_stem_wgrad(io.x, dz_stem, c.grad(P.stem.w_idx), B, H, W, cs.st));
+  dz_side_done();
+  if (side) {  // every gradient is complete before the caller's next kernel on `st` (optimizer, all-reduce)
+    MTG_CUDA(cudaEventRecord(side->done, side->s));
+    MTG_CUDA(cudaStreamWaitEvent(st, side->done, 0));
+  }
   return MTG_OK;
 }
 
