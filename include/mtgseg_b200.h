@@ -209,6 +209,15 @@ int mtgseg_pose_pack_weights(const mtgseg_pose_desc* desc, const void* const* pa
 int mtgseg_pose_forward(const mtgseg_pose_desc* desc, const float* features, const void* packed, float* heatmaps, float* coords,
                         void* workspace, size_t workspace_bytes, int batch, void* stream);
 int mtgseg_decode_heatmaps(const float* heatmaps, float* coords, int batch, int num_keypoints, int H, int W, void* stream);
+/* CornerMetrics.update (train-pose-estimation_custom/metrics.py:29-73): per (image, keypoint) the argmax of the predicted and of the
+ * target heatmap [B,K,H,W] fp32, scaled to image pixels, Euclidean distance.  ACCUMULATES into acc (32 bytes, zero it to reset):
+ * { double sum_of_distances; uint64 n; uint64 n_within_3px; uint64 n_within_6px } (compute(): metrics.py:75-100). */
+int mtgseg_corner_metrics(const float* pred, const float* target, void* acc, int batch, int num_keypoints, int H, int W, float image_w,
+                          float image_h, void* stream);
+/* CornerLoss = nn.MSELoss on heatmaps (metrics.py:105-136): loss[0] = mean((pred-target)^2); dpred (optional) = 2 (pred-target) / n.
+ * scratch >= mtgseg_mse_scratch_floats() floats.  Deterministic (fixed reduction order). */
+size_t mtgseg_mse_scratch_floats(void);
+int mtgseg_mse_loss(const float* pred, const float* target, float* dpred, float* loss, float* scratch, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,9 @@ SIGNATURES = {
     "mtgseg_pose_pack_weights": (_i, [C.POINTER(PoseDesc), C.POINTER(_vp), _i, _vp, _vp]),
     "mtgseg_pose_forward": (_i, [C.POINTER(PoseDesc), _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "mtgseg_decode_heatmaps": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "mtgseg_corner_metrics": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_float, C.c_float, _vp]),
+    "mtgseg_mse_scratch_floats": (_sz, []),
+    "mtgseg_mse_loss": (_i, [_vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
     "mtgseg_launch_count": (C.c_ulonglong, []),
     "mtgseg_forward_infer_profiled": (_i, [_ND, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp, C.POINTER(LayerProf), _i,
                                            C.POINTER(_i)]),

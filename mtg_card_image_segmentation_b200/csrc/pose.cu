@@ -92,11 +92,8 @@ __global__ void adaptive_pool_kernel(const bf16* __restrict__ in, float* __restr
 }
 
 // per (image, keypoint): argmax over H*W (lowest index on ties) -> (x/(W-1), y/(H-1)) interleaved
-__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ hm, float* __restrict__ coords, int NK, int H, int W) {
-  __shared__ float sv[256];
-  __shared__ int si[256];
-  const int bk = blockIdx.x, n = H * W;
-  const float* p = hm + static_cast<size_t>(bk) * n;
+// first maximum of p[0..n) over the block (ties -> lowest index, as torch.max on the CPU); result valid in thread 0
+__device__ __forceinline__ int block_argmax(const float* __restrict__ p, int n, float* sv, int* si) {
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int i = threadIdx.x; i < n; i += 256) {
@@ -112,11 +109,79 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h
     }
     __syncthreads();
   }
+  const int r = si[0];
+  __syncthreads();  // sv / si may be reused by the caller
+  return r;
+}
+
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ hm, float* __restrict__ coords, int NK, int H, int W) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const int bk = blockIdx.x, n = H * W;
+  const int idx = block_argmax(hm + static_cast<size_t>(bk) * n, n, sv, si);
   if (threadIdx.x == 0) {
-    const int idx = si[0], b = bk / NK, k = bk % NK;
+    const int b = bk / NK, k = bk % NK;
     coords[static_cast<size_t>(b) * NK * 2 + 2 * k] = static_cast<float>(idx % W) / static_cast<float>(W - 1);
     coords[static_cast<size_t>(b) * NK * 2 + 2 * k + 1] = static_cast<float>(idx / W) / static_cast<float>(H - 1);
   }
+}
+
+// CornerMetrics.update (train-pose-estimation_custom/metrics.py:29-73): argmax of the predicted and of the target heatmap,
+// both scaled to image pixels, Euclidean distance; accumulated as {sum of distances (fp64), n, n(<=3px), n(<=6px)}.
+// The fp32 arithmetic follows the reference's operation order (x * image_w / (W-1); sqrt(dx*dx + dy*dy) without FMA
+// contraction), so the threshold counts are exactly the reference's.
+struct CornerAcc { double sum; unsigned long long n, n3, n6; };
+__global__ void __launch_bounds__(256) corner_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target, CornerAcc* acc,
+                                                             int H, int W, float image_w, float image_h) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const int n = H * W;
+  const int ip = block_argmax(pred + static_cast<size_t>(blockIdx.x) * n, n, sv, si);
+  const int it = block_argmax(target + static_cast<size_t>(blockIdx.x) * n, n, sv, si);
+  if (threadIdx.x == 0) {
+    const float wd = static_cast<float>(W - 1), hd = static_cast<float>(H - 1);
+    const float px = __fdiv_rn(__fmul_rn(static_cast<float>(ip % W), image_w), wd), py = __fdiv_rn(__fmul_rn(static_cast<float>(ip / W), image_h), hd);
+    const float tx = __fdiv_rn(__fmul_rn(static_cast<float>(it % W), image_w), wd), ty = __fdiv_rn(__fmul_rn(static_cast<float>(it / W), image_h), hd);
+    const float dx = __fsub_rn(px, tx), dy = __fsub_rn(py, ty);
+    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    atomicAdd(&acc->sum, static_cast<double>(dist));
+    atomicAdd(&acc->n, 1ull);
+    if (dist <= 3.0f) atomicAdd(&acc->n3, 1ull);
+    if (dist <= 6.0f) atomicAdd(&acc->n6, 1ull);
+  }
+}
+
+// CornerLoss = nn.MSELoss() on the heatmaps (metrics.py:105-136): mean((p - t)^2), optional dpred = 2 (p - t) / n.
+// Two fixed-order stages (per-block partial sums, then one block): run-to-run deterministic.
+constexpr int MSE_BLOCKS = 1024;
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, float* __restrict__ dpred,
+                                                          float* __restrict__ partial, long long n, float gscale) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float d = p[i] - t[i];
+    s = fmaf(d, d, s);
+    if (dpred) dpred[i] = d * gscale;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) mse_final_kernel(const float* __restrict__ partial, int blocks, double inv_n, float* __restrict__ loss) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < blocks; i += 256) s += static_cast<double>(partial[i]);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = static_cast<float>(red[0] * inv_n);
 }
 
 struct PosePlan {
@@ -216,6 +281,30 @@ int mtgseg_pose_pack_weights(const mtgseg_pose_desc* d, const void* const* param
 int mtgseg_decode_heatmaps(const float* heatmaps, float* coords, int batch, int num_keypoints, int H, int W, void* stream) {
   MTG_REQUIRE(heatmaps && coords && batch > 0 && num_keypoints > 0 && H > 1 && W > 1, MTG_ERR_ARG, "decode_heatmaps: bad arguments");
   decode_kernel<<<batch * num_keypoints, 256, 0, static_cast<cudaStream_t>(stream)>>>(heatmaps, coords, num_keypoints, H, W);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int mtgseg_corner_metrics(const float* pred, const float* target, void* acc, int batch, int num_keypoints, int H, int W, float image_w,
+                          float image_h, void* stream) {
+  MTG_REQUIRE(pred && target && acc && batch > 0 && num_keypoints > 0 && H > 1 && W > 1, MTG_ERR_ARG, "corner_metrics: bad arguments");
+  static_assert(sizeof(CornerAcc) == 32, "accumulator layout is part of the ABI: {double sum; uint64 n, n3, n6}");
+  corner_metrics_kernel<<<batch * num_keypoints, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, target, static_cast<CornerAcc*>(acc), H, W,
+                                                                                             image_w, image_h);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+size_t mtgseg_mse_scratch_floats(void) { return MSE_BLOCKS; }
+
+int mtgseg_mse_loss(const float* pred, const float* target, float* dpred, float* loss, float* scratch, long long n, void* stream) {
+  MTG_REQUIRE(pred && target && loss && scratch && n > 0, MTG_ERR_ARG, "mse_loss: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > MSE_BLOCKS) blocks = MSE_BLOCKS;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mse_partial_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(pred, target, dpred, scratch, n, 2.0f / static_cast<float>(n));
+  MTG_LAUNCH_CHECK();
+  mse_final_kernel<<<1, 256, 0, st>>>(scratch, static_cast<int>(blocks), 1.0 / static_cast<double>(n), loss);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -85,3 +85,82 @@ def decode_heatmaps(heatmaps: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(h.device):
         N.check(N.load().mtgseg_decode_heatmaps(h.data_ptr(), coords.data_ptr(), B, K, H, W, N.stream_ptr()), "mtgseg_decode_heatmaps")
     return coords
+
+
+class _MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        if not pred.is_cuda:
+            raise RuntimeError("CornerLoss: CUDA tensors required (no CPU fallback)")
+        if pred.shape != target.shape:
+            raise RuntimeError(f"CornerLoss: shape mismatch {tuple(pred.shape)} vs {tuple(target.shape)}")
+        p = pred.detach().float().contiguous()
+        t = target.detach().float().contiguous()
+        lib = N.load()
+        need_grad = pred.requires_grad
+        dpred = torch.empty_like(p) if need_grad else None
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        scratch = torch.empty(lib.mtgseg_mse_scratch_floats(), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            N.check(lib.mtgseg_mse_loss(p.data_ptr(), t.data_ptr(), N.ptr(dpred), loss.data_ptr(), scratch.data_ptr(), p.numel(),
+                                        N.stream_ptr()), "mtgseg_mse_loss")
+        ctx.save_for_backward(dpred) if need_grad else None
+        ctx.in_dtype = pred.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dpred,) = ctx.saved_tensors
+        return (dpred * grad_out).to(ctx.in_dtype), None
+
+
+class CornerLoss(nn.Module):
+    """``CornerLoss`` (train-pose-estimation_custom/metrics.py:105-136): heatmap MSE, value and gradient from one fused pass."""
+
+    def __init__(self, image_size=(480, 640), heatmap_size=(160, 120)):
+        super().__init__()
+        self.image_size = image_size
+        self.heatmap_size = heatmap_size
+
+    def forward(self, predictions: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        return _MseFn.apply(predictions, targets)
+
+
+class CornerMetrics:
+    """``CornerMetrics`` (train-pose-estimation_custom/metrics.py:8-100): same constructor, ``reset`` / ``update`` / ``compute`` and
+    result keys.  ``update`` is one kernel (argmax of both heatmaps, pixel distance, counts) accumulating on the device; nothing
+    is copied to the host until ``compute``.  The reference keeps every distance in a Python list; here the accumulator is
+    {fp64 sum, n, n(<=3 px), n(<=6 px)}, which is all ``compute`` needs."""
+
+    def __init__(self, image_size=(480, 640)):
+        self.image_size = image_size
+        self._acc = None
+        self.reset()
+
+    def reset(self):
+        if self._acc is not None:
+            self._acc.zero_()
+
+    def update(self, predictions: torch.Tensor, targets: torch.Tensor):
+        if not predictions.is_cuda:
+            raise RuntimeError("CornerMetrics: CUDA tensors required (no CPU fallback)")
+        p = predictions.detach().float().contiguous()
+        t = targets.detach().float().contiguous()
+        if p.shape != t.shape or p.dim() != 4:
+            raise RuntimeError(f"CornerMetrics: expected two (B,K,H,W) heatmap tensors, got {tuple(p.shape)} and {tuple(t.shape)}")
+        if self._acc is None or self._acc.device != p.device:
+            self._acc = torch.zeros(4, dtype=torch.int64, device=p.device)  # 32 bytes: {double sum; uint64 n, n3, n6}
+        B, K, H, W = p.shape
+        with torch.cuda.device(p.device):
+            N.check(N.load().mtgseg_corner_metrics(p.data_ptr(), t.data_ptr(), self._acc.data_ptr(), B, K, H, W, float(self.image_size[0]),
+                                                   float(self.image_size[1]), N.stream_ptr()), "mtgseg_corner_metrics")
+
+    def compute(self):
+        if self._acc is None:
+            return {"corner_acc_3px": 0.0, "corner_acc_6px": 0.0, "mean_corner_distance": 0.0}
+        host = self._acc.cpu()
+        total = float(host[:1].view(torch.float64)[0])
+        n, n3, n6 = (int(v) for v in host[1:])
+        if n == 0:
+            return {"corner_acc_3px": 0.0, "corner_acc_6px": 0.0, "mean_corner_distance": 0.0}
+        return {"corner_acc_3px": n3 / n * 100, "corner_acc_6px": n6 / n * 100, "mean_corner_distance": total / n}

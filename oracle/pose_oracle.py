@@ -69,3 +69,33 @@ def decode_heatmaps(hm):
     coords[:, 0::2] = (idx % W).float() / (W - 1)
     coords[:, 1::2] = (idx // W).float() / (H - 1)
     return coords
+
+
+def corner_loss(pred, target):
+    """CornerLoss.forward (metrics.py:125-136): nn.MSELoss() on the heatmaps."""
+    return ((pred.float() - target.float()) ** 2).mean()
+
+
+def corner_distances(pred, target, image_size=(480, 640)):
+    """CornerMetrics.update (metrics.py:29-73): per (image, keypoint) pixel distance between the argmax of the predicted and of the
+    target heatmap; float32 arithmetic in the reference's order (torch float32 coordinates, numpy float32 distance)."""
+    import numpy as np
+    B, K, H, W = pred.shape
+    pi = pred.reshape(B, K, -1).max(dim=2).indices
+    ti = target.reshape(B, K, -1).max(dim=2).indices
+    px = ((pi % W).float() * image_size[0] / (W - 1)).numpy(); py = ((pi // W).float() * image_size[1] / (H - 1)).numpy()
+    tx = ((ti % W).float() * image_size[0] / (W - 1)).numpy(); ty = ((ti // W).float() * image_size[1] / (H - 1)).numpy()
+    out = []
+    for i in range(B):
+        for j in range(K):
+            out.append(np.sqrt((px[i, j] - tx[i, j]) ** 2 + (py[i, j] - ty[i, j]) ** 2))
+    return out
+
+
+def corner_compute(distances):
+    """CornerMetrics.compute (metrics.py:75-100)."""
+    import numpy as np
+    if not distances:
+        return {"corner_acc_3px": 0.0, "corner_acc_6px": 0.0, "mean_corner_distance": 0.0}
+    d = np.array(distances)
+    return {"corner_acc_3px": np.mean(d <= 3.0) * 100, "corner_acc_6px": np.mean(d <= 6.0) * 100, "mean_corner_distance": np.mean(d)}

@@ -77,3 +77,46 @@ def test_pose_head_full_size():
     assert tuple(hm.shape) == (2, 4, 120, 160) and tuple(coords.shape) == (2, 8)
     emax, el2 = D.report("pose full vs bf16-emulated oracle", hm.cpu(), emu)
     assert emax <= 1.5e-2 and el2 <= 1.5e-2
+
+
+def test_corner_metrics_and_loss_oracle_vs_reference_golden():
+    """CornerMetrics.update/compute and CornerLoss of the unmodified reference (recorded by oracle/make_golden_pose.py) vs the
+    oracle restatement: every distance bit-identical (float32 arithmetic in the reference's order), compute() identical."""
+    g = load_golden("pose.pt")
+    p, t = g["metrics"]["pred"].float(), g["metrics"]["target"].float()
+    for case in g["metrics"]["cases"]:
+        d = PO.corner_distances(p[:3], t[:3], case["image_size"]) + PO.corner_distances(p[3:], t[3:], case["image_size"])
+        assert [float(v) for v in d] == case["distances"]
+        got = PO.corner_compute(d)
+        assert {k: float(v) for k, v in got.items()} == case["compute"]
+    assert PO.corner_compute([]) == g["metrics"]["empty"]
+    assert float(PO.corner_loss(p, t)) == pytest.approx(g["loss"]["value"], rel=1e-6)
+
+
+@pytest.mark.gpu
+def test_corner_metrics_and_loss_cuda_vs_golden():
+    """The CUDA CornerMetrics / CornerLoss against the reference's recorded results: threshold counts exact (integer work),
+    mean distance and loss to 1e-6 relative, gradient of the loss to 1e-6."""
+    from mtg_card_image_segmentation_b200.pose import CornerLoss, CornerMetrics
+    g = load_golden("pose.pt")
+    p, t = g["metrics"]["pred"].float().cuda(), g["metrics"]["target"].float().cuda()
+    for case in g["metrics"]["cases"]:
+        m = CornerMetrics(case["image_size"])
+        assert m.compute() == g["metrics"]["empty"]
+        m.update(p[:3], t[:3])
+        m.update(p[3:], t[3:])
+        got, want = m.compute(), case["compute"]
+        assert got["corner_acc_3px"] == want["corner_acc_3px"] and got["corner_acc_6px"] == want["corner_acc_6px"]
+        assert got["mean_corner_distance"] == pytest.approx(want["mean_corner_distance"], rel=1e-6)
+        m.reset()
+        m.update(p[:1], t[:1])
+        d = PO.corner_distances(p[:1].cpu(), t[:1].cpu(), case["image_size"])
+        assert m.compute()["mean_corner_distance"] == pytest.approx(float(sum(float(v) for v in d) / len(d)), rel=1e-6)
+    pg = p.clone().requires_grad_(True)
+    loss = CornerLoss()(pg, t)
+    assert float(loss.detach()) == pytest.approx(g["loss"]["value"], rel=1e-6)
+    (3.0 * loss).backward()
+    want = g["loss"]["grad_sample"].cuda() * 3.0
+    assert torch.allclose(pg.grad.reshape(-1)[::53], want, rtol=1e-6, atol=1e-12)
+    # run-to-run determinism of the two-stage reduction
+    assert float(CornerLoss()(p, t)) == float(CornerLoss()(p, t))
