@@ -135,6 +135,42 @@ def test_training_reduces_loss_and_eval_uses_new_stats():
     assert D.report("eval after training vs emulated oracle", z, ref)[0] <= 2e-2
 
 
+def test_grad_scaler_loop_matches_plain_step():
+    """train/train.py:96-105: scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update().  The scaled gradient flows back
+    through the fused loss and the native backward; after unscaling, one AdamW step must land where the unscaled step lands
+    (the scale is a power of two: exact in fp32, up to the bf16 rounding of the scaled activations' gradients)."""
+    x, m = O.synthetic_cards(4, seed=5, height=64, width=48)
+    sd = O.make_weights(41)
+    xc, mc = x.cuda(), m.cuda()
+
+    def one_step(scale):
+        model = _train_model(sd)
+        opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        crit = M.CombinedLoss()
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(xc), mc)
+        if scale:
+            scaler = torch.amp.GradScaler("cuda", init_scale=scale)
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)  # as for gradient clipping in the reference's loop
+            scaler.step(opt)
+            scaler.update()
+            assert scaler.get_scale() == scale  # no inf / nan was found
+        else:
+            loss.backward()
+            opt.step()
+        return float(loss.detach()), [p.detach().float().cpu().clone() for p in model.parameters()]
+
+    l0, p0 = one_step(0)
+    l1, p1 = one_step(1024.0)
+    assert l0 == l1
+    worst = max(float((a - b).abs().max()) for a, b in zip(p0, p1))
+    moved = max(float((a - sd[k].float()).abs().max()) for a, (k, _) in zip(p0, [kv for kv in _train_model(sd).named_parameters()]))
+    print(f"GradScaler step vs plain step: max param difference {worst:.3e} (a step moves parameters by up to {moved:.3e})")
+    # AdamW normalises the gradient: a 1e-3 step; the two runs may differ by bf16 rounding of scaled vs unscaled gradients
+    assert moved > 5e-4 and worst <= 0.05 * moved  # measured 4.5e-6 vs 1e-3
+
+
 # ------------------------------------------------------------------------------------------------------------
 # per-kernel backward checks against torch autograd on identical (bf16-rounded) inputs
 # ------------------------------------------------------------------------------------------------------------
