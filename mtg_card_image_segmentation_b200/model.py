@@ -143,7 +143,7 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, out_dtype, *params):
-        tensors = model._state_tensors()
+        tensors = model._step_tensors  # resolved by the caller: parameters, or masked non-leaf weights under active pruning
         logits, x32 = model.engine().train_forward(tensors, x, out_dtype)
         ctx.model, ctx.tensors, ctx.x32 = model, tensors, x32
         ctx.param_ids = {id(p): i for i, p in enumerate(params)}
@@ -175,6 +175,11 @@ class CardSegmentationModel(nn.Module):
         self.model = _LRASPP(num_classes, inter_channels=128)
         self._engine = None
         self._state_cache = None
+        self._state_sig = None
+        self._has_masks = False
+        self._slots = None
+        self._param_slots = None
+        self._ref_keys = list(self.state_dict().keys())  # the reference's 319-key layout (train/utils.py:227-280 checkpoints)
         self.last_flat_grad = None
 
     # -- engine plumbing ---------------------------------------------------------------------
@@ -183,12 +188,45 @@ class CardSegmentationModel(nn.Module):
             self._engine = SegEngine(self.num_classes, self.model.classifier.cbr[0].out_channels)
         return self._engine
 
+    def _state_slots(self):
+        """(module, attribute) of the 319 reference state entries, in reference order.  Captured once: the key list of a freshly
+        built model IS the reference layout; torch.nn.utils.prune later renames `weight` -> `weight_orig` + `weight_mask` in the
+        state_dict, but the effective tensor is still reachable as `module.weight`."""
+        if self._slots is None:
+            slots = []
+            for key in self._ref_keys:
+                prefix, _, attr = key.rpartition(".")
+                slots.append((self.get_submodule(prefix) if prefix else self, attr))
+            self._slots = slots
+            # the slots that are Parameters in the reference layout: their identity validates the cache
+            self._param_slots = [(m, a) for m, a in slots if a in m._parameters]
+        return self._slots
+
     def _state_tensors(self):
-        """The 319 state tensors in reference order (cached: building a state_dict costs ~0.3 ms per call).  Module
-        surgery that adds/removes parameters (e.g. torch.nn.utils.prune) must call ``invalidate_cache()``."""
-        if self._state_cache is None:
-            self._state_cache = list(self.state_dict(keep_vars=True).values())
-        return self._state_cache
+        """The 319 state tensors in reference order.  Cached (resolving them costs ~0.1 ms) and self-validating: the cache is
+        keyed on the identity of the parameters, so module surgery that swaps Parameter objects (torch.nn.utils.prune apply /
+        remove, train/prune.py:60-113) is picked up without any call from the user.  While pruning masks are active
+        (evaluation and fine-tuning of a masked model, train/prune.py:144-175) the effective `weight = weight_orig * weight_mask` is
+        refreshed through the pruning hook on every call (the native path never runs the child modules' forward, which is what
+        normally triggers that hook) and nothing is cached; under autograd it is a non-leaf tensor, so gradients reach `weight_orig`
+        already multiplied by the mask."""
+        self._state_slots()
+        # ~20 us: one dict lookup per parameter slot (walking self.parameters() costs 0.5 ms).  A pruned `weight` leaves
+        # module._parameters (-> None), prune.remove registers a new Parameter object: both change the signature.
+        sig = tuple(id(m._parameters.get(a)) for m, a in self._param_slots)
+        if self._state_cache is not None and sig == self._state_sig and not self._has_masks:
+            return self._state_cache
+        self._has_masks = False
+        for mod in {m for m, _ in self._state_slots()}:
+            for hook in mod._forward_pre_hooks.values():
+                if isinstance(hook, torch.nn.utils.prune.BasePruningMethod):
+                    hook(mod, None)  # module.<name> = <name>_orig * <name>_mask
+                    self._has_masks = True
+        tensors = [getattr(m, a) for m, a in self._state_slots()]
+        if self._has_masks and self._engine is not None:
+            self._engine._stats_dirty = True  # recomputed tensors may reuse an address with version 0: always repack
+        self._state_cache, self._state_sig = tensors, sig
+        return tensors
 
     def invalidate_cache(self):
         self._state_cache = None
@@ -214,7 +252,9 @@ class CardSegmentationModel(nn.Module):
             if torch.is_grad_enabled() and any(p.requires_grad for p in params):
                 if not all(p.requires_grad for p in params):
                     raise RuntimeError("the CUDA training step computes all parameter gradients; freezing a subset is not supported")
-                return _TrainStep.apply(self, x, out_dtype, *params)
+                tensors = self._state_tensors()
+                self._step_tensors = tensors
+                return _TrainStep.apply(self, x, out_dtype, *[t for t in tensors if t.requires_grad])
             return self.engine().train_forward(self._state_tensors(), x, out_dtype)[0]
         return self.engine().infer(self._state_tensors(), x, logits_dtype=out_dtype)
 

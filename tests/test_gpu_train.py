@@ -171,6 +171,63 @@ def test_grad_scaler_loop_matches_plain_step():
     assert moved > 5e-4 and worst <= 0.05 * moved  # measured 4.5e-6 vs 1e-3
 
 
+def test_pruning_flow_masks_active_then_removed():
+    """train/prune.py:52-113,144-175 on the drop-in model: global magnitude pruning of the conv children, evaluation and fine-tuning
+    with the masks ACTIVE (weight = weight_orig * weight_mask, maintained by torch's pruning hook), then prune.remove.  No call
+    into the package is needed: the state-tensor cache notices the module surgery by itself."""
+    import torch.nn.utils.prune as prune
+    x, m = O.synthetic_cards(4, seed=9, height=64, width=48)
+    sd = O.calibrate_running_stats(O.make_weights(43), x)
+    xc, mc = x.cuda(), m.cuda()
+    model = _train_model(sd).eval()
+    with torch.no_grad():
+        dense = model(xc).float().cpu()
+    convs = [(mod, "weight") for mod in model.model.modules() if isinstance(mod, torch.nn.Conv2d)]
+    prune.global_unstructured(convs, pruning_method=prune.L1Unstructured, amount=0.3)
+    assert len(list(model.state_dict().keys())) > 319  # weight_orig + weight_mask: the state_dict no longer has the reference layout
+    # (1) evaluation with masks active == the oracle on the masked weights
+    masked_sd = {k: v.detach().cpu() for k, v in zip(model._ref_keys, model._state_tensors())}
+    assert list(masked_sd) == list(sd) and all(masked_sd[k].shape == sd[k].shape for k in sd)
+    zeros = sum(int((masked_sd[k] == 0).sum()) for k in sd if sd[k].dim() == 4)
+    total = sum(sd[k].numel() for k in sd if sd[k].dim() == 4)
+    assert abs(zeros / total - 0.3) < 0.01
+    with torch.no_grad():
+        pruned = model(xc).float().cpu()
+    ref = O.forward_bf16_emulated(masked_sd, x)
+    assert D.report("pruned (masks active) vs emulated oracle on masked weights", pruned, ref)[0] <= 2e-2
+    assert float((pruned - dense).abs().max()) > 1e-3  # pruning did change the function
+    # (2) fine-tuning with masks active: masked positions get no gradient and stay zero in the effective weight
+    model.train()
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0)
+    crit = M.CombinedLoss()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(xc), mc)
+        loss.backward()
+        losses.append(float(loss.detach()))
+        opt.step()
+    assert all(l == l for l in losses)
+    for mod, _ in convs:
+        g = mod.weight_orig.grad
+        assert g is not None and bool((g[mod.weight_mask == 0] == 0).all())
+    moved = max(float((mod.weight_orig.detach().cpu() - sd[k]).abs().max()) for k, (mod, a) in zip(model._ref_keys, model._state_slots())
+                if a == "weight" and hasattr(mod, "weight_orig"))
+    assert moved > 1e-4  # the surviving weights were trained
+    model.eval()
+    with torch.no_grad():
+        tuned = model(xc).float()
+    eff = model._state_tensors()
+    assert all(bool((t[mod.weight_mask == 0] == 0).all()) for t, (mod, a) in zip(eff, model._state_slots()) if a == "weight" and hasattr(mod, "weight_mask"))
+    # (3) prune.remove makes the masks permanent: same function, reference state_dict layout again
+    for mod, _ in convs:
+        prune.remove(mod, "weight")
+    assert sorted(model.state_dict().keys()) == sorted(sd.keys())
+    with torch.no_grad():
+        final = model(xc).float()
+    assert torch.equal(final, tuned)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # per-kernel backward checks against torch autograd on identical (bf16-rounded) inputs
 # ------------------------------------------------------------------------------------------------------------
