@@ -248,14 +248,15 @@ class CardSegmentationModel(nn.Module):
                                "CPU fallback. Move the model and the batch to 'cuda'.")
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
         if self.training:
-            params = list(self.parameters())
-            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-                if not all(p.requires_grad for p in params):
-                    raise RuntimeError("the CUDA training step computes all parameter gradients; freezing a subset is not supported")
-                tensors = self._state_tensors()
-                self._step_tensors = tensors
-                return _TrainStep.apply(self, x, out_dtype, *[t for t in tensors if t.requires_grad])
-            return self.engine().train_forward(self._state_tensors(), x, out_dtype)[0]
+            tensors = self._state_tensors()
+            if torch.is_grad_enabled():
+                req = [t for t in tensors if t.requires_grad]  # parameters, or masked non-leaf weights under active pruning
+                if req:
+                    if len(req) != len(self._param_slots):
+                        raise RuntimeError("the CUDA training step computes all parameter gradients; freezing a subset is not supported")
+                    self._step_tensors = tensors
+                    return _TrainStep.apply(self, x, out_dtype, *req)
+            return self.engine().train_forward(tensors, x, out_dtype)[0]
         return self.engine().infer(self._state_tensors(), x, logits_dtype=out_dtype)
 
     @torch.no_grad()
