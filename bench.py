@@ -340,9 +340,27 @@ def run_ours(args):
         host_ms = min(host_ms)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # exposed communication: the gradient all-reduce is not overlapped with the backward pass, so its isolated time IS the
+        # exposed time; measured on the flat buffer of the last step, max over ranks
+        allreduce_ms = None
+        if world > 1:
+            flat = tmodel.last_flat_grad
+            for _ in range(3):
+                average_gradients(flat)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a0.record()
+            for _ in range(10):
+                average_gradients(flat)
+            a1.record()
+            torch.cuda.synchronize()
+            at = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
+            dist.all_reduce(at, op=dist.ReduceOp.MAX)
+            allreduce_ms = at.item()
         res = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "workload": label,
                "value": world * TB * tsteps / (tt.item() * 1e-3), "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps,
                "batch_per_gpu": TB, "global_batch": TB * world, "loss": float(last.item()),
+               "allreduce_ms": allreduce_ms,  # isolated (= exposed) all-reduce + averaging of the flat fp32 gradient; null at N=1
                "host_enqueue_ms_per_step": host_ms,  # >= ms_per_step would mean the step is host-launch bound on this box
                "gpu_launches_per_step": launches_per_step,
                "parallelism": f"data parallel x{world}, per-replica BatchNorm, one NCCL all-reduce of the 16.8 MB flat fp32 gradient"}
@@ -355,6 +373,26 @@ def run_ours(args):
         train = train_leg(args.train_batch, "configs[2]: train/train.py step, batch 32 per GPU")
         if 256 % world == 0:
             train_dp = train_leg(256 // world, f"configs[3]: data-parallel step, global batch 256 = {256 // world} per GPU")
+
+    # ---------------- configs[0] on the GPU: batch-1 latency (the reference's own CPU-runnable case, timed on the CPU below) ----
+    latency_b1 = None
+    if rank == 0 and not args.no_graph:
+        x1 = x[:1].contiguous()
+        g1 = GraphedInference(model, x1, logits_dtype=torch.float32)
+        for _ in range(10):
+            g1.replay()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        l0.record()
+        for _ in range(200):
+            g1.replay()
+        l1.record()
+        torch.cuda.synchronize()
+        ms1 = l0.elapsed_time(l1) / 200
+        latency_b1 = {"ms_per_image": ms1, "value": 1e3 / ms1, "unit": UNIT, "launches": g1.launches_per_replay,
+                      "sample": "200 CUDA-graph replays of a B=1 forward (fp32 logits out), device-resident input; the kernels are "
+                                "tuned for B=256: this is launch / latency bound"}
+        del g1
 
     # ---------------- pose head forward (configs[4], second half): tensor-bound 256-channel convs at 160x120 --------
     pose = None
@@ -416,7 +454,7 @@ def run_ours(args):
                                     "eager_predict": {"value": e2e_u8_eager, "unit": UNIT},
                                     "note": "same calls fed raw uint8 HWC frames; (v/255-mean)/std fused into the stem kernel"}},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "train": train, "train_global256": train_dp, "pose_head": pose,
+            "roofline": roofline, "cpu_baseline": cpu, "latency_batch1": latency_b1, "train": train, "train_global256": train_dp, "pose_head": pose,
         }
         emit(line)
     if world > 1:
