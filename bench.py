@@ -201,7 +201,7 @@ def run_ours(args):
             read_back = [torch.cuda.Event(), torch.cuda.Event()]
             if graphed:
                 example = torch.zeros(host_batch.shape, dtype=host_batch.dtype, device=dev)
-                graphs = [GraphedInference(model, example, logits_dtype=None, want_mask=True) for _ in range(2)]
+                graphs = [GraphedInference(model, example, logits_dtype=None, want_mask=True, splits=args.splits) for _ in range(2)]
                 xbuf = [gi.x for gi in graphs]
             else:
                 xbuf = [torch.empty(host_batch.shape, dtype=host_batch.dtype, device=dev) for _ in range(2)]
@@ -487,7 +487,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--splits", type=int, default=1, help="concurrent sub-batches (streams) inside the CUDA graph")
+    ap.add_argument("--splits", type=int, default=2,
+                    help="concurrent sub-batches inside the CUDA graph (images are independent units; measured at B=256: 1 -> 3.74 ms, 2 -> 3.60 ms, 4 -> 3.95 ms)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--no-pose", action="store_true", help="skip the pose-head leg")

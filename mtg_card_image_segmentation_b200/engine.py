@@ -69,7 +69,8 @@ class SegEngine:
         return cur
 
     # -- inference ---------------------------------------------------------------------------
-    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None, ws_slot=0, out=None):
+    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None, ws_slot=0, out=None, mask_out=None):
+        """`out` / `mask_out`: caller-owned logits / uint8 mask buffers (e.g. batch slices of a larger tensor)."""
         u8 = x.dtype == torch.uint8
         if u8:  # raw HWC pixels: normalisation is fused into the stem kernel
             if x.dim() != 4 or x.shape[3] != 3:
@@ -92,7 +93,11 @@ class SegEngine:
             logits = None
             if logits_dtype is not None:
                 logits = out if out is not None else torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
-            mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+            mask = None
+            if want_mask:
+                mask = mask_out if mask_out is not None else torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+                if mask.dtype != torch.uint8 or tuple(mask.shape) != (B, H, W) or not mask.is_contiguous() or mask.device != dev:
+                    raise RuntimeError("mask_out must be a contiguous uint8 (B,H,W) tensor on the input's device")
             counts = None
             if targets is not None:
                 if targets.dtype != torch.int64 or tuple(targets.shape) != (B, H, W) or targets.device != dev:
@@ -194,6 +199,8 @@ class GraphedInference:
         hw = tuple(self.x.shape[1:3]) if self.x.dtype == torch.uint8 else tuple(self.x.shape[2:])
         logits = None if logits_dtype is None else torch.empty((B, eng.num_classes) + hw, dtype=logits_dtype, device=self.x.device)
 
+        mask = torch.empty((B,) + hw, dtype=torch.uint8, device=self.x.device) if want_mask and splits > 1 else None
+
         def run_all():
             if splits == 1:
                 return eng.infer(tensors, self.x, logits_dtype=logits_dtype, want_mask=want_mask, out=logits)
@@ -202,14 +209,13 @@ class GraphedInference:
                 st = self._streams[i]
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
-                    eng.infer(tensors, self.x[bounds[i]:bounds[i + 1]], logits_dtype=logits_dtype, ws_slot=i,
-                              out=logits[bounds[i]:bounds[i + 1]])
+                    sl = slice(bounds[i], bounds[i + 1])
+                    eng.infer(tensors, self.x[sl], logits_dtype=logits_dtype, want_mask=want_mask, ws_slot=i,
+                              out=None if logits is None else logits[sl], mask_out=None if mask is None else mask[sl])
             for st in self._streams:
                 main.wait_stream(st)
-            return logits
+            return {"logits": logits, "mask": mask, "counts": None} if want_mask else logits
 
-        if splits > 1 and (want_mask or logits is None):
-            raise RuntimeError("GraphedInference: splits > 1 supports logits output only")
         self._streams = [torch.cuda.Stream() for _ in range(splits)] if splits > 1 else []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

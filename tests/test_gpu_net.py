@@ -253,3 +253,8 @@ def test_graphed_inference_mask_only_matches_predict():
             other = torch.flip(batch, dims=[0])
             assert torch.equal(gi.run(other)["mask"], torch.flip(want, dims=[0]))
             assert torch.equal(gi.run(batch)["mask"], want)
+            # two concurrent sub-batches inside the graph (what bench.py replays): images are independent units, same bits
+            g2 = GraphedInference(model, torch.zeros_like(batch), logits_dtype=torch.float32, want_mask=True, splits=2)
+            out2 = g2.run(batch)
+            assert torch.equal(out2["mask"], want)
+            assert torch.equal(out2["logits"], model.engine().infer(model._state_tensors(), batch, torch.float32))
