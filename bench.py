@@ -357,12 +357,32 @@ def run_ours(args):
             at = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
             dist.all_reduce(at, op=dist.ReduceOp.MAX)
             allreduce_ms = at.item()
+        # the same step captured once and replayed as one CUDA graph (engine.GraphedTrainStep; single-GPU only: the
+        # data-parallel step keeps the eager all-reduce).  Same work per step: re-pack, forward, loss, backward, AdamW.
+        graphed = None
+        if world == 1:
+            from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+            gs = GraphedTrainStep(tmodel, crit, opt, xt, mt)
+            for _ in range(3):
+                gs.step(xt, mt)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            g0.record()
+            for _ in range(tsteps):
+                gl = gs.step(xt, mt)  # includes the device-to-device copy of the batch into the captured buffers
+            g1.record()
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1) / tsteps
+            graphed = {"api": "engine.GraphedTrainStep(model, criterion, optimizer, x, y).step(x, y)", "ms_per_step": gms,
+                       "value": TB / (gms * 1e-3), "unit": UNIT, "loss": float(gl.item()), "launches_per_replay": gs.launches_per_replay}
+            del gs
         res = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "workload": label,
                "value": world * TB * tsteps / (tt.item() * 1e-3), "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps,
                "batch_per_gpu": TB, "global_batch": TB * world, "loss": float(last.item()),
                "allreduce_ms": allreduce_ms,  # isolated (= exposed) all-reduce + averaging of the flat fp32 gradient; null at N=1
                "host_enqueue_ms_per_step": host_ms,  # >= ms_per_step would mean the step is host-launch bound on this box
                "gpu_launches_per_step": launches_per_step,
+               "graphed": graphed,  # null under torchrun
                "parallelism": f"data parallel x{world}, per-replica BatchNorm, one NCCL all-reduce of the 16.8 MB flat fp32 gradient"}
         del tmodel, opt
         torch.cuda.empty_cache()

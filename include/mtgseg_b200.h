@@ -99,6 +99,11 @@ int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* pac
                     void* stream);
 int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int step, const float* inv_scale, const float* found_inf, void* stream);
+/* CUDA-graph form of the same step (train/train.py:105 inside a captured training step): the scalars of a captured launch
+ * are frozen, so they are read from `hyper`, an 8-float DEVICE block {lr, beta1, beta2, eps, weight_decay, 1-beta1^step,
+ * sqrt(1-beta2^step), 0} that mtgseg_adamw_hyper (one 1-thread launch, outside the graph) rewrites before every replay. */
+int mtgseg_adamw_hyper(float* hyper, float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+int mtgseg_adamw_step_dev(const void* chunk_table, int n_chunks, const float* hyper, void* stream);
 
 /* Same, fed with the RAW image batch: uint8 [batch,in_h,in_w,3] (HWC, what cv2 / the camera delivers, train/dataset.py:66-70);
  * A.Normalize's (v/255 - mean)/std with the ImageNet constants (train/dataset.py:182-185) is fused into the stem's load, so the

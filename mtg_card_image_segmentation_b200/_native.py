@@ -46,6 +46,8 @@ SIGNATURES = {
     "mtgseg_forward_train": (_i, [_ND, _vp, _vp, C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
     "mtgseg_backward": (_i, [_ND, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
     "mtgseg_adamw_step": (_i, [_vp, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _vp, _vp]),
+    "mtgseg_adamw_hyper": (_i, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp]),
+    "mtgseg_adamw_step_dev": (_i, [_vp, _i, _vp, _vp]),
     "mtgseg_bn_scratch_floats": (_sz, [_i, _i, _i]),
     "mtgseg_bn_train_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
                                  _i, _i, _i, _i, _vp]),

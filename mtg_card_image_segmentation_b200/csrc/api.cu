@@ -124,6 +124,14 @@ int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float bet
   return launch_adamw(chunk_table, n_chunks, lr, beta1, beta2, eps, weight_decay, step, inv_scale, found_inf, S(stream));
 }
 
+int mtgseg_adamw_hyper(float* hyper, float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+  return launch_adamw_hyper(hyper, lr, beta1, beta2, eps, weight_decay, step, S(stream));
+}
+
+int mtgseg_adamw_step_dev(const void* chunk_table, int n_chunks, const float* hyper, void* stream) {
+  return launch_adamw_dev(chunk_table, n_chunks, hyper, S(stream));
+}
+
 // ---- per-operator training entry points (unit tests) ---------------------------------------------------
 size_t mtgseg_bn_scratch_floats(int B, int HW, int C) { return bn_partial_floats(B, HW, C); }
 

@@ -180,6 +180,9 @@ int launch_fill_f32(float* p, float v, size_t n, cudaStream_t st);
 // chunk_table: device array of {float* p; const float* g; float* m; float* v; int n;} (one CTA per entry)
 int launch_adamw(const void* chunk_table, int n_chunks, float lr, float b1, float b2, float eps, float wd, int step,
                  const float* inv_scale, const float* found_inf, cudaStream_t st);
+// captured (CUDA-graph) steps: the scalars live in an 8-float device block written by launch_adamw_hyper before every replay
+int launch_adamw_hyper(float* hyper, float lr, float b1, float b2, float eps, float wd, int step, cudaStream_t st);
+int launch_adamw_dev(const void* chunk_table, int n_chunks, const float* hyper, cudaStream_t st);
 // [N][K] fp32 -> [K][N] bf16 ; [O][I][3][3] fp32 -> [I][9 (flipped)][O] bf16   (dgrad operands)
 int launch_pack_transpose_bf16(const float* in, bf16* out, int N, int K, cudaStream_t st);
 int launch_pack_dgrad3x3(const float* in, bf16* out, int O, int I, cudaStream_t st);

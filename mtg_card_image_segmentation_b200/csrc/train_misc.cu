@@ -315,8 +315,11 @@ __global__ void fill_f32_kernel(float* __restrict__ p, float v, size_t n) {
 struct AdamChunk { float* p; const float* g; float* m; float* v; int n; int pad; };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale,
-                                                    const float* __restrict__ found_inf) {
+                                                    const float* __restrict__ found_inf, const float* __restrict__ hyper) {
   if (found_inf && *found_inf != 0.f) return;
+  if (hyper) {  // captured step: the scalars of THIS replay live in device memory (adamw_hyper_kernel)
+    lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; bc1 = hyper[5]; bc2_sqrt = hyper[6];
+  }
   const AdamChunk c = chunks[blockIdx.x];
   const float gs = inv_scale ? *inv_scale : 1.f;
   const float step_size = lr / bc1, decay = 1.f - lr * wd;
@@ -337,6 +340,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamChunk* __restrict_
     reinterpret_cast<float4*>(c.p)[i] = p4; reinterpret_cast<float4*>(c.m)[i] = m4; reinterpret_cast<float4*>(c.v)[i] = v4;
   }
   for (int i = n4 * 4 + threadIdx.x; i < c.n; i += blockDim.x) upd(c.p[i], c.g[i], c.m[i], c.v[i]);
+}
+
+__global__ void adamw_hyper_kernel(float* hyper, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  hyper[0] = lr; hyper[1] = b1; hyper[2] = b2; hyper[3] = eps; hyper[4] = wd; hyper[5] = bc1; hyper[6] = bc2_sqrt; hyper[7] = 0.f;
 }
 
 }  // namespace
@@ -412,7 +419,23 @@ int launch_adamw(const void* chunk_table, int n_chunks, float lr, float b1, floa
   MTG_REQUIRE(chunk_table && n_chunks > 0 && step > 0, MTG_ERR_ARG, "adamw: bad arguments");
   const float bc1 = 1.f - powf(b1, static_cast<float>(step));
   const float bc2s = sqrtf(1.f - powf(b2, static_cast<float>(step)));
-  adamw_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const AdamChunk*>(chunk_table), lr, b1, b2, eps, wd, bc1, bc2s, inv_scale, found_inf);
+  adamw_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const AdamChunk*>(chunk_table), lr, b1, b2, eps, wd, bc1, bc2s, inv_scale, found_inf,
+                                         nullptr);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_adamw_hyper(float* hyper, float lr, float b1, float b2, float eps, float wd, int step, cudaStream_t st) {
+  MTG_REQUIRE(hyper && step > 0, MTG_ERR_ARG, "adamw_hyper: bad arguments");
+  adamw_hyper_kernel<<<1, 1, 0, st>>>(hyper, lr, b1, b2, eps, wd, 1.f - powf(b1, static_cast<float>(step)),
+                                      sqrtf(1.f - powf(b2, static_cast<float>(step))));
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+
+int launch_adamw_dev(const void* chunk_table, int n_chunks, const float* hyper, cudaStream_t st) {
+  MTG_REQUIRE(chunk_table && n_chunks > 0 && hyper, MTG_ERR_ARG, "adamw_dev: bad arguments");
+  adamw_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const AdamChunk*>(chunk_table), 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f, nullptr, nullptr, hyper);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

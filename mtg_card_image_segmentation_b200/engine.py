@@ -21,6 +21,7 @@ class SegEngine:
         self._ws = None
         self._ws_extra = {}
         self._train_ws = None
+        self._static_flat = None
         self._stats_dirty = False
         self._desc_cache = {}
 
@@ -149,7 +150,11 @@ class SegEngine:
         dlogits = dlogits.contiguous()
         with torch.cuda.device(dev):
             sizes = [t.numel() if p else 0 for t, p in zip(tensors, is_param)]
-            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            flat = self._static_flat  # GraphedTrainStep: one fixed gradient buffer, so that the captured addresses never change
+            if flat is not None and flat.numel() == sum(sizes) and flat.device == dev:
+                flat.zero_()
+            else:
+                flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
             views, off = [], 0
             for t, n in zip(tensors, sizes):
                 views.append(flat[off:off + n].view_as(t) if n else None)
@@ -236,3 +241,116 @@ class GraphedInference:
     def run(self, x):
         self.x.copy_(x, non_blocking=True)
         return self.replay()
+
+
+class GraphedTrainStep:
+    """The body of train/train.py:88-110's loop -- ``optimizer.zero_grad(); loss = criterion(model(x), y); loss.backward();
+    optimizer.step()`` -- captured once and replayed as ONE CUDA graph (weight re-pack, ~480 kernels on two streams, AdamW).
+
+    At batch 32 the step is a chain of short dependent launches; the graph removes the per-launch gaps.  ``step(x, y)`` copies the
+    batch into the captured buffers, refreshes the optimizer's device hyperparameter block (so LR schedulers keep working) and
+    replays; it returns the captured loss scalar (a device tensor: read it when you need it).  Building the object leaves model,
+    BatchNorm statistics and optimizer state exactly as they were (the warm-up steps run on a snapshot that is restored).
+    Construct it under the same ``torch.autocast`` context as the loop.  Not supported: GradScaler (bf16 needs none), several
+    parameter groups, criteria other than this package's CombinedLoss / DiceLoss (the step calls the engine and the fused loss
+    kernel directly, without autograd), active pruning masks, data-parallel capture (use the eager step with ``parallel.average_gradients``)."""
+
+    def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3):
+        from .optim import FusedAdamW
+        if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
+            raise RuntimeError("GraphedTrainStep needs a FusedAdamW optimizer with one parameter group")
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            raise RuntimeError("GraphedTrainStep captures a single-GPU step; data-parallel training uses the eager step")
+        if not model.training:
+            raise RuntimeError("GraphedTrainStep: call model.train() first")
+        if not example_x.is_cuda:
+            raise RuntimeError("GraphedTrainStep runs on CUDA (sm_100a) only")
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        dev = example_x.device
+        eng = model.engine()
+        tensors = model._state_tensors()
+        if model._has_masks:
+            raise RuntimeError("GraphedTrainStep does not support active pruning masks (the masked weights are rebuilt on the host)")
+        self._params = list(optimizer.param_groups[0]["params"])
+        self._is_param = [bool(t.requires_grad) for t in tensors]
+        if sum(self._is_param) != len(self._params) or {id(p) for p in self._params} != {id(t) for t in tensors if t.requires_grad}:
+            raise RuntimeError("GraphedTrainStep: the optimizer must hold exactly the model's parameters, all trainable")
+        from .utils import loss_weights
+        self._loss_weights = loss_weights(criterion)
+        self._logits_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+        self.x = example_x.detach().float().contiguous().clone()
+        self.y = example_y.detach().contiguous().clone()
+        if self.x.dim() != 4 or self.x.shape[1] != 3 or self.y.dtype != torch.int64 or self.y.device != dev or \
+                tuple(self.y.shape) != (self.x.shape[0],) + tuple(self.x.shape[2:]):
+            raise RuntimeError("GraphedTrainStep: expected a (B,3,H,W) batch and int64 (B,H,W) targets on the same CUDA device")
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            snap = [t.detach().clone() for t in tensors]
+            snap_opt = []
+            for p in self._params:
+                st = optimizer.state.get(p)
+                snap_opt.append((st["step"].clone(), st["exp_avg"].clone(), st["exp_avg_sq"].clone()) if st else None)
+        eng._static_flat = torch.empty(sum(p.numel() for p in self._params), dtype=torch.float32, device=dev)
+        try:
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._forward_backward()
+                optimizer.step()  # eager: creates the optimizer state and the chunk table for the static gradient buffer
+                for _ in range(max(1, warmup - 1)):
+                    self._one_step()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            eng._stats_dirty = True  # the capture must contain the weight re-pack
+            before = eng.lib.mtgseg_launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._captured_body()
+            self.launches_per_replay = int(eng.lib.mtgseg_launch_count() - before)
+        finally:
+            self._keep = (eng._static_flat, eng._train_ws, eng._packed, getattr(self, "_table", None))  # addresses the graph holds
+            eng._static_flat = None
+        with torch.no_grad():  # undo the warm-up steps
+            for t, s in zip(tensors, snap):
+                t.copy_(s)
+            for p, s in zip(self._params, snap_opt):
+                st = optimizer.state[p]
+                if s is None:
+                    st["step"].zero_(); st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+                else:
+                    st["step"].copy_(s[0]); st["exp_avg"].copy_(s[1]); st["exp_avg_sq"].copy_(s[2])
+        eng._stats_dirty = True
+
+    def _forward_backward(self):
+        # straight through the engine, no autograd: the autograd engine would run AccumulateGrad nodes on whatever stream they were
+        # created on (e.g. the default stream of earlier eager steps whose loss tensor is still alive), which a capture forbids
+        from .utils import fused_loss
+        model, eng = self.model, self.model.engine()
+        tensors = model._state_tensors()
+        logits, x32 = eng.train_forward(tensors, self.x, self._logits_dtype)
+        loss3, dlogits = fused_loss(logits, self.y, *self._loss_weights, True)
+        flat, views = eng.train_backward(tensors, self._is_param, x32, dlogits)
+        model.last_flat_grad = flat
+        for t, v in zip(tensors, views):
+            if v is not None:
+                t.grad = v
+        return loss3[0]
+
+    def _captured_body(self):
+        loss = self._forward_backward()
+        self._table = self.optimizer.step_captured(self.hyper)
+        return loss
+
+    def _one_step(self):
+        self.optimizer.advance(self.hyper)
+        return self._captured_body()
+
+    def step(self, x, y):
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.optimizer.advance(self.hyper)
+        self.graph.replay()
+        torch.autograd.graph.increment_version(self._params)  # parameters changed behind autograd's back
+        self.model.engine()._stats_dirty = True               # so did the BatchNorm running statistics
+        return self.loss

@@ -33,23 +33,38 @@ def _check_pair(predictions, targets, what):
         raise RuntimeError(f"{what}: unsupported logits dtype {predictions.dtype}")
 
 
+def fused_loss(predictions, targets, dice_weight, ce_weight, smooth, need_grad):
+    """One kernel pass: loss3 = (total, dice, ce) and, when asked, d(total)/d(logits).  Also what engine.GraphedTrainStep calls
+    directly (no autograd inside a captured step)."""
+    lib = N.load()
+    p = predictions.contiguous()
+    t = targets.contiguous()
+    B, C, H, W = p.shape
+    dlogits = torch.empty_like(p) if need_grad else None
+    scratch = torch.empty(lib.mtgseg_loss_scratch_bytes() // 4, dtype=torch.float32, device=p.device)
+    loss3 = torch.empty(3, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        N.check(lib.mtgseg_loss_fwd_bwd(p.data_ptr(), _DT[p.dtype], t.data_ptr(), N.ptr(dlogits), scratch.data_ptr(),
+                                        loss3.data_ptr(), B, H * W, C, dice_weight, ce_weight, smooth, N.stream_ptr()),
+                "mtgseg_loss_fwd_bwd")
+    return loss3, dlogits
+
+
+def loss_weights(criterion):
+    """(dice_weight, ce_weight, smooth) of a DiceLoss / CombinedLoss module."""
+    if isinstance(criterion, CombinedLoss):
+        return float(criterion.dice_weight), float(criterion.ce_weight), float(criterion.dice_loss.smooth)
+    if isinstance(criterion, DiceLoss):
+        return 1.0, 0.0, float(criterion.smooth)
+    raise RuntimeError("expected this package's CombinedLoss or DiceLoss (train/utils.py:15-92)")
+
+
 class _FusedLoss(torch.autograd.Function):
     """loss3 = (total, dice, ce); the gradient w.r.t. the logits is produced by the same kernel pass."""
 
     @staticmethod
     def forward(ctx, predictions, targets, dice_weight, ce_weight, smooth):
-        lib = N.load()
-        p = predictions.contiguous()
-        t = targets.contiguous()
-        B, C, H, W = p.shape
-        need_grad = predictions.requires_grad
-        dlogits = torch.empty_like(p) if need_grad else None
-        scratch = torch.empty(lib.mtgseg_loss_scratch_bytes() // 4, dtype=torch.float32, device=p.device)
-        loss3 = torch.empty(3, dtype=torch.float32, device=p.device)
-        with torch.cuda.device(p.device):
-            N.check(lib.mtgseg_loss_fwd_bwd(p.data_ptr(), _DT[p.dtype], t.data_ptr(), N.ptr(dlogits), scratch.data_ptr(),
-                                            loss3.data_ptr(), B, H * W, C, dice_weight, ce_weight, smooth, N.stream_ptr()),
-                    "mtgseg_loss_fwd_bwd")
+        loss3, dlogits = fused_loss(predictions, targets, dice_weight, ce_weight, smooth, predictions.requires_grad)
         ctx.dlogits = dlogits
         ctx.mark_non_differentiable(loss3)
         return loss3[0], loss3

@@ -171,6 +171,79 @@ def test_grad_scaler_loop_matches_plain_step():
     assert moved > 5e-4 and worst <= 0.05 * moved  # measured 4.5e-6 vs 1e-3
 
 
+def test_graphed_train_step_matches_eager_loop():
+    """engine.GraphedTrainStep = train/train.py:88-110's loop body replayed as one CUDA graph.  Building it must leave the model,
+    the BatchNorm statistics and the optimizer untouched; the replays must follow the eager loop on the same batches (same loss at
+    step 1 bit for bit: the forward is deterministic; later steps up to the atomics' summation order in the weight gradients),
+    honour learning-rate changes made between steps (the captured scalars are frozen, the device block is not), advance
+    num_batches_tracked / the optimizer step counts, and leave the model ready for eval."""
+    from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+    sd = O.make_weights(47)
+    data = [O.synthetic_cards(4, seed=s, height=64, width=48) for s in (21, 22, 23)]
+    data = [(a.cuda(), b.cuda()) for a, b in data]
+    lrs = [3e-4, 1e-3, 5e-4]
+
+    def final_state(model):
+        return {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+
+    def eager():
+        model = _train_model(sd)
+        opt, crit, losses = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4), M.CombinedLoss(), []
+        for (xb, mb), lr in zip(data, lrs):
+            opt.param_groups[0]["lr"] = lr
+            opt.zero_grad(set_to_none=True)
+            loss = crit(model(xb), mb)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        return losses, final_state(model), model
+
+    def graphed():
+        model = _train_model(sd)
+        opt, crit, losses = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4), M.CombinedLoss(), []
+        g = GraphedTrainStep(model, crit, opt, data[2][0], data[2][1])  # example batch: any data of the right shape
+        untouched = final_state(model)
+        for k, v in sd.items():
+            assert torch.equal(untouched[k], v.float()), f"building the graph changed {k}"
+        assert all(float(st["step"]) == 0 and not st["exp_avg"].any() for st in opt.state.values())
+        first = None
+        for (xb, mb), lr in zip(data, lrs):
+            opt.param_groups[0]["lr"] = lr
+            losses.append(float(g.step(xb, mb)))
+            if first is None:
+                first = final_state(model)
+        assert all(float(st["step"]) == 3 for st in opt.state.values())
+        return losses, final_state(model), model, first, g.launches_per_replay
+
+    le, se_, me = eager()
+    lg, sg, mg, first, launches = graphed()
+    print(f"losses eager {le} graphed {lg}; {launches} launches per replay")
+    assert launches > 300
+    assert lg[0] == le[0]
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg))
+    # AdamW's first step moves every weight by ~lr*sign(g): the step taken must be the 3e-4 set after construction, not the 1e-3 the
+    # graph was captured under
+    pk = [k for k, _ in me.named_parameters()]
+    step1 = max(float((first[k] - sd[k].float()).abs().max()) for k in pk)
+    assert 2.4e-4 <= step1 <= 3.6e-4, step1
+    moved = max(float((se_[k] - sd[k].float()).abs().max()) for k in pk)
+    worst = max(float((se_[k] - sg[k]).abs().max()) for k in pk)
+    n = sum(se_[k].numel() for k in pk)
+    mean_moved = sum(float((se_[k] - sd[k].float()).abs().sum()) for k in pk) / n
+    mean_diff = sum(float((se_[k] - sg[k]).abs().sum()) for k in pk) / n
+    print(f"after 3 steps: graphed vs eager parameter difference mean {mean_diff:.3e} max {worst:.3e}; the steps moved parameters by "
+          f"mean {mean_moved:.3e} max {moved:.3e}")
+    # AdamW's early steps are sign-like: a weight whose gradient is at noise level (atomics' summation order, amplified by the bf16
+    # activations of a random-init net) may move by up to lr in either direction, so the bound is on the mean, not on the worst
+    assert mean_diff <= 0.2 * mean_moved and worst <= moved
+    assert int(sg["model.backbone.0.1.num_batches_tracked"]) == int(se_["model.backbone.0.1.num_batches_tracked"]) == 3
+    rs = [k for k in sd if k.endswith("running_var")]
+    assert max(float((se_[k] - sg[k]).abs().max() / se_[k].abs().max()) for k in rs) <= 2e-2
+    with torch.no_grad():
+        ze, zg = me.eval()(data[0][0]).float(), mg.eval()(data[0][0]).float()
+    assert float((ze - zg).abs().max()) <= 0.1 * float(ze.abs().max())
+
+
 def test_pruning_flow_masks_active_then_removed():
     """train/prune.py:52-113,144-175 on the drop-in model: global magnitude pruning of the conv children, evaluation and fine-tuning
     with the masks ACTIVE (weight = weight_orig * weight_mask, maintained by torch's pruning hook), then prune.remove.  No call
