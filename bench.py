@@ -112,6 +112,33 @@ def cpu_reference_forward(batch, steps, warmup, threads):
     return batch * steps / dt, dt / steps * 1e3
 
 
+def cpu_reference_train_step(batch, steps, warmup, threads):
+    """The reference's CPU training step (train/train.py:89-111 without autocast): fp32 train-mode forward of the oracle port,
+    Dice/CE loss, autograd backward, torch.optim.AdamW(lr 1e-3, wd 1e-4) on the 178 tensors. Returns images/s and ms/step."""
+    from oracle import lraspp_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.make_weights(0)
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=1e-3, weight_decay=1e-4)
+    x, m = O.synthetic_cards(min(batch, 8), seed=1234, height=H, width=W)
+    reps = (batch + x.shape[0] - 1) // x.shape[0]
+    x, m = x.repeat(reps, 1, 1, 1)[:batch].contiguous(), m.repeat(reps, 1, 1)[:batch].contiguous()
+    dt = 0.0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        upd = {}
+        loss = O.combined_loss(O.forward(sd, x, training=True, bn_updates=upd), m)
+        loss.backward()
+        opt.step()
+        with torch.no_grad():  # running statistics, as nn.BatchNorm2d updates them in place
+            for k, v in upd.items():
+                sd[k].copy_(v)
+        if i >= warmup:
+            dt += time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -453,6 +480,10 @@ def run_ours(args):
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "3 steps x B=32 fp32 eval forward at 320x240, oracle port (torch oneDNN), 1 warm-up",
                "config0_batch1": {"value": ips1, "unit": UNIT, "ms_per_image": ms1, "sample": "20 x B=1 fp32 eval forward, 5 warm-up"}}
+        if not args.no_train:
+            tips, tms = cpu_reference_train_step(32, 2, 1, threads)  # configs[2] on the host cores, beside the `train` leg
+            cpu["train_step_batch32"] = {"value": tips, "unit": UNIT, "ms_per_step": tms,
+                                         "sample": "2 steps x B=32 fp32 train step (fwd + Dice/CE + autograd bwd + torch AdamW), 1 warm-up"}
 
     if rank == 0:
         line = {
