@@ -244,6 +244,55 @@ def test_graphed_train_step_matches_eager_loop():
     assert float((ze - zg).abs().max()) <= 0.1 * float(ze.abs().max())
 
 
+def test_graphed_train_step_under_autocast_and_rebuild():
+    """train/train.py:96-99 runs the forward under autocast: a GraphedTrainStep built inside the same context produces reduced-
+    precision logits like the eager loop (same first loss, bit for bit), a second graph built on the same model / optimizer after
+    some steps continues from the current state, and an eager step afterwards still works (the graph does not leave the optimizer
+    or the engine in a captured-only mode)."""
+    from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+    sd = O.make_weights(53)
+    x, m = O.synthetic_cards(4, seed=31, height=64, width=48)
+    xc, mc = x.cuda(), m.cuda()
+    crit = M.CombinedLoss()
+
+    def eager_losses(n):
+        model = _train_model(sd)
+        opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        out = []
+        for _ in range(n):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = model(xc)
+                assert logits.dtype == torch.bfloat16
+                loss = crit(logits, mc)
+            loss.backward()
+            opt.step()
+            out.append(float(loss.detach()))
+        return out
+
+    ref = eager_losses(4)
+    model = _train_model(sd)
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        g1 = GraphedTrainStep(model, crit, opt, xc, mc)
+    got = [float(g1.step(xc, mc)) for _ in range(2)]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        g2 = GraphedTrainStep(model, crit, opt, xc, mc)  # rebuilt mid-training: must continue from step 2, not restart
+    assert all(float(st["step"]) == 2 for st in opt.state.values())
+    got.append(float(g2.step(xc, mc)))
+    opt.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = crit(model(xc), mc)
+    loss.backward()
+    opt.step()
+    got.append(float(loss.detach()))
+    print(f"autocast losses eager {ref} graphed/rebuilt/eager {got}")
+    assert got[0] == ref[0]
+    assert all(abs(a - b) <= 5e-3 * abs(a) for a, b in zip(ref, got))
+    assert all(float(st["step"]) == 4 for st in opt.state.values())
+    assert int(model.state_dict()["model.backbone.0.1.num_batches_tracked"]) == 4
+
+
 def test_pruning_flow_masks_active_then_removed():
     """train/prune.py:52-113,144-175 on the drop-in model: global magnitude pruning of the conv children, evaluation and fine-tuning
     with the masks ACTIVE (weight = weight_orig * weight_mask, maintained by torch's pruning hook), then prune.remove.  No call

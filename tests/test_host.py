@@ -119,3 +119,22 @@ def test_arch_table_in_sync_with_cuda_plan():
         assert (int(r[0]), int(r[1]), int(r[2]), int(r[3]), r[4] == "true", {"RELU": "RE", "HSWISH": "HS"}[r[5]],
                 int(r[6]), int(r[7])) == tuple(b)
     assert [tuple(b) for b in arch.BLOCKS] == [tuple(b) for b in O.BLOCKS]
+
+
+def test_graphed_train_step_rejects_what_it_cannot_capture():
+    """engine.GraphedTrainStep fails loudly (before touching CUDA) for setups whose step it would not reproduce: a foreign
+    optimizer (its scalar arguments would be frozen into the graph), a foreign criterion, eval mode, CPU tensors."""
+    from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+    from mtg_card_image_segmentation_b200.optim import FusedAdamW
+    model = M.create_model(2, pretrained=False).train()
+    x, y = torch.zeros(2, 3, 64, 48), torch.zeros(2, 64, 48, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="FusedAdamW"):
+        GraphedTrainStep(model, M.CombinedLoss(), torch.optim.AdamW(model.parameters()), x, y)
+    opt = FusedAdamW(model.parameters(), lr=1e-3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedTrainStep(model, M.CombinedLoss(), opt, x, y)
+    with pytest.raises(RuntimeError, match="model.train"):
+        GraphedTrainStep(model.eval(), M.CombinedLoss(), opt, x, y)
+    two = FusedAdamW([{"params": list(model.parameters())[:10]}, {"params": list(model.parameters())[10:]}], lr=1e-3)
+    with pytest.raises(RuntimeError, match="one parameter group"):
+        GraphedTrainStep(model.train(), M.CombinedLoss(), two, x, y)
