@@ -29,8 +29,11 @@ __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+constexpr int kRowsInFlight = 4;  // rows (16-byte vectors per operand) a thread loads before consuming them
+
 struct Geo {  // thread -> (channel vector, row lane) mapping shared by all kernels here
   int C, CV, CVc, PL, HW, rows_per_chunk, chunks;
+  int B, ipc;  // batch; images per CTA of the REDUCING kernels (1 for the elementwise ones)
 };
 
 struct Lane {
@@ -72,31 +75,36 @@ __device__ __forceinline__ void block_reduce_store(const Geo& g, const Lane& l, 
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-// grid (chunks, groups, B): partial[((n*chunks + chunk)*2 + {0,1})*C + c] = sum z, sum z^2 over the chunk's rows of image n
+// grid (chunks, groups, ceil(B / ipc)): partial[((zb*chunks + chunk)*2 + {0,1})*C + c] = sum z, sum z^2 over the chunk's rows of
+// the CTA's ipc images.  ipc bounds the number of partial slots: the finalize kernel has one warp per channel walking all slots,
+// and with one slot per (image, chunk) it took 38 us per layer at B = 256 (8192 slots on the 160x120 layers).
 __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ z, float* __restrict__ partial, const Geo g) {
   __shared__ float red[256 * 8];
   const Lane l = lane_of(g);
-  const int n = blockIdx.z, chunk = blockIdx.x;
+  const int chunk = blockIdx.x;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   if (l.active) {
     const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
-    const bf16* base = z + static_cast<size_t>(n) * g.HW * g.C + l.c0;
-    for (int r = r0 + l.pl; r < r1; r += g.PL) {
-      float f[8];
-      unpack8(ldg16(base + static_cast<size_t>(r) * g.C), f);
+    const int n0 = blockIdx.z * g.ipc, n1 = min(g.B, n0 + g.ipc);
+    for (int n = n0; n < n1; ++n) {
+      const bf16* base = z + static_cast<size_t>(n) * g.HW * g.C + l.c0;
+      for (int r = r0 + l.pl; r < r1; r += g.PL) {
+        float f[8];
+        unpack8(ldg16(base + static_cast<size_t>(r) * g.C), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
+        for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
+      }
     }
   }
-  const size_t slot = (static_cast<size_t>(n) * g.chunks + chunk) * 2;
+  const size_t slot = (static_cast<size_t>(blockIdx.z) * g.chunks + chunk) * 2;
   float* const dst[2] = {partial + slot * g.C, partial + (slot + 1) * g.C};
   block_reduce_store<2>(g, l, acc, red, dst, 0);
 }
 
 struct BnFinP {
-  const float* partial; int slots;  // slots = B*chunks ; layout [slot][2][C]
+  const float* partial; int slots;  // slots = ceil(B/ipc)*chunks ; layout [slot][2][C]
   double count;                     // B*HW
   const float* gamma; const float* beta; float eps, momentum;
   float* running_mean; float* running_var; long long* num_batches_tracked;
@@ -157,25 +165,40 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const G
     load8f(p.shift + l.c0, sh);
     const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
     const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
-    for (int r = r0 + l.pl; r < r1; r += g.PL) {
-      const size_t off = img + static_cast<size_t>(r) * g.C;
-      float f[8];
-      unpack8(ldg16(p.z + off), f);
+    // kRowsInFlight independent 16-byte loads per thread before the first use: the loop is latency bound otherwise (the store
+    // in the body keeps the compiler from hoisting the next row's load)
+    for (int r = r0 + l.pl; r < r1; r += kRowsInFlight * g.PL) {
+      uint4 zq[kRowsInFlight], rq[kRowsInFlight];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], sc[j], sh[j]), p.act);
-      if (p.residual) {
-        float rf[8];
-        unpack8(ldg16(p.residual + off), rf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += rf[j];
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        const int rr = r + u * g.PL;
+        const size_t off = img + static_cast<size_t>(rr < r1 ? rr : r) * g.C;
+        zq[u] = ldg16(p.z + off);
+        if (p.residual) rq[u] = ldg16(p.residual + off);
       }
-      const uint4 q = pack8(f);
-      *reinterpret_cast<uint4*>(p.y + off) = q;
-      if (p.gap) {
-        float rf[8];
-        unpack8(q, rf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gsum[0][j] += rf[j];
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        const int rr = r + u * g.PL;
+        if (rr >= r1) break;
+        const size_t off = img + static_cast<size_t>(rr) * g.C;
+        float f[8];
+        unpack8(zq[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], sc[j], sh[j]), p.act);
+        if (p.residual) {
+          float rf[8];
+          unpack8(rq[u], rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += rf[j];
+        }
+        const uint4 q = pack8(f);
+        *reinterpret_cast<uint4*>(p.y + off) = q;
+        if (p.gap) {
+          float rf[8];
+          unpack8(q, rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gsum[0][j] += rf[j];
+        }
       }
     }
   }
@@ -199,12 +222,12 @@ struct BnBwdP {
   bf16* dz;                                 // (apply)
 };
 
-__device__ __forceinline__ void bwd_load(const BnBwdP& p, const Geo& g, const Lane& l, int n, size_t off, const float (&sc)[8],
-                                         const float (&sh)[8], const float (&mu)[8], const float (&rs)[8], const float (&ses)[8],
-                                         const float (&sed)[8], float (&dyh)[8], float (&xh)[8]) {
+__device__ __forceinline__ void bwd_terms(const BnBwdP& p, const uint4& zq, const uint4& dq, const float (&sc)[8],
+                                          const float (&sh)[8], const float (&mu)[8], const float (&rs)[8], const float (&ses)[8],
+                                          const float (&sed)[8], float (&dyh)[8], float (&xh)[8]) {
   float zf[8], df[8];
-  unpack8(ldg16(p.z + off), zf);
-  unpack8(ldg16(p.dy + off), df);
+  unpack8(zq, zf);
+  unpack8(dq, df);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float d = p.se_s ? fmaf(df[j], ses[j], sed[j]) : df[j];
@@ -217,7 +240,7 @@ template <bool kApply>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g) {
   __shared__ float red[256 * 8];
   const Lane l = lane_of(g);
-  const int n = blockIdx.z, chunk = blockIdx.x;
+  const int chunk = blockIdx.x;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
@@ -226,32 +249,47 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g
     load8f(p.scale + l.c0, sc); load8f(p.shift + l.c0, sh); load8f(p.mean + l.c0, mu); load8f(p.rstd + l.c0, rs);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ses[j] = 1.f; sed[j] = 0.f; c1[j] = c2[j] = 0.f; }
-    if (p.se_s) {
-      load8f(p.se_s + static_cast<size_t>(n) * g.C + l.c0, ses);
-      load8f(p.se_dmean + static_cast<size_t>(n) * g.C + l.c0, sed);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sed[j] *= p.inv_hw;
-    }
     if (kApply) { load8f(p.c1 + l.c0, c1); load8f(p.c2 + l.c0, c2); }
     const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
-    const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
-    for (int r = r0 + l.pl; r < r1; r += g.PL) {
-      const size_t off = img + static_cast<size_t>(r) * g.C;
-      float dyh[8], xh[8];
-      bwd_load(p, g, l, n, off, sc, sh, mu, rs, ses, sed, dyh, xh);
-      if (kApply) {
-        float o[8];
+    const int n0 = blockIdx.z * g.ipc, n1 = min(g.B, n0 + g.ipc);  // the reduce pass walks ipc images (see bn_stats_kernel)
+    for (int n = n0; n < n1; ++n) {
+      if (p.se_s) {
+        load8f(p.se_s + static_cast<size_t>(n) * g.C + l.c0, ses);
+        load8f(p.se_dmean + static_cast<size_t>(n) * g.C + l.c0, sed);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dyh[j] - c1[j] - xh[j] * c2[j]);
-        *reinterpret_cast<uint4*>(p.dz + off) = pack8(o);
-      } else {
+        for (int j = 0; j < 8; ++j) sed[j] *= p.inv_hw;
+      }
+      const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
+      for (int r = r0 + l.pl; r < r1; r += kRowsInFlight * g.PL) {  // loads of kRowsInFlight rows first, see bn_apply_kernel
+        uint4 zq[kRowsInFlight], dq[kRowsInFlight];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[0][j] += dyh[j]; acc[1][j] = fmaf(dyh[j], xh[j], acc[1][j]); }
+        for (int u = 0; u < kRowsInFlight; ++u) {
+          const int rr = r + u * g.PL;
+          const size_t off = img + static_cast<size_t>(rr < r1 ? rr : r) * g.C;
+          zq[u] = ldg16(p.z + off);
+          dq[u] = ldg16(p.dy + off);
+        }
+#pragma unroll
+        for (int u = 0; u < kRowsInFlight; ++u) {
+          const int rr = r + u * g.PL;
+          if (rr >= r1) break;
+          float dyh[8], xh[8];
+          bwd_terms(p, zq[u], dq[u], sc, sh, mu, rs, ses, sed, dyh, xh);
+          if (kApply) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dyh[j] - c1[j] - xh[j] * c2[j]);
+            *reinterpret_cast<uint4*>(p.dz + img + static_cast<size_t>(rr) * g.C) = pack8(o);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[0][j] += dyh[j]; acc[1][j] = fmaf(dyh[j], xh[j], acc[1][j]); }
+          }
+        }
       }
     }
   }
   if (!kApply) {
-    const size_t slot = (static_cast<size_t>(n) * g.chunks + chunk) * 2;
+    const size_t slot = (static_cast<size_t>(blockIdx.z) * g.chunks + chunk) * 2;
     float* const dst[2] = {p.partial + slot * g.C, p.partial + (slot + 1) * g.C};
     block_reduce_store<2>(g, l, acc, red, dst, 0);
   }
@@ -276,11 +314,17 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   c2[c] = static_cast<float>(sx / count);
 }
 
-Geo make_geo(int C, int HW, int want_chunks) {
+Geo make_geo(int C, int HW, int want_chunks, int B) {
   Geo g{};
   g.C = C; g.CV = C / 8; g.CVc = group_vectors(g.CV); g.PL = 256 / g.CVc; g.HW = HW;
   g.chunks = want_chunks;
   g.rows_per_chunk = ceil_div(HW, g.chunks);
+  g.B = B; g.ipc = 1;
+  return g;
+}
+// the reducing passes: at most ~512 partial slots per channel
+Geo reducing_geo(Geo g) {
+  g.ipc = ceil_div(g.B * g.chunks, 512);
   return g;
 }
 
@@ -300,17 +344,18 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.z && a.y && a.gamma && a.beta && a.scale && a.shift && a.save_mean && a.save_rstd && a.partial, MTG_ERR_ARG,
               "bn_train_fwd: null pointer");
   MTG_REQUIRE(a.C % 8 == 0, MTG_ERR_UNSUPPORTED, "bn_train_fwd: C %% 8 != 0");
-  const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C));
+  const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C), a.B), gr = reducing_geo(g);
   dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
-  bn_stats_kernel<<<grid, 256, 0, st>>>(a.z, a.partial, g);
+  const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
+  bn_stats_kernel<<<rgrid, 256, 0, st>>>(a.z, a.partial, gr);
   MTG_LAUNCH_CHECK();
-  BnFinP f{a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
+  BnFinP f{a.partial, static_cast<int>(rgrid.z) * g.chunks, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
            a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd, a.C};
   bn_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(f);
   MTG_LAUNCH_CHECK();
   Geo ga = g;
   if (a.gap) {  // the SE pool wants few partials per image
-    ga = make_geo(a.C, a.HW, a.gap_chunks);
+    ga = make_geo(a.C, a.HW, a.gap_chunks, a.B);
     grid = dim3(ga.chunks, ceil_div(ga.CV, ga.CVc), a.B);
   }
   BnApplyP ap{a.z, a.scale, a.shift, a.act, a.residual, a.y, a.gap};
@@ -322,13 +367,14 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
 int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.z && a.dy && a.dz && a.scale && a.shift && a.save_mean && a.save_rstd && a.partial && a.dgamma && a.dbeta &&
                   a.c1 && a.c2, MTG_ERR_ARG, "bn_train_bwd: null pointer");
-  const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C));
+  const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C), a.B), gr = reducing_geo(g);
   dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
+  const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
   BnBwdP p{a.z, a.dy, a.scale, a.shift, a.save_mean, a.save_rstd, a.act, a.se_s, a.se_dmean, 1.f / static_cast<float>(a.HW),
            a.c1, a.c2, a.partial, a.dz};
-  bn_bwd_kernel<false><<<grid, 256, 0, st>>>(p, g);
+  bn_bwd_kernel<false><<<rgrid, 256, 0, st>>>(p, gr);
   MTG_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(a.partial, a.B * g.chunks, static_cast<double>(a.B) * a.HW, a.dgamma,
+  bn_bwd_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(a.partial, static_cast<int>(rgrid.z) * g.chunks, static_cast<double>(a.B) * a.HW, a.dgamma,
                                                              a.dbeta, a.c1, a.c2, a.C);
   MTG_LAUNCH_CHECK();
   bn_bwd_kernel<true><<<grid, 256, 0, st>>>(p, g);

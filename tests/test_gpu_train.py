@@ -364,7 +364,9 @@ def _chk(name, got, ref, tol_max=1e-2, tol_l2=5e-3):
 
 
 @pytest.mark.parametrize("B,HW,C,act,res,se", [(3, 300, 960, 2, False, True), (2, 4800, 72, 1, False, False),
-                                               (4, 1200, 40, 0, True, False), (2, 19200, 16, 2, False, False)])
+                                               (4, 1200, 40, 0, True, False), (2, 19200, 16, 2, False, False),
+                                               # B * chunks > 512: the reducing kernels walk two images per CTA (last CTA: one)
+                                               (21, 19200, 64, 1, False, False), (19, 19200, 64, 2, True, True)])
 def test_bn_train_fwd_bwd(B, HW, C, act, res, se):
     g = torch.Generator().manual_seed(C)
     lib = N.load()

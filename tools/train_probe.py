@@ -6,11 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import mtg_card_image_segmentation_b200 as M
 from mtg_card_image_segmentation_b200.optim import FusedAdamW
-from oracle.lraspp_oracle import synthetic_cards
 B = int(os.environ.get("TRAIN_B", "32"))
 steps = int(os.environ.get("TRAIN_STEPS", "3"))
-x, m = synthetic_cards(min(B, 8), seed=1)
-x = x.repeat((B + 7) // 8, 1, 1, 1)[:B].cuda(); m = m.repeat((B + 7) // 8, 1, 1)[:B].cuda()
+g = torch.Generator().manual_seed(1)  # noise images with a rectangular "card" mask (the oracle is test-only: not imported here)
+x = torch.randn(B, 3, 320, 240, generator=g).cuda()
+m = torch.zeros(B, 320, 240, dtype=torch.int64)
+m[:, 60:260, 50:190] = 1
+m = m.cuda()
 torch.manual_seed(0)
 model = M.create_model(2, False).cuda().train()
 opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
