@@ -441,7 +441,8 @@ def test_wgrad(M, N_, K, taps, H, W, se, tc):
 
 
 @pytest.mark.parametrize("B,H,W,C,k,stride,dil", [(2, 20, 15, 960, 5, 1, 2), (2, 80, 60, 72, 5, 2, 1), (2, 40, 30, 240, 3, 2, 1),
-                                                  (3, 33, 21, 16, 3, 1, 1)])
+                                                  (3, 33, 21, 16, 3, 1, 1), (5, 40, 30, 120, 5, 1, 1), (37, 20, 15, 672, 5, 1, 1),
+                                                  (9, 160, 120, 64, 3, 2, 1)])
 def test_dw_bwd(B, H, W, C, k, stride, dil):
     g = torch.Generator().manual_seed(C + k)
     x = torch.randn(B, H, W, C, generator=g).bfloat16().cuda()
