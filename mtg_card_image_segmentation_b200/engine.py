@@ -350,6 +350,7 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.optimizer.advance(self.hyper)
+        self.optimizer._opt_called = True  # what torch's LR schedulers check before their own step()
         self.graph.replay()
         torch.autograd.graph.increment_version(self._params)  # parameters changed behind autograd's back
         self.model.engine()._stats_dirty = True               # so did the BatchNorm running statistics
