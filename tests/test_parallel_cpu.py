@@ -28,6 +28,17 @@ def _worker(rank, world, port, out):
     P.merge_counts(counts)
     ok = ok and counts.tolist() == [10 * world + sum(range(world)), world, 2 * world, 3 * sum(range(world))]
     sl = P.shard_batch(257, rank, world)
+    # the captured single-GPU training step must refuse a data-parallel job (its graph holds no all-reduce)
+    import mtg_card_image_segmentation_b200 as M
+    from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+    from mtg_card_image_segmentation_b200.optim import FusedAdamW
+    model = M.create_model(2, pretrained=False).train()
+    try:
+        GraphedTrainStep(model, M.CombinedLoss(), FusedAdamW(model.parameters()), torch.zeros(1, 3, 64, 48),
+                         torch.zeros(1, 64, 48, dtype=torch.int64))
+        ok = False
+    except RuntimeError as e:
+        ok = ok and "data-parallel" in str(e)
     out[rank] = (bool(ok), sl.start, sl.stop, float((mine - flat).abs().max()) > 0)
     dist.destroy_process_group()
 
