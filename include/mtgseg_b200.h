@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MTGSEG_ABI_VERSION 1
+#define MTGSEG_ABI_VERSION 2
 
 #define MTGSEG_OK 0
 #define MTGSEG_ERR_ARG (-1)
@@ -78,6 +78,15 @@ int mtgseg_pack_weights(const mtgseg_net_desc* desc, const void* const* params, 
 int mtgseg_forward_infer(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits, int logits_dtype,
                          uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace, size_t workspace_bytes,
                          int batch, void* stream);
+
+/* The same forward in IEEE float32 end to end: what train/evaluate.py:66 computes (`self.model(images)`, no autocast) and what
+ * train/export.py:159 holds the exported graph to (1e-4).  Reads the fp32 parameters directly (`params` = the 319 state_dict
+ * device pointers, as for mtgseg_pack_weights), keeps fp32 NHWC activations in `workspace` (mtgseg_workspace_bytes_f32) and
+ * accumulates with round-to-nearest FMAs on the CUDA cores; outputs as for mtgseg_forward_infer. */
+size_t mtgseg_workspace_bytes_f32(const mtgseg_net_desc* desc, int batch);
+int mtgseg_forward_infer_f32(const mtgseg_net_desc* desc, const float* x, const void* const* params, int n_params, void* logits,
+                             int logits_dtype, uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace,
+                             size_t workspace_bytes, int batch, void* stream);
 
 /* One training step = mtgseg_forward_train -> (loss, mtgseg_loss_fwd_bwd) -> mtgseg_backward -> mtgseg_adamw_step ->
  * mtgseg_pack_weights, all on one stream with one workspace of mtgseg_train_workspace_bytes().
@@ -136,12 +145,14 @@ int mtgseg_metric_counts(const void* logits, int logits_dtype, const int64_t* ta
 
 /* CombinedLoss.forward + backward (train/utils.py:58-92, train/train.py:96-101) in one pass:
  *   loss3[0] = dice_weight*(1 - dice) + ce_weight*CE, loss3[1] = dice loss, loss3[2] = CE
- *   dlogits (same dtype/layout as logits, may be NULL) = d loss3[0] / d logits
+ *   dlogits (logits' layout, may be NULL) = d loss3[0] / d logits, stored as dlogits_dtype: the logits' dtype or
+ *           MTGSEG_LOGITS_F32.  fp16 logits (the reference's autocast dtype, train/train.py:96) want F32: the unscaled
+ *           gradient (~1e-7 at batch 32) is an fp16 subnormal until GradScaler's factor (train/train.py:101) is applied.
  * logits [batch,num_classes,hw]; targets int64 [batch,hw]; scratch = mtgseg_loss_scratch_bytes() bytes. */
 size_t mtgseg_loss_scratch_bytes(void);
-int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, float* scratch,
-                        float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight, float ce_weight,
-                        float smooth, void* stream);
+int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, int dlogits_dtype,
+                        float* scratch, float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight,
+                        float ce_weight, float smooth, void* stream);
 
 /* ---- per-operator entry points (unit tests, profiling) ------------------------------------------------ */
 /* nn.Conv2d 1x1 (+ folded BN, activation, residual, squeeze-excite input scale) on NHWC bf16:

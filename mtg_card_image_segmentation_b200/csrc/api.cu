@@ -81,6 +81,36 @@ int mtgseg_forward_infer_u8(const mtgseg_net_desc* desc, const uint8_t* x_hwc, c
   return forward_infer_impl(desc, nullptr, x_hwc, packed, logits, logits_dtype, mask, counts4, targets, workspace, workspace_bytes, batch, stream);
 }
 
+size_t mtgseg_workspace_bytes_f32(const mtgseg_net_desc* desc, int batch) {
+  NetPlan P;
+  if (plan_for(desc, P) != MTG_OK || batch <= 0) return 0;
+  InferF32IO io;
+  io.batch = batch;
+  size_t need = 0;
+  if (run_infer_f32(P, io, nullptr, 0, &need, nullptr) != MTG_OK) return 0;
+  return need;
+}
+
+int mtgseg_forward_infer_f32(const mtgseg_net_desc* desc, const float* x, const void* const* params, int n_params, void* logits,
+                             int logits_dtype, uint8_t* mask, uint64_t* counts4, const int64_t* targets, void* workspace,
+                             size_t workspace_bytes, int batch, void* stream) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(x && params && workspace, MTG_ERR_ARG, "forward_infer_f32: null pointer");
+  MTG_REQUIRE(n_params == P.n_params, MTG_ERR_ARG, "forward_infer_f32: expected %d state_dict entries, got %d", P.n_params, n_params);
+  for (int i = 0; i < n_params; ++i) MTG_REQUIRE(params[i] != nullptr, MTG_ERR_ARG, "forward_infer_f32: params[%d] is NULL", i);
+  MTG_REQUIRE(batch > 0, MTG_ERR_ARG, "forward_infer_f32: batch must be positive");
+  MTG_REQUIRE(logits || mask || counts4, MTG_ERR_ARG, "forward_infer_f32: no output requested");
+  MTG_REQUIRE(!logits || (logits_dtype >= LOGITS_F32 && logits_dtype <= LOGITS_F16), MTG_ERR_ARG, "forward_infer_f32: bad logits dtype %d", logits_dtype);
+  MTG_REQUIRE(!counts4 || targets, MTG_ERR_ARG, "forward_infer_f32: counts4 needs targets");
+  MTG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MTG_ERR_ARG, "forward_infer_f32: workspace must be 256-byte aligned");
+  InferF32IO io;
+  io.x = x; io.params = params; io.logits = logits; io.logits_dtype = logits_dtype; io.mask = mask; io.counts4 = counts4;
+  io.targets = targets; io.batch = batch;
+  return run_infer_f32(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, nullptr, S(stream));
+}
+
 size_t mtgseg_train_workspace_bytes(const mtgseg_net_desc* desc, int batch) {
   NetPlan P;
   if (plan_for(desc, P) != MTG_OK || batch <= 0) return 0;
@@ -244,11 +274,11 @@ int mtgseg_metric_counts(const void* logits, int logits_dtype, const int64_t* ta
 
 size_t mtgseg_loss_scratch_bytes(void) { return loss_scratch_bytes(); }
 
-int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, float* scratch,
-                        float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight, float ce_weight,
-                        float smooth, void* stream) {
-  return launch_loss(logits, logits_dtype, targets, dlogits, scratch, loss3, batch, hw, num_classes, dice_weight, ce_weight,
-                     smooth, S(stream));
+int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, int dlogits_dtype,
+                        float* scratch, float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight,
+                        float ce_weight, float smooth, void* stream) {
+  return launch_loss(logits, logits_dtype, targets, dlogits, dlogits_dtype, scratch, loss3, batch, hw, num_classes, dice_weight,
+                     ce_weight, smooth, S(stream));
 }
 
 int mtgseg_conv1x1(const void* a, const void* w, void* out, int M, int N, int K, const float* scale, const float* shift,

@@ -27,9 +27,11 @@ template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p =
 template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16(v); }
 template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half(v); }
 
-template <typename T>
+// T: logits element type; G: gradient element type (T, or float: fp16 logits get fp32 gradients, the unscaled values
+// (~1e-7 at B=32, 320x240) are fp16 subnormals and must not be narrowed before the GradScaler factor is applied)
+template <typename T, typename G>
 __global__ void __launch_bounds__(256) loss_kernel(const T* __restrict__ logits, const int64_t* __restrict__ targets,
-                                                   T* __restrict__ dlogits, float* __restrict__ partials, long long batch,
+                                                   G* __restrict__ dlogits, float* __restrict__ partials, long long batch,
                                                    long long hw, int nc, float g_ce, float g_dice) {
   __shared__ float red[2][8];
   float s_pt = 0.f, s_log = 0.f;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const T* __restrict__ logits,
     s_pt += pt;
     s_log += logf(pt);
     if (dlogits) {
-      T* gp = dlogits + n * nc * hw + px;
+      G* gp = dlogits + n * nc * hw + px;
 #pragma unroll
       for (int c = 0; c < MAX_NC; ++c)
         if (c < nc) {
@@ -105,7 +107,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partials, int blo
 
 size_t loss_scratch_bytes() { return sizeof(float) * 2 * LOSS_BLOCKS; }
 
-int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, float* scratch, float* loss3,
+int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, int dlogits_dtype, float* scratch, float* loss3,
                 long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st) {
   MTG_REQUIRE(logits && targets && scratch && loss3, MTG_ERR_ARG, "loss: null pointer");
   MTG_REQUIRE(nc >= 2 && nc <= MAX_NC, MTG_ERR_UNSUPPORTED, "loss: num_classes %d not in [2,%d]", nc, MAX_NC);
@@ -116,14 +118,17 @@ int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlo
   long long blocks = (batch * hw + 256 * 4 - 1) / (256 * 4);
   if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
   const int g = static_cast<int>(blocks);
-  if (dtype == LOGITS_F32)
-    loss_kernel<float><<<g, 256, 0, st>>>(static_cast<const float*>(logits), targets, static_cast<float*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice);
-  else if (dtype == LOGITS_BF16)
-    loss_kernel<bf16><<<g, 256, 0, st>>>(static_cast<const bf16*>(logits), targets, static_cast<bf16*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice);
-  else if (dtype == LOGITS_F16)
-    loss_kernel<__half><<<g, 256, 0, st>>>(static_cast<const __half*>(logits), targets, static_cast<__half*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice);
-  else
-    MTG_REQUIRE(false, MTG_ERR_ARG, "loss: unknown logits dtype %d", dtype);
+  if (!dlogits) dlogits_dtype = dtype;
+  MTG_REQUIRE(dlogits_dtype == dtype || dlogits_dtype == LOGITS_F32, MTG_ERR_UNSUPPORTED,
+              "loss: dlogits must have the logits' dtype or be float32 (got %d for logits %d)", dlogits_dtype, dtype);
+  const bool gf = dlogits_dtype == LOGITS_F32;
+#define MTG_LOSS_LAUNCH(T, G) \
+  loss_kernel<T, G><<<g, 256, 0, st>>>(static_cast<const T*>(logits), targets, static_cast<G*>(dlogits), scratch, batch, hw, nc, g_ce, g_dice)
+  if (dtype == LOGITS_F32) MTG_LOSS_LAUNCH(float, float);
+  else if (dtype == LOGITS_BF16) { if (gf) MTG_LOSS_LAUNCH(bf16, float); else MTG_LOSS_LAUNCH(bf16, bf16); }
+  else if (dtype == LOGITS_F16) { if (gf) MTG_LOSS_LAUNCH(__half, float); else MTG_LOSS_LAUNCH(__half, __half); }
+  else MTG_REQUIRE(false, MTG_ERR_ARG, "loss: unknown logits dtype %d", dtype);
+#undef MTG_LOSS_LAUNCH
   MTG_LAUNCH_CHECK();
   loss_finalize_kernel<<<1, 256, 0, st>>>(scratch, g, n, dice_w, ce_w, smooth, loss3);
   MTG_LAUNCH_CHECK();

@@ -64,6 +64,16 @@ int pack_weights(const NetPlan& P, const void* const* params, void* packed, cuda
 int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes, size_t* ws_needed, cudaStream_t st,
               LayerProfiler* prof = nullptr);
 
+// fp32-exact inference (f32net.cu): what train/evaluate.py:66 computes (no autocast); reads the fp32 master parameters directly
+struct InferF32IO {
+  const float* x = nullptr;            // [B][3][H][W] fp32
+  const void* const* params = nullptr; // the 319 state_dict device pointers
+  void* logits = nullptr; int logits_dtype = LOGITS_F32;
+  uint8_t* mask = nullptr; uint64_t* counts4 = nullptr; const int64_t* targets = nullptr;
+  int batch = 0;
+};
+int run_infer_f32(const NetPlan& P, const InferF32IO& io, uint8_t* ws, size_t ws_bytes, size_t* ws_needed, cudaStream_t st);
+
 // training step (net_train.cu): forward with batch-statistics BatchNorm keeping what backward needs in `ws`,
 // then backward producing fp32 parameter gradients in the reference (state_dict) layout.
 struct TrainIO {

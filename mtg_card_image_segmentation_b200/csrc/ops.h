@@ -105,8 +105,8 @@ int launch_metric_counts(const void* logits, int logits_dtype, const int64_t* ta
 
 // ---- fused CombinedLoss forward + gradient (loss.cu) ---------------------------------------------
 size_t loss_scratch_bytes();
-// loss3 = {total, dice_loss, ce_loss}; dlogits (same dtype/layout as logits, nullable) = dLoss/dlogits
-int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, float* scratch, float* loss3,
+// loss3 = {total, dice_loss, ce_loss}; dlogits (logits' layout; logits' dtype or float32; nullable) = dLoss/dlogits
+int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, int dlogits_dtype, float* scratch, float* loss3,
                 long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st);
 
 // ---- training-mode BatchNorm forward / backward (bn_train.cu) --------------------------------------

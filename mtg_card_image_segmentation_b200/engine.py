@@ -24,6 +24,8 @@ class SegEngine:
         self._static_flat = None
         self._stats_dirty = False
         self._desc_cache = {}
+        self._train_gen = 0    # bumped by every training-mode forward (the ONE workspace holds the last forward's activations)
+        self._pack_count = 0   # bumped by every re-pack of the weight arena
 
     def desc(self, h: int, w: int) -> N.NetDesc:
         key = (h, w)
@@ -53,11 +55,14 @@ class SegEngine:
         arr = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
         N.check(self.lib.mtgseg_pack_weights(C.byref(d), arr, n, self._packed.data_ptr(), N.stream_ptr()), "mtgseg_pack_weights")
         self._packed_sig = sig
+        self._pack_count += 1
         return self._packed
 
-    def workspace(self, d: N.NetDesc, batch: int, device, slot: int = 0) -> torch.Tensor:
-        """Activation workspace; `slot` > 0 selects an independent buffer (concurrent sub-batches on other streams)."""
-        need = self.lib.mtgseg_workspace_bytes(C.byref(d), batch)
+    def workspace(self, d: N.NetDesc, batch: int, device, slot=0) -> torch.Tensor:
+        """Activation workspace; `slot` != 0 selects an independent buffer (concurrent sub-batches on other streams;
+        ("f32", i) = the fp32-exact path's larger workspace)."""
+        f32 = isinstance(slot, tuple)
+        need = (self.lib.mtgseg_workspace_bytes_f32 if f32 else self.lib.mtgseg_workspace_bytes)(C.byref(d), batch)
         if need == 0:
             raise RuntimeError(f"mtgseg_workspace_bytes failed: {self.lib.mtgseg_last_error().decode()}")
         cur = self._ws if slot == 0 else self._ws_extra.get(slot)
@@ -70,9 +75,15 @@ class SegEngine:
         return cur
 
     # -- inference ---------------------------------------------------------------------------
-    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None, ws_slot=0, out=None, mask_out=None):
-        """`out` / `mask_out`: caller-owned logits / uint8 mask buffers (e.g. batch slices of a larger tensor)."""
+    def infer(self, tensors, x, logits_dtype=torch.float32, want_mask=False, targets=None, ws_slot=0, out=None, mask_out=None,
+              precision="bf16"):
+        """`out` / `mask_out`: caller-owned logits / uint8 mask buffers (e.g. batch slices of a larger tensor).
+        precision "bf16": tensor-core path (bf16 storage, fp32 accumulate); "fp32": IEEE fp32 end to end (train/evaluate.py:66)."""
+        if precision not in ("bf16", "fp32"):
+            raise RuntimeError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         u8 = x.dtype == torch.uint8
+        if u8 and precision == "fp32":
+            raise RuntimeError("the fp32-exact path takes the normalised float32 (B,3,H,W) batch, not raw uint8 frames")
         if u8:  # raw HWC pixels: normalisation is fused into the stem kernel
             if x.dim() != 4 or x.shape[3] != 3:
                 raise RuntimeError(f"uint8 input must be (B,H,W,3) raw pixels, got {tuple(x.shape)}")
@@ -88,9 +99,15 @@ class SegEngine:
         dev = x.device
         fwd = self.lib.mtgseg_forward_infer_u8 if u8 else self.lib.mtgseg_forward_infer
         with torch.cuda.device(dev):
-            packed = self.pack(tensors, dev)
             d = self.desc(H, W)
-            ws = self.workspace(d, B, dev, ws_slot)
+            if precision == "fp32":
+                for t in tensors:
+                    if t.device != dev or not t.is_contiguous():
+                        raise RuntimeError("model parameters/buffers must be contiguous and on the input's CUDA device")
+                ws = self.workspace(d, B, dev, ("f32", ws_slot))
+            else:
+                packed = self.pack(tensors, dev)
+                ws = self.workspace(d, B, dev, ws_slot)
             logits = None
             if logits_dtype is not None:
                 logits = out if out is not None else torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
@@ -105,10 +122,16 @@ class SegEngine:
                     raise RuntimeError("targets must be an int64 (B,H,W) tensor on the input's device")
                 targets = targets.contiguous()
                 counts = torch.zeros(4, dtype=torch.int64, device=dev)
-            rc = fwd(
-                C.byref(d), x.data_ptr(), packed.data_ptr(), N.ptr(logits),
-                _TORCH_TO_LOGITS.get(logits_dtype, N.LOGITS_NONE), N.ptr(mask), N.ptr(counts), N.ptr(targets),
-                ws.data_ptr(), ws.numel(), B, N.stream_ptr())
+            if precision == "fp32":
+                rc = self.lib.mtgseg_forward_infer_f32(
+                    C.byref(d), x.data_ptr(), self._ptr_array(tensors), len(tensors), N.ptr(logits),
+                    _TORCH_TO_LOGITS.get(logits_dtype, N.LOGITS_NONE), N.ptr(mask), N.ptr(counts), N.ptr(targets),
+                    ws.data_ptr(), ws.numel(), B, N.stream_ptr())
+            else:
+                rc = fwd(
+                    C.byref(d), x.data_ptr(), packed.data_ptr(), N.ptr(logits),
+                    _TORCH_TO_LOGITS.get(logits_dtype, N.LOGITS_NONE), N.ptr(mask), N.ptr(counts), N.ptr(targets),
+                    ws.data_ptr(), ws.numel(), B, N.stream_ptr())
             N.check(rc, "mtgseg_forward_infer")
         if want_mask or targets is not None:
             return {"logits": logits, "mask": mask, "counts": counts}
@@ -141,10 +164,21 @@ class SegEngine:
                                                self._train_ws.numel(), B, N.stream_ptr())
             N.check(rc, "mtgseg_forward_train")
         self._stats_dirty = True  # running statistics changed under the folded-BN cache
+        self._train_gen += 1
         return logits, x
 
-    def train_backward(self, tensors, is_param, x, dlogits):
-        """loss.backward(): returns (flat fp32 gradient buffer, list of per-state-entry views or None)."""
+    def train_token(self):
+        """Identifies the forward whose activations the workspace holds and the weight arena it used (checked by backward)."""
+        return (self._train_gen, self._pack_count)
+
+    def train_backward(self, tensors, is_param, x, dlogits, token=None):
+        """loss.backward(): returns (flat fp32 gradient buffer, list of per-state-entry views or None).  `token` =
+        train_token() taken right after the forward this backward belongs to."""
+        if token is not None and token != self.train_token():
+            what = ("another training-mode forward has overwritten the saved activations" if token[0] != self._train_gen else
+                    "the weights were re-packed (optimizer step, load_state_dict or an eval-mode forward) after the forward")
+            raise RuntimeError(f"backward() of a stale forward: {what}. The CUDA training step keeps ONE set of saved "
+                               "activations per model: call backward() before the next model(x) / optimizer.step().")
         B, _, H, W = x.shape
         dev = x.device
         dlogits = dlogits.contiguous()
@@ -193,7 +227,7 @@ class GraphedInference:
     units): kernels of different sub-batches fill each other's ramp-up / drain phases.
     ``run(x)`` copies ``x`` into the captured input buffer and replays; outputs are the captured tensors."""
 
-    def __init__(self, model, example, logits_dtype=torch.bfloat16, want_mask=False, splits=1):
+    def __init__(self, model, example, logits_dtype=torch.bfloat16, want_mask=False, splits=1, precision="bf16"):
         self.model = model
         self.x = example.clone()
         eng, tensors = model.engine(), model._state_tensors()
@@ -208,7 +242,7 @@ class GraphedInference:
 
         def run_all():
             if splits == 1:
-                return eng.infer(tensors, self.x, logits_dtype=logits_dtype, want_mask=want_mask, out=logits)
+                return eng.infer(tensors, self.x, logits_dtype=logits_dtype, want_mask=want_mask, out=logits, precision=precision)
             main = torch.cuda.current_stream()
             for i in range(splits):
                 st = self._streams[i]
@@ -216,7 +250,8 @@ class GraphedInference:
                 with torch.cuda.stream(st):
                     sl = slice(bounds[i], bounds[i + 1])
                     eng.infer(tensors, self.x[sl], logits_dtype=logits_dtype, want_mask=want_mask, ws_slot=i,
-                              out=None if logits is None else logits[sl], mask_out=None if mask is None else mask[sl])
+                              out=None if logits is None else logits[sl], mask_out=None if mask is None else mask[sl],
+                              precision=precision)
             for st in self._streams:
                 main.wait_stream(st)
             return {"logits": logits, "mask": mask, "counts": None} if want_mask else logits

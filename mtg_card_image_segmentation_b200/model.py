@@ -146,6 +146,7 @@ class _TrainStep(torch.autograd.Function):
         tensors = model._step_tensors  # resolved by the caller: parameters, or masked non-leaf weights under active pruning
         logits, x32 = model.engine().train_forward(tensors, x, out_dtype)
         ctx.model, ctx.tensors, ctx.x32 = model, tensors, x32
+        ctx.token = model.engine().train_token()
         ctx.param_ids = {id(p): i for i, p in enumerate(params)}
         return logits
 
@@ -153,7 +154,7 @@ class _TrainStep(torch.autograd.Function):
     def backward(ctx, dlogits):
         model, tensors = ctx.model, ctx.tensors
         is_param = [id(t) in ctx.param_ids for t in tensors]
-        flat, views = model.engine().train_backward(tensors, is_param, ctx.x32, dlogits)
+        flat, views = model.engine().train_backward(tensors, is_param, ctx.x32, dlogits, ctx.token)
         model.last_flat_grad = flat  # one contiguous buffer: a data-parallel driver all-reduces it in one call
         grads = [None] * len(ctx.param_ids)
         for t, v in zip(tensors, views):
@@ -179,6 +180,10 @@ class CardSegmentationModel(nn.Module):
         self._has_masks = False
         self._slots = None
         self._param_slots = None
+        # Arithmetic of an eval-mode forward.  "auto" follows the reference's own dtype rule: under torch.autocast
+        # (train/train.py:96,142) the tensor-core path (bf16 storage, fp32 accumulate); without autocast (train/evaluate.py:66)
+        # IEEE float32 end to end, within 1e-4 of the reference.  "bf16" / "fp32" force one of them.
+        self.inference_precision = "auto"
         self._ref_keys = list(self.state_dict().keys())  # the reference's 319-key layout (train/utils.py:227-280 checkpoints)
         self.last_flat_grad = None
 
@@ -257,14 +262,23 @@ class CardSegmentationModel(nn.Module):
                     self._step_tensors = tensors
                     return _TrainStep.apply(self, x, out_dtype, *req)
             return self.engine().train_forward(tensors, x, out_dtype)[0]
-        return self.engine().infer(self._state_tensors(), x, logits_dtype=out_dtype)
+        return self.engine().infer(self._state_tensors(), x, logits_dtype=out_dtype, precision=self._precision(x))
+
+    def _precision(self, x, override=None):
+        mode = override or self.inference_precision
+        if mode == "auto":
+            return "bf16" if (torch.is_autocast_enabled("cuda") or x.dtype != torch.float32) else "fp32"
+        if mode not in ("bf16", "fp32"):
+            raise RuntimeError(f"inference_precision must be 'auto', 'bf16' or 'fp32', got {mode!r}")
+        return mode
 
     @torch.no_grad()
-    def predict(self, x, targets=None, want_logits=False):
+    def predict(self, x, targets=None, want_logits=False, precision=None):
         """Batched inference as train/evaluate.py:66-78 uses it, fused: returns the uint8 argmax mask and, when
-        ``targets`` is given, the int64[4] confusion counts; logits only on request."""
+        ``targets`` is given, the int64[4] confusion counts; logits only on request.  ``precision``: None = the model's
+        ``inference_precision`` rule (fp32-exact for a float32 batch outside autocast, like evaluate.py:66), or "bf16" / "fp32"."""
         return self.engine().infer(self._state_tensors(), x, logits_dtype=torch.float32 if want_logits else None,
-                                   want_mask=True, targets=targets)
+                                   want_mask=True, targets=targets, precision=self._precision(x, precision))
 
 
 def create_model(num_classes=2, pretrained=True):

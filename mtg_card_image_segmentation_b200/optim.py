@@ -25,7 +25,11 @@ class FusedAdamW(torch.optim.Optimizer):
         """Device chunk table of one parameter group.  It only depends on pointers; the caching allocator hands the same gradient
         block back every step, so in steady state the device copy is reused."""
         dev = params[0].device
-        key = (gi, tuple(p.grad.data_ptr() for p in params), tuple(p.data_ptr() for p in params))
+        # every pointer a record embeds is part of the key: Optimizer.load_state_dict (utils.load_checkpoint) REPLACES the
+        # exp_avg / exp_avg_sq tensors, and a table built before the load would keep updating the freed ones
+        key = (gi, tuple(p.grad.data_ptr() for p in params), tuple(p.data_ptr() for p in params),
+               tuple(self.state[p]["exp_avg"].data_ptr() for p in params),
+               tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in params))
         if key not in self._tables:  # (the flat gradient buffer alternates between two allocator blocks)
             if len(self._tables) >= 8:
                 self._tables.clear()
@@ -38,6 +42,16 @@ class FusedAdamW(torch.optim.Optimizer):
             host = torch.from_numpy(np.array(recs, dtype=_REC).view(np.uint8).copy()).pin_memory()
             self._tables[key] = (host.to(dev, non_blocking=True), len(recs), host)
         return self._tables[key]
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables.clear()  # the moment tensors were replaced
+        self._state_epoch = getattr(self, "_state_epoch", 0) + 1  # engine.GraphedTrainStep refuses to replay a stale capture
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_tables"):
+            self._tables.clear()
 
     def _checked_params(self, group, init_state):
         params = [p for p in group["params"] if p.grad is not None]

@@ -40,11 +40,16 @@ def fused_loss(predictions, targets, dice_weight, ce_weight, smooth, need_grad):
     p = predictions.contiguous()
     t = targets.contiguous()
     B, C, H, W = p.shape
-    dlogits = torch.empty_like(p) if need_grad else None
+    # fp16 logits (the reference's autocast dtype) get an fp32 gradient: unscaled it is ~1e-7, an fp16 subnormal; it is narrowed
+    # only after GradScaler's factor has been multiplied in (_FusedLoss.backward), like autocast's fp32 softmax / CE backward
+    dlogits = None
+    if need_grad:
+        dlogits = torch.empty_like(p, dtype=torch.float32) if p.dtype == torch.float16 else torch.empty_like(p)
     scratch = torch.empty(lib.mtgseg_loss_scratch_bytes() // 4, dtype=torch.float32, device=p.device)
     loss3 = torch.empty(3, dtype=torch.float32, device=p.device)
     with torch.cuda.device(p.device):
-        N.check(lib.mtgseg_loss_fwd_bwd(p.data_ptr(), _DT[p.dtype], t.data_ptr(), N.ptr(dlogits), scratch.data_ptr(),
+        N.check(lib.mtgseg_loss_fwd_bwd(p.data_ptr(), _DT[p.dtype], t.data_ptr(), N.ptr(dlogits),
+                                        _DT[dlogits.dtype] if need_grad else N.LOGITS_NONE, scratch.data_ptr(),
                                         loss3.data_ptr(), B, H * W, C, dice_weight, ce_weight, smooth, N.stream_ptr()),
                 "mtgseg_loss_fwd_bwd")
     return loss3, dlogits
@@ -66,6 +71,7 @@ class _FusedLoss(torch.autograd.Function):
     def forward(ctx, predictions, targets, dice_weight, ce_weight, smooth):
         loss3, dlogits = fused_loss(predictions, targets, dice_weight, ce_weight, smooth, predictions.requires_grad)
         ctx.dlogits = dlogits
+        ctx.out_dtype = predictions.dtype
         ctx.mark_non_differentiable(loss3)
         return loss3[0], loss3
 
@@ -73,7 +79,8 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, grad_total, _grad_parts):
         if ctx.dlogits is None:
             return None, None, None, None, None
-        return ctx.dlogits * grad_total.to(ctx.dlogits.dtype), None, None, None, None
+        # scale in the gradient's own precision (fp32 for fp16 logits), narrow afterwards (autograd casts to the logits' dtype too)
+        return (ctx.dlogits * grad_total.to(ctx.dlogits.dtype)).to(ctx.out_dtype), None, None, None, None
 
 
 class DiceLoss(nn.Module):

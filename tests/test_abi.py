@@ -33,7 +33,7 @@ def test_binding_covers_header_and_basic_queries():
     from mtg_card_image_segmentation_b200 import _native as N
     assert sorted(N.SIGNATURES) == _declared()
     lib = N.load()
-    assert lib.mtgseg_version() == 1
+    assert lib.mtgseg_version() == 2
     assert lib.mtgseg_param_count() == 319
     d = N.NetDesc(320, 240, 2, 128)
     packed = lib.mtgseg_packed_bytes(ctypes.byref(d))

@@ -21,9 +21,12 @@ import mtg_card_image_segmentation_b200 as M  # noqa: E402
 import devops as D  # noqa: E402
 
 
-def _model(sd):
+def _model(sd, precision="bf16"):
+    """The tests of this file pin the tensor-core (bf16 storage) path unless they say otherwise; the default "auto" rule would
+    run a float32 batch outside autocast through the fp32-exact path (tests/test_gpu_fp32.py)."""
     m = M.create_model(2, pretrained=False)
     m.load_state_dict(sd, strict=True)
+    m.inference_precision = precision
     return m.cuda().eval()
 
 

@@ -33,6 +33,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 def _train_model(sd):
     m = M.create_model(2, pretrained=False)
     m.load_state_dict(sd, strict=True)
+    m.inference_precision = "bf16"  # eval-mode checks in this file compare against the bf16-emulated oracle
     return m.cuda().train()
 
 
@@ -115,6 +116,7 @@ def test_training_reduces_loss_and_eval_uses_new_stats():
     """A few real optimisation steps through the public surface (train/train.py:89-111 shape of the loop)."""
     x, m = O.synthetic_cards(8, seed=3, height=64, width=48)
     model = M.create_model(2, pretrained=False).cuda().train()
+    model.inference_precision = "bf16"
     opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
     crit = M.CombinedLoss()
     xc, mc = x.cuda(), m.cuda()
@@ -489,6 +491,7 @@ def test_parity_on_short_trained_weights():
     tolerances (2e-2 relative logits, >= 99.9 % identical masks) are stated for."""
     torch.manual_seed(0)
     model = M.create_model(2, pretrained=False).cuda().train()
+    model.inference_precision = "bf16"
     opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
     crit = M.CombinedLoss()
     first = last = None
