@@ -206,6 +206,23 @@ int mtgseg_stem_wgrad(const float* x, const void* dz, float* dw, int B, int H, i
 /* transpose of the align_corners=False bilinear upsample: g[B,NC,Hf,Wf] -> out fp32 [B,Hc,Wc,NC] */
 int mtgseg_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int Hc, int Wc, int Hf, int Wf, void* stream);
 
+/* backward of SqueezeExcitation (tv:ops/misc.py:252-261: s = hardsigmoid(fc2(relu(fc1(mean(y))))), out = s * y) for the part that
+ * goes THROUGH the gate, given da = dL/d(out) [B,HW,C] bf16 and the block's saved forward state (y = the depthwise output the gate
+ * multiplied, s [B,C], hid = relu(fc1(...)) [B,SQ], gap = per-chunk channel sums of y [B,gap_chunks,C]):
+ *   dmean[B,C] = dL/d(mean(y)) (mtgseg_bn_train_bwd adds dmean/HW to every pixel's gradient through se_dmean),
+ *   dw2[C,SQ], db2[C], dw1[SQ,C], db1[SQ] = gradients of fc2 / fc1 (OVERWRITTEN).  w1 / w2: the fp32 master weights.
+ * scratch >= mtgseg_se_bwd_scratch_floats(B, C, SQ) floats. */
+size_t mtgseg_se_bwd_scratch_floats(int B, int C, int SQ);
+int mtgseg_se_block_bwd(const void* da, const void* y, const float* s, const float* hid, const float* gap, int gap_chunks,
+                        const float* w1, const float* w2, float* dmean, float* dw1, float* db1, float* dw2, float* db2,
+                        float* scratch, int B, int HW, int C, int SQ, void* stream);
+/* backward of the head tail (train/model.py:137-142; forward = mtgseg_head_mix): d_lowres [B,Hl,Wl,NC] = gradient of the
+ * low-resolution logits, d_h2 [B,Hh,Wh,NC] = its x2-bilinear transpose (mtgseg_upsample_bwd).  Writes dcbr [B,Hh,Wh,IC] bf16,
+ * dlow [B,Hl,Wl,LC] bf16; ACCUMULATES (atomics; zero first) ds [B,IC], dw_high [NC,IC], dw_low [NC,LC], db_high [NC], db_low [NC]. */
+int mtgseg_head_bwd(const float* d_lowres, const float* d_h2, const void* cbr, const float* s, const void* low, const float* w_high,
+                    const float* w_low, void* dcbr, float* ds, void* dlow, float* dw_high, float* dw_low, float* db_high,
+                    float* db_low, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC, int NC, void* stream);
+
 /* ---- corner-keypoint head of the pose pipeline (BASELINE.json configs[4]) ----------------------------------
  * HRNetPoseHead.forward in eval mode (train-pose-estimation_custom/model.py:10-77) on a backbone feature map and
  * LiteHRNet.decode_heatmaps (model.py:133-164).  params = the 28 state_dict entries of HRNetPoseHead in order.

@@ -226,6 +226,41 @@ int mtgseg_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int
                              static_cast<long long>(Hf) * Wf, 1, S(stream));
 }
 
+size_t mtgseg_se_bwd_scratch_floats(int B, int C, int SQ) { return static_cast<size_t>(B) * (16 * C + C + SQ); }
+
+int mtgseg_se_block_bwd(const void* da, const void* y, const float* s, const float* hid, const float* gap, int gap_chunks,
+                        const float* w1, const float* w2, float* dmean, float* dw1, float* db1, float* dw2, float* db2,
+                        float* scratch, int B, int HW, int C, int SQ, void* stream) {
+  MTG_REQUIRE(da && y && s && hid && gap && w1 && w2 && dmean && dw1 && db1 && dw2 && db2 && scratch, MTG_ERR_ARG, "se_block_bwd: null pointer");
+  MTG_REQUIRE(gap_chunks >= 1 && gap_chunks <= 16, MTG_ERR_ARG, "se_block_bwd: gap_chunks must be in [1,16]");
+  float* ds_part = scratch;                                     // [B][chunks][C]
+  float* dpre2 = scratch + static_cast<size_t>(B) * 16 * C;     // [B][C]
+  float* dpre1 = dpre2 + static_cast<size_t>(B) * C;            // [B][SQ]
+  int rc = launch_dot_pool(static_cast<const bf16*>(da), static_cast<const bf16*>(y), ds_part, B, HW, C, gap_chunks, S(stream));
+  if (rc) return rc;
+  SeBwdArgs a;
+  a.ds_partial = ds_part; a.chunks = gap_chunks; a.s = s; a.hid = hid; a.w1 = w1; a.w2 = w2;
+  a.dpre2 = dpre2; a.dpre1 = dpre1; a.dmean = dmean; a.B = B; a.C = C; a.SQ = SQ;
+  rc = launch_se_bwd(a, S(stream));
+  if (rc) return rc;
+  rc = launch_outer_sum(dpre2, hid, 1, 1.f, dw2, db2, B, C, SQ, S(stream));
+  if (rc) return rc;
+  return launch_outer_sum(dpre1, gap, gap_chunks, 1.f / static_cast<float>(HW), dw1, db1, B, SQ, C, S(stream));
+}
+
+int mtgseg_head_bwd(const float* d_lowres, const float* d_h2, const void* cbr, const float* s, const void* low, const float* w_high,
+                    const float* w_low, void* dcbr, float* ds, void* dlow, float* dw_high, float* dw_low, float* db_high,
+                    float* db_low, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC, int NC, void* stream) {
+  MTG_REQUIRE(d_lowres && d_h2 && cbr && s && low && w_high && w_low && dcbr && ds && dlow && dw_high && dw_low && db_high && db_low,
+              MTG_ERR_ARG, "head_bwd: null pointer");
+  HeadBwdArgs a;
+  a.d_o = d_lowres; a.dh2 = d_h2; a.cbr = static_cast<const bf16*>(cbr); a.s = s; a.low = static_cast<const bf16*>(low);
+  a.w_high = w_high; a.w_low = w_low; a.dcbr = static_cast<bf16*>(dcbr); a.ds = ds; a.dlow = static_cast<bf16*>(dlow);
+  a.dw_high = dw_high; a.dw_low = dw_low; a.db_high = db_high; a.db_low = db_low;
+  a.B = B; a.Hh = Hh; a.Wh = Wh; a.Hl = Hl; a.Wl = Wl; a.IC = IC; a.LC = LC; a.NC = NC;
+  return launch_head_bwd(a, S(stream));
+}
+
 unsigned long long mtgseg_launch_count(void) { return launch_count(); }
 
 int mtgseg_forward_infer_profiled(const mtgseg_net_desc* desc, const float* x, const void* packed, void* logits,

@@ -266,3 +266,32 @@ def load_checkpoint(model, optimizer, scheduler, checkpoint_path):
     print(f"Checkpoint loaded from: {checkpoint_path}")
     print(f"Resumed from epoch: {epoch}, Best metric: {best_metric:.4f}")
     return epoch, best_metric
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining names train/train.py:18-21 and train/evaluate.py:17-20 import from `utils`, so that this module can stand in
+# for it as a whole (tests/test_reference_drivers.py runs the reference's drivers that way)
+# ------------------------------------------------------------------------------------------------
+
+_PRINTED = (("Loss", "loss"), ("Mean IoU", "mean_iou"), ("IoU Background", "iou_background"), ("IoU Card", "iou_card"),
+            ("Mean Dice", "mean_dice"), ("Dice Background", "dice_background"), ("Dice Card", "dice_card"),
+            ("Pixel Accuracy", "pixel_accuracy"))
+
+
+def print_metrics(metrics, prefix=""):
+    """Same eight lines, labels and 4-decimal format as train/utils.py:399-415."""
+    print(f"{prefix}Metrics:")
+    for label, key in _PRINTED:
+        print(f"  {label}: {metrics.get(key, 0):.4f}")
+
+
+def _visualisation_only(name):
+    def fn(*args, **kwargs):
+        raise RuntimeError(f"{name} is matplotlib visualisation (train/utils.py:282-397), outside the B200 hot path: "
+                           "call the reference's own helper (it works on this package's model and metrics unchanged).")
+    fn.__name__ = name
+    return fn
+
+
+plot_training_history = _visualisation_only("plot_training_history")
+visualize_predictions = _visualisation_only("visualize_predictions")

@@ -261,3 +261,37 @@ def test_graphed_inference_mask_only_matches_predict():
             out2 = g2.run(batch)
             assert torch.equal(out2["mask"], want)
             assert torch.equal(out2["logits"], model.engine().infer(model._state_tensors(), batch, torch.float32))
+
+
+def test_batch_256_graph_replay_matches_per_image_calls_and_oracle():
+    """BASELINE.json configs[1] shape: B=256 at 320x240 through engine.GraphedInference(splits=2) -- the call bench.py times (two
+    concurrent 128-image sub-batches inside one CUDA graph; >= 8 tiles per SM in the early layers, i.e. the per-warp epilogue mode
+    and resident-weight GEMM paths that small batches never reach).  Every image must carry the same bits as a batch-1 call, and
+    eight images spread over both sub-batches are held to the oracle."""
+    from mtg_card_image_segmentation_b200.engine import GraphedInference
+    xs, ms = O.synthetic_cards(64, seed=2024)
+    sd = O.calibrate_running_stats(O.make_weights(31), xs[:8])
+    order = torch.randperm(256, generator=torch.Generator().manual_seed(1)) % 64
+    x256 = xs[order].contiguous().cuda()
+    model = _model(sd)
+    with torch.no_grad():
+        gi = GraphedInference(model, torch.zeros_like(x256), logits_dtype=torch.float32, want_mask=True, splits=2)
+        out = gi.run(x256)
+        torch.cuda.synchronize()
+        z256, mask256 = out["logits"], out["mask"]
+        picks = [0, 37, 69, 127, 128, 191, 200, 255]
+        for i in picks:
+            single = model.predict(x256[i:i + 1], want_logits=True)
+            assert torch.equal(single["logits"][0], z256[i]), f"image {i}: batch-256 replay differs from a batch-1 call"
+            assert torch.equal(single["mask"][0], mask256[i])
+        assert torch.equal(mask256.bool(), z256[:, 1] > z256[:, 0])
+        # duplicates of one card (the batch tiles 64 cards) are bit-identical wherever they sit in the batch
+        first_of = {}
+        for pos, card in enumerate(order.tolist()):
+            if card in first_of:
+                assert torch.equal(z256[pos], z256[first_of[card]])
+            else:
+                first_of[card] = pos
+        xp = xs[order[picks]]
+        ref = O.forward(sd, xp)
+    _check_three_levels("B=256 replay, 8 spread images", z256[picks].cpu(), sd, xp, ref)

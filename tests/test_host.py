@@ -97,6 +97,54 @@ def test_export_composite_forward_matches_oracle():
     assert str(traced.inlined_graph).count("aten::_convolution") == 66
 
 
+def _onnx_graph(model, x):
+    """The opset-11 ONNX graph torch.onnx.export(model, x, opset_version=11, do_constant_folding=True, input_names=['input'],
+    output_names=['output']) builds (train/export.py:68-79), taken from the TorchScript exporter right before serialisation
+    (writing the file needs the `onnx` wheel, absent here; building the graph does not)."""
+    from torch.onnx._internal.torchscript_exporter import utils as TU
+    from torch.onnx._internal.torchscript_exporter._globals import GLOBALS
+    GLOBALS.export_onnx_opset_version = 11
+    with TU.exporter_context(model, torch.onnx.TrainingMode.EVAL, False):
+        graph, params, _ = TU._model_to_graph(model, (x,), do_constant_folding=True, input_names=["input"], output_names=["output"])
+    hist = {}
+    for n in graph.nodes():
+        hist[n.kind()] = hist.get(n.kind(), 0) + 1
+    return graph, params, hist
+
+
+def test_onnx_export_graph_histogram():
+    """a15 / f2: the exported graph is the reference's -- 66 Conv (BatchNorm folded), 28 HardSigmoid, 29 Mul, 20 Relu, 11 Add,
+    9 GlobalAveragePool, 2 Resize, 1 Sigmoid, 131 initialisers, tensors named 'input' / 'output' (SURVEY.md §3E)."""
+    import warnings
+    m = M.create_model(2, False).eval()
+    x = torch.randn(1, 3, 320, 240)  # export.py:62-66: dummy input at Config resolution
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        graph, params, hist = _onnx_graph(m, x)
+    want = {"onnx::Conv": 66, "onnx::HardSigmoid": 28, "onnx::Mul": 29, "onnx::Relu": 20, "onnx::Add": 11,
+            "onnx::GlobalAveragePool": 9, "onnx::Resize": 2, "onnx::Sigmoid": 1}
+    assert {k: hist.get(k, 0) for k in want} == want, hist
+    assert "onnx::BatchNormalization" not in hist
+    assert len(params) == 131
+    assert [i.debugName() for i in graph.inputs()][0] == "input" and [o.debugName() for o in graph.outputs()] == ["output"]
+    # initialisers carry the reference's parameter names (what the demo's ORT session and onnx_fp16_converter.py see)
+    assert "model.classifier.cbr.0.weight" not in params  # folded with its BatchNorm into an anonymous Conv weight
+    assert "model.classifier.low_classifier.weight" in params and "model.backbone.4.block.2.fc1.bias" in params
+    resize = [n for n in graph.nodes() if n.kind() == "onnx::Resize"]
+    for n in resize:  # opset-11 Resize: 'half_pixel' is the default coordinate_transformation_mode and is omitted when it applies
+        assert n.s("mode") == "linear"
+        assert "coordinate_transformation_mode" not in n.attributeNames() or n.s("coordinate_transformation_mode") == "half_pixel"
+    if has_reference():  # node for node the same op sequence as the unmodified reference's export
+        from oracle import ref_loader as R
+        ref = R.load_reference(("model",))["model"].create_model(2, pretrained=False).eval()
+        R.unload()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rgraph, rparams, rhist = _onnx_graph(ref, x)
+        assert rhist == hist and len(rparams) == len(params)
+        assert [n.kind() for n in rgraph.nodes()] == [n.kind() for n in graph.nodes()]
+
+
 def test_repo_layout_rules():
     """Only tests/, bench.py and __graft_entry__.py may touch oracle/; the product never does."""
     pkg = os.path.join(ROOT, "mtg_card_image_segmentation_b200")
