@@ -173,7 +173,9 @@ int mtgseg_bn_train_fwd(const void* z, void* y, const void* residual, const floa
   a.z = static_cast<const bf16*>(z); a.y = static_cast<bf16*>(y); a.residual = static_cast<const bf16*>(residual);
   a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum; a.running_mean = running_mean; a.running_var = running_var;
   a.num_batches_tracked = reinterpret_cast<long long*>(num_batches_tracked);
-  a.scale = scale; a.shift = shift; a.save_mean = save_mean; a.save_rstd = save_rstd; a.partial = scratch;
+  a.scale = scale; a.shift = shift; a.save_mean = save_mean; a.save_rstd = save_rstd;
+  a.stat = reinterpret_cast<double*>(scratch); a.stats_done = false;  // scratch (8-byte aligned) holds the fp64 accumulators
+  MTG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7) == 0, MTG_ERR_ARG, "bn_train_fwd: scratch must be 8-byte aligned");
   a.gap = gap; a.gap_chunks = gap_chunks; a.act = act; a.B = B; a.HW = HW; a.C = C;
   return launch_bn_train_fwd(a, S(stream));
 }
@@ -184,8 +186,8 @@ int mtgseg_bn_train_bwd(const void* z, const void* dy, void* dz, const float* sc
   BnTrainBwdArgs a;
   a.z = static_cast<const bf16*>(z); a.dy = static_cast<const bf16*>(dy); a.dz = static_cast<bf16*>(dz);
   a.scale = scale; a.shift = shift; a.save_mean = save_mean; a.save_rstd = save_rstd; a.se_s = se_s; a.se_dmean = se_dmean;
-  a.partial = scratch; a.dgamma = dgamma; a.dbeta = dbeta;
-  a.c1 = scratch + bn_partial_floats(B, HW, C); a.c2 = a.c1 + C;  // scratch holds bn_scratch_floats + 2*C floats
+  MTG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7) == 0, MTG_ERR_ARG, "bn_train_bwd: scratch must be 8-byte aligned");
+  a.bstat = reinterpret_cast<double*>(scratch); a.bstat_zeroed = false; a.dgamma = dgamma; a.dbeta = dbeta;
   a.act = act; a.B = B; a.HW = HW; a.C = C;
   return launch_bn_train_bwd(a, S(stream));
 }

@@ -7,7 +7,12 @@
 //            reduce: sum dyh, sum dyh*xhat -> dbeta, dgamma ;  dz = scale*(dyh - mean(dyh) - xhat*mean(dyh*xhat))
 // Semantics: nn.BatchNorm2d in train mode (tv:models/mobilenetv3.py:155 eps 1e-3 / momentum 1e-2 for the backbone,
 // train/model.py:111 defaults for the head), nn.Hardswish / nn.ReLU derivatives as in SURVEY.md App. B.
-// All reductions are two-stage (per-CTA partials in fixed order, then a tiny finalize kernel): deterministic.
+// Statistics are per-channel fp64 accumulators ([2][C]: sum, sum of squares; or sum dyh, sum dyh*xhat): CTAs reduce their rows
+// in fixed order in fp32 and add ONE fp64 atomic per channel (the producing conv kernels do the same from their epilogues, so a
+// layer needs no statistics pass at all).  There is no finalize launch: every CTA of the elementwise pass derives scale / shift
+// (or the two backward means) for its own channels from the accumulators; the CTA (chunk 0, image 0) of every channel group
+// also writes the saved statistics, the running-stat EMA and dgamma / dbeta.  (fp64 sums of fp32 partials of similar magnitude
+// are exact, so the result does not depend on the order in which the atomics land.)
 #include "ops.h"
 
 namespace mtgseg {
@@ -72,13 +77,34 @@ __device__ __forceinline__ void block_reduce_store(const Geo& g, const Lane& l, 
   }
 }
 
+// same reduction, result ADDED to the fp64 accumulators dst[k * C + c]
+template <int K>
+__device__ __forceinline__ void block_reduce_atomic(const Geo& g, const Lane& l, float (&vals)[K][8], float* red, double* dst) {
+  const int cw = g.CVc * 8;
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();
+    if (l.pl < g.PL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(l.pl * g.CVc + l.vl) * 8 + j] = l.active ? vals[k][j] : 0.f;
+    }
+    __syncthreads();
+    for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < g.C) {
+        float s = 0.f;
+        for (int r = 0; r < g.PL; ++r) s += red[r * cw + cl];
+        atomicAdd(dst + static_cast<size_t>(k) * g.C + c, static_cast<double>(s));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-// grid (chunks, groups, ceil(B / ipc)): partial[((zb*chunks + chunk)*2 + {0,1})*C + c] = sum z, sum z^2 over the chunk's rows of
-// the CTA's ipc images.  ipc bounds the number of partial slots: the finalize kernel has one warp per channel walking all slots,
-// and with one slot per (image, chunk) it took 38 us per layer at B = 256 (8192 slots on the 160x120 layers).
-__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ z, float* __restrict__ partial, const Geo g) {
+// grid (chunks, groups, ceil(B / ipc)): stat[c] += sum z, stat[C + c] += sum z^2 over the chunk's rows of the CTA's ipc images.
+// Only for layers whose producer does not deliver the statistics from its epilogue (the stem, the per-op ABI entry).
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ z, double* __restrict__ stat, const Geo g) {
   __shared__ float red[256 * 8];
   const Lane l = lane_of(g);
   const int chunk = blockIdx.x;
@@ -98,71 +124,63 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
       }
     }
   }
-  const size_t slot = (static_cast<size_t>(blockIdx.z) * g.chunks + chunk) * 2;
-  float* const dst[2] = {partial + slot * g.C, partial + (slot + 1) * g.C};
-  block_reduce_store<2>(g, l, acc, red, dst, 0);
-}
-
-struct BnFinP {
-  const float* partial; int slots;  // slots = ceil(B/ipc)*chunks ; layout [slot][2][C]
-  double count;                     // B*HW
-  const float* gamma; const float* beta; float eps, momentum;
-  float* running_mean; float* running_var; long long* num_batches_tracked;
-  float* scale; float* shift; float* save_mean; float* save_rstd;
-  int C;
-};
-// one warp per channel: lanes stride over the (image, chunk) partial slots, fp64 shuffle reduction (fixed order).
-// Kept as its own launch (C/8 CTAs): folding it into the statistics kernel as "the last CTA of a channel group finalizes"
-// was measured and rejected: one CTA then reduces up to 128 channels x B*chunks slots alone (B=32 step 9.67 -> 11.04 ms).
-__device__ __forceinline__ void warp_sum2(double& a, double& b) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
-}
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinP p) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (c == 0 && lane == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
-  if (c >= p.C) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = lane; k < p.slots; k += 32) {
-    s += p.partial[(static_cast<size_t>(k) * 2) * p.C + c];
-    ss += p.partial[(static_cast<size_t>(k) * 2 + 1) * p.C + c];
-  }
-  warp_sum2(s, ss);
-  if (lane != 0) return;
-  const double mean = s / p.count;
-  double var = ss / p.count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
-  const float sc = p.gamma[c] * rstd;
-  p.scale[c] = sc;
-  p.shift[c] = p.beta[c] - static_cast<float>(mean) * sc;
-  p.save_mean[c] = static_cast<float>(mean);
-  p.save_rstd[c] = rstd;
-  if (p.running_mean) {
-    const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
-    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * static_cast<float>(mean);
-    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * static_cast<float>(unbiased);
-  }
+  block_reduce_atomic<2>(g, l, acc, red, stat);
 }
 
 struct BnApplyP {
-  const bf16* z; const float* scale; const float* shift; int act; const bf16* residual; bf16* y; float* gap;
+  const bf16* z; int act; const bf16* residual; bf16* y; float* gap;
+  // finalize (folded in): batch statistics -> scale / shift for this CTA's channels; the CTA (chunk 0, image 0) of every channel
+  // group also saves them and updates the running statistics
+  const double* stat; double count;
+  const float* gamma; const float* beta; float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float* scale; float* shift; float* save_mean; float* save_rstd;
 };
 // grid (chunks, groups, B)
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const Geo g) {
   __shared__ float red[256 * 8];
+  __shared__ float s_sc[128], s_sh[128];
   const Lane l = lane_of(g);
   const int n = blockIdx.z, chunk = blockIdx.x;
+  const bool writer = chunk == 0 && n == 0;
+  if (writer && blockIdx.y == 0 && threadIdx.x == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+  // scale / shift of this CTA's channels: ONE thread per channel does the fp64 arithmetic (the fp64 issue rate is 1/64 of
+  // fp32 here: done by every thread for its 8 channels it cost more than the whole streaming loop of a small layer)
+  {
+    const int cw = g.CVc * 8;
+    for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < g.C) {
+        const double mean = p.stat[c] / p.count;
+        double var = p.stat[g.C + c] / p.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+        const float sc = __ldg(p.gamma + c) * rstd;
+        const float sh = __ldg(p.beta + c) - static_cast<float>(mean) * sc;
+        s_sc[cl] = sc;
+        s_sh[cl] = sh;
+        if (writer) {
+          p.scale[c] = sc;
+          p.shift[c] = sh;
+          p.save_mean[c] = static_cast<float>(mean);
+          p.save_rstd[c] = rstd;
+          if (p.running_mean) {
+            const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
+            p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * static_cast<float>(mean);
+            p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * static_cast<float>(unbiased);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
   float gsum[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) gsum[0][j] = 0.f;
   if (l.active) {
     float sc[8], sh[8];
-    load8f(p.scale + l.c0, sc);
-    load8f(p.shift + l.c0, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = s_sc[l.vl * 8 + j]; sh[j] = s_sh[l.vl * 8 + j]; }
     const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
     const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
     // kRowsInFlight independent 16-byte loads per thread before the first use: the loop is latency bound otherwise (the store
@@ -217,8 +235,8 @@ struct BnBwdP {
   const float* mean; const float* rstd;     // saved batch statistics
   int act;
   const float* se_s; const float* se_dmean; float inv_hw;  // optional: dy' = dy*se_s[n,c] + se_dmean[n,c]*inv_hw
-  const float* c1; const float* c2;         // (apply) mean(dyh), mean(dyh*xhat)
-  float* partial;                           // (reduce) [slot][2][C]
+  double* bstat; double count;              // [2][C]: sum dyh, sum dyh*xhat (reduce adds, apply reads)
+  float* dgamma; float* dbeta;              // (apply, designated CTA) = the two sums
   bf16* dz;                                 // (apply)
 };
 
@@ -239,8 +257,23 @@ __device__ __forceinline__ void bwd_terms(const BnBwdP& p, const uint4& zq, cons
 template <bool kApply>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g) {
   __shared__ float red[256 * 8];
+  __shared__ float s_c1[kApply ? 128 : 1], s_c2[kApply ? 128 : 1];
   const Lane l = lane_of(g);
   const int chunk = blockIdx.x;
+  if (kApply) {  // mean(dyh), mean(dyh*xhat) of this CTA's channels: one thread per channel does the fp64 part (see bn_apply_kernel)
+    const int cw = g.CVc * 8;
+    const bool writer = chunk == 0 && blockIdx.z == 0;
+    for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
+      const int c = blockIdx.y * cw + cl;
+      if (c < g.C) {
+        const double s = p.bstat[c], sx = p.bstat[g.C + c];
+        s_c1[cl] = static_cast<float>(s / p.count);
+        s_c2[cl] = static_cast<float>(sx / p.count);
+        if (writer) { p.dbeta[c] = static_cast<float>(s); p.dgamma[c] = static_cast<float>(sx); }
+      }
+    }
+    __syncthreads();
+  }
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
@@ -249,9 +282,12 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g
     load8f(p.scale + l.c0, sc); load8f(p.shift + l.c0, sh); load8f(p.mean + l.c0, mu); load8f(p.rstd + l.c0, rs);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ses[j] = 1.f; sed[j] = 0.f; c1[j] = c2[j] = 0.f; }
-    if (kApply) { load8f(p.c1 + l.c0, c1); load8f(p.c2 + l.c0, c2); }
+    if (kApply) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c1[j] = s_c1[l.vl * 8 + j]; c2[j] = s_c2[l.vl * 8 + j]; }
+    }
     const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
-    const int n0 = blockIdx.z * g.ipc, n1 = min(g.B, n0 + g.ipc);  // the reduce pass walks ipc images (see bn_stats_kernel)
+    const int n0 = blockIdx.z * g.ipc, n1 = min(g.B, n0 + g.ipc);  // the reduce pass walks ipc images per CTA (fewer atomics)
     for (int n = n0; n < n1; ++n) {
       if (p.se_s) {
         load8f(p.se_s + static_cast<size_t>(n) * g.C + l.c0, ses);
@@ -288,30 +324,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g
       }
     }
   }
-  if (!kApply) {
-    const size_t slot = (static_cast<size_t>(blockIdx.z) * g.chunks + chunk) * 2;
-    float* const dst[2] = {p.partial + slot * g.C, p.partial + (slot + 1) * g.C};
-    block_reduce_store<2>(g, l, acc, red, dst, 0);
-  }
-}
-
-// dbeta = sum dyh ; dgamma = sum dyh*xhat ; c1 = dbeta/count ; c2 = dgamma/count
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int slots, double count,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              float* __restrict__ c1, float* __restrict__ c2, int C) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int k = lane; k < slots; k += 32) {
-    s += partial[(static_cast<size_t>(k) * 2) * C + c];
-    sx += partial[(static_cast<size_t>(k) * 2 + 1) * C + c];
-  }
-  warp_sum2(s, sx);
-  if (lane != 0) return;
-  dbeta[c] = static_cast<float>(s);
-  dgamma[c] = static_cast<float>(sx);
-  c1[c] = static_cast<float>(s / count);
-  c2[c] = static_cast<float>(sx / count);
+  if (!kApply) block_reduce_atomic<2>(g, l, acc, red, p.bstat);
 }
 
 Geo make_geo(int C, int HW, int want_chunks, int B) {
@@ -322,7 +335,7 @@ Geo make_geo(int C, int HW, int want_chunks, int B) {
   g.B = B; g.ipc = 1;
   return g;
 }
-// the reducing passes: at most ~512 partial slots per channel
+// the reducing passes: at most ~512 CTAs (= fp64 atomics) per channel
 Geo reducing_geo(Geo g) {
   g.ipc = ceil_div(g.B * g.chunks, 512);
   return g;
@@ -330,7 +343,7 @@ Geo reducing_geo(Geo g) {
 
 }  // namespace
 
-// chunks per image for the BN kernels: ~16 rows per thread, at most 32 per image (bounds the partial buffers)
+// chunks per image for the BN kernels: ~16 rows per thread, at most 32 per image
 int bn_chunks(int HW, int C) {
   const int PL = 256 / group_vectors(C / 8);
   int ch = ceil_div(HW, PL * 16);
@@ -338,44 +351,42 @@ int bn_chunks(int HW, int C) {
   if (ch < 1) ch = 1;
   return ch;
 }
-size_t bn_partial_floats(int B, int HW, int C) { return static_cast<size_t>(B) * bn_chunks(HW, C) * 2 * C; }
+size_t bn_partial_floats(int B, int HW, int C) { (void)B; (void)HW; return static_cast<size_t>(8) * C; }  // 2 x [2][C] fp64 accumulators
 
 int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
-  MTG_REQUIRE(a.z && a.y && a.gamma && a.beta && a.scale && a.shift && a.save_mean && a.save_rstd && a.partial, MTG_ERR_ARG,
+  MTG_REQUIRE(a.z && a.y && a.gamma && a.beta && a.scale && a.shift && a.save_mean && a.save_rstd && a.stat, MTG_ERR_ARG,
               "bn_train_fwd: null pointer");
   MTG_REQUIRE(a.C % 8 == 0, MTG_ERR_UNSUPPORTED, "bn_train_fwd: C %% 8 != 0");
   const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C), a.B), gr = reducing_geo(g);
   dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
-  const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
-  bn_stats_kernel<<<rgrid, 256, 0, st>>>(a.z, a.partial, gr);
-  MTG_LAUNCH_CHECK();
-  BnFinP f{a.partial, static_cast<int>(rgrid.z) * g.chunks, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
-           a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd, a.C};
-  bn_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(f);
-  MTG_LAUNCH_CHECK();
+  if (!a.stats_done) {  // the producer did not accumulate the statistics from its epilogue
+    MTG_CUDA(cudaMemsetAsync(a.stat, 0, sizeof(double) * 2 * a.C, st));
+    const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
+    bn_stats_kernel<<<rgrid, 256, 0, st>>>(a.z, a.stat, gr);
+    MTG_LAUNCH_CHECK();
+  }
   Geo ga = g;
   if (a.gap) {  // the SE pool wants few partials per image
     ga = make_geo(a.C, a.HW, a.gap_chunks, a.B);
     grid = dim3(ga.chunks, ceil_div(ga.CV, ga.CVc), a.B);
   }
-  BnApplyP ap{a.z, a.scale, a.shift, a.act, a.residual, a.y, a.gap};
+  BnApplyP ap{a.z, a.act, a.residual, a.y, a.gap, a.stat, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
+              a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd};
   bn_apply_kernel<<<grid, 256, 0, st>>>(ap, ga);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
 
 int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st) {
-  MTG_REQUIRE(a.z && a.dy && a.dz && a.scale && a.shift && a.save_mean && a.save_rstd && a.partial && a.dgamma && a.dbeta &&
-                  a.c1 && a.c2, MTG_ERR_ARG, "bn_train_bwd: null pointer");
+  MTG_REQUIRE(a.z && a.dy && a.dz && a.scale && a.shift && a.save_mean && a.save_rstd && a.bstat && a.dgamma && a.dbeta, MTG_ERR_ARG,
+              "bn_train_bwd: null pointer");
   const Geo g = make_geo(a.C, a.HW, bn_chunks(a.HW, a.C), a.B), gr = reducing_geo(g);
   dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
   const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
   BnBwdP p{a.z, a.dy, a.scale, a.shift, a.save_mean, a.save_rstd, a.act, a.se_s, a.se_dmean, 1.f / static_cast<float>(a.HW),
-           a.c1, a.c2, a.partial, a.dz};
+           a.bstat, static_cast<double>(a.B) * a.HW, a.dgamma, a.dbeta, a.dz};
+  if (!a.bstat_zeroed) MTG_CUDA(cudaMemsetAsync(a.bstat, 0, sizeof(double) * 2 * a.C, st));
   bn_bwd_kernel<false><<<rgrid, 256, 0, st>>>(p, gr);
-  MTG_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(a.C, 8), 256, 0, st>>>(a.partial, static_cast<int>(rgrid.z) * g.chunks, static_cast<double>(a.B) * a.HW, a.dgamma,
-                                                             a.dbeta, a.c1, a.c2, a.C);
   MTG_LAUNCH_CHECK();
   bn_bwd_kernel<true><<<grid, 256, 0, st>>>(p, g);
   MTG_LAUNCH_CHECK();

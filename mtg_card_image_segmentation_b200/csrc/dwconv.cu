@@ -146,6 +146,7 @@ struct DwS {
   int act, H, W, C, Ho, Wo, pad, CV, CVc, PL, strips, band, bands, R, Wp;
   int xoff;  // offset of the input tile inside the dynamic buffer, in uint4 (weights first, padded to 128 bytes for TMA)
   int dbg;   // MTGSEG_DW_PHASE (timing experiments only): 1 = fill phase only, 2 = compute phase only (reads an unfilled tile)
+  double* stat;  // training (kernels instantiated with ST): [2][C] fp64, += per-channel sum / sum of squares of the stored outputs
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
@@ -176,7 +177,9 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const float (&x)[8], const
 // TMA: phase 1 is ONE 4-D box load of the band's input rows (out-of-bounds rows / columns / channels are zero filled by
 // the TMA unit = the convolution padding) plus one 2-D box load of the weights, issued by thread 0 and awaited on an
 // mbarrier; no per-thread address arithmetic.  !TMA: the same tile gathered with 16-byte cp.async (kept for A/B).
-template <int KS, int STRIDE, int DIL, int TW, bool TMA, bool F2>
+// ST: training variant -- instead of the SE pool partials the epilogue accumulates the BatchNorm statistics (sum, sum of squares
+// of the bf16-rounded outputs) and adds them to p.stat with one fp64 atomic per channel and CTA.
+template <int KS, int STRIDE, int DIL, int TW, bool TMA, bool F2, bool ST = false>
 __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                                                               const DwS p) {
   extern __shared__ __align__(128) uint4 dsm[];
@@ -231,9 +234,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
   const int vl = tid % p.CVc, pl = tid / p.CVc;
   const bool active = pl < p.PL && vl < nv;
   const int c0 = (v0 + (active ? vl : 0)) * 8;
-  float acc_gap[8];
+  float acc_gap[8], acc_sq[ST ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc_gap[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < (ST ? 8 : 1); ++j) acc_sq[j] = 0.f;
   if (active) {
     float sc[8], sh[8];
     {
@@ -279,7 +284,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
             for (int j = 0; j < 8; ++j) o[j] = actf(fmaf(acc[t][j], sc[j], sh[j]));
             const uint4 packed = pack8(o);
             *reinterpret_cast<uint4*>(out_n + (static_cast<size_t>(oy0 + ry) * p.Wo + ox0 + t) * p.C) = packed;
-            if (p.gap) {
+            if (ST) {
+              float rf[8];
+              unpack8(packed, rf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { acc_gap[j] += rf[j]; acc_sq[j] = fmaf(rf[j], rf[j], acc_sq[j]); }
+            } else if (p.gap) {
               float rf[8];
               unpack8(packed, rf);
 #pragma unroll
@@ -294,7 +304,26 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
       else finish([&](float v) { return apply_act(v, p.act); });
     }
   }
-  if (p.gap) {
+  if (ST) {
+    const int cw = p.CVc * 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      __syncthreads();  // (k = 0: every thread is done with the staged tile: its first 8 KB become the reduction buffer)
+      if (pl < p.PL) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(pl * p.CVc + vl) * 8 + j] = active ? (k == 0 ? acc_gap[j] : acc_sq[j]) : 0.f;
+      }
+      __syncthreads();
+      for (int cl = tid; cl < cw; cl += blockDim.x) {
+        const int c = blockIdx.y * cw + cl;
+        if (c < p.C) {
+          float s = 0.f;
+          for (int l = 0; l < p.PL; ++l) s += red[l * cw + cl];
+          atomicAdd(p.stat + k * p.C + c, static_cast<double>(s));
+        }
+      }
+    }
+  } else if (p.gap) {
     const int cw = p.CVc * 8;
     __syncthreads();  // every thread is done with the staged tile: its first 8 KB become the reduction buffer
     if (pl < p.PL) {
@@ -321,7 +350,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
 // (the 8-channel kernel sits where shared-memory bandwidth and issue bandwidth meet; 8 pixels x 8 channels spills).
 // Same tile layout and TMA fill as dwconv_smem_kernel; the plan is made with TW = 8.
 // ---------------------------------------------------------------------------------------------------------
-template <int KS, int DIL>
+template <int KS, int DIL, bool ST = false>
 __global__ void __launch_bounds__(256, 2) dwconv_half_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                                                               const DwS p) {
   constexpr int TW = 8, NI = (TW - 1) + (KS - 1) * DIL + 1;
@@ -350,7 +379,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_half_kernel(const __grid_consta
   const int vl = tid % HV, pl = tid / HV;
   const bool active = pl < PLh && vl < nvh;
   const int c0 = v0 * 8 + (active ? vl : 0) * 4;
-  float acc_gap[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc_gap[4] = {0.f, 0.f, 0.f, 0.f}, acc_sq[4] = {0.f, 0.f, 0.f, 0.f};
   // one bf16x2 word -> (even channel, odd channel) as packed fp32x2
   auto widen = [](uint32_t w) {
     uint64_t r;
@@ -403,9 +432,14 @@ __global__ void __launch_bounds__(256, 2) dwconv_half_kernel(const __grid_consta
             for (int j = 0; j < 4; ++j) o[j] = actf(fmaf(a[j], sc[j], sh[j]));
             const uint2 packed = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
             *reinterpret_cast<uint2*>(out_n + (static_cast<size_t>(oy0 + ry) * p.Wo + ox0 + t) * p.C) = packed;
-            if (p.gap) {
-              acc_gap[0] += __uint_as_float(packed.x << 16); acc_gap[1] += __uint_as_float(packed.x & 0xFFFF0000u);
-              acc_gap[2] += __uint_as_float(packed.y << 16); acc_gap[3] += __uint_as_float(packed.y & 0xFFFF0000u);
+            if (ST || p.gap) {
+              const float r[4] = {__uint_as_float(packed.x << 16), __uint_as_float(packed.x & 0xFFFF0000u),
+                                  __uint_as_float(packed.y << 16), __uint_as_float(packed.y & 0xFFFF0000u)};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc_gap[j] += r[j];
+                if (ST) acc_sq[j] = fmaf(r[j], r[j], acc_sq[j]);
+              }
             }
           }
         }
@@ -416,7 +450,26 @@ __global__ void __launch_bounds__(256, 2) dwconv_half_kernel(const __grid_consta
       else finish([&](float v) { return apply_act(v, p.act); });
     }
   }
-  if (p.gap) {
+  if (ST) {
+    const int cw = p.CVc * 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      __syncthreads();
+      if (pl < PLh) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[(pl * HV + vl) * 4 + j] = active ? (k == 0 ? acc_gap[j] : acc_sq[j]) : 0.f;
+      }
+      __syncthreads();
+      for (int cl = tid; cl < cw; cl += blockDim.x) {
+        const int c = blockIdx.y * cw + cl;
+        if (c < p.C) {
+          float s = 0.f;
+          for (int l = 0; l < PLh; ++l) s += red[l * cw + cl];
+          atomicAdd(p.stat + k * p.C + c, static_cast<double>(s));
+        }
+      }
+    }
+  } else if (p.gap) {
     const int cw = p.CVc * 8;
     __syncthreads();  // every thread is done with the staged tile: its first bytes become the reduction buffer (PLh * cw floats <= 4 KB)
     if (pl < PLh) {
@@ -530,14 +583,14 @@ int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap
   return dw_plan(H, W, C, k, stride, dil, need_gap).bands;
 }
 
-template <int KS, int STRIDE, int DIL, int TW, bool TMA, bool F2>
+template <int KS, int STRIDE, int DIL, int TW, bool TMA, bool F2, bool ST = false>
 int launch_smem2(const CUtensorMap& tmx, const CUtensorMap& tmw, const DwS& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    MTG_CUDA(cudaFuncSetAttribute(dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    MTG_CUDA(cudaFuncSetAttribute(dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2><<<grid, 256, smem, st>>>(tmx, tmw, p);
+  dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2, ST><<<grid, 256, smem, st>>>(tmx, tmw, p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -561,6 +614,10 @@ int launch_smem(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaS
     const unsigned wb[2] = {static_cast<unsigned>(p.CVc * 8), static_cast<unsigned>(KS * KS)};
     rc = make_tma_map_bf16(&tmw, a.w, 2, wd, ws, wb, 0);
     if (rc != MTG_OK) return rc;
+  }
+  if (p.stat) {
+    MTG_REQUIRE(v == 0 || v == 7, MTG_ERR_UNSUPPORTED, "dwconv: BatchNorm statistics need the default kernel variant (MTGSEG_DW_VARIANT=0)");
+    return launch_smem2<KS, STRIDE, DIL, TW, true, true, true>(tmx, tmw, p, grid, smem, st);
   }
   switch (v) {
     case 0: case 7: return launch_smem2<KS, STRIDE, DIL, TW, true, true>(tmx, tmw, p, grid, smem, st);
@@ -588,9 +645,11 @@ int launch_half(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaS
   static bool configured = false;
   if (!configured) {
     MTG_CUDA(cudaFuncSetAttribute(dwconv_half_kernel<KS, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    MTG_CUDA(cudaFuncSetAttribute(dwconv_half_kernel<KS, DIL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  dwconv_half_kernel<KS, DIL><<<grid, 256, smem, st>>>(tmx, tmw, p);
+  if (p.stat) dwconv_half_kernel<KS, DIL, true><<<grid, 256, smem, st>>>(tmx, tmw, p);
+  else dwconv_half_kernel<KS, DIL><<<grid, 256, smem, st>>>(tmx, tmw, p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -602,8 +661,9 @@ int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
     const DwPlan q = dw_plan(a.H, a.W, a.C, a.k, a.stride, a.dil, a.gap_partial != nullptr);
     MTG_REQUIRE(q.ok, MTG_ERR_UNSUPPORTED, "dwconv: feature map %dx%d (C=%d, k=%d) does not fit the shared-memory tiling", a.H, a.W, a.C, a.k);
     MTG_REQUIRE(!a.gap_partial || a.chunks == q.bands, MTG_ERR_ARG, "dwconv: gap_partial must have mtgseg_dwconv_chunks() = %d chunks, got %d", q.bands, a.chunks);
+    MTG_REQUIRE(!(a.stat && a.gap_partial), MTG_ERR_ARG, "dwconv: statistics and pool partials are exclusive");
     DwS s{a.in, a.w, a.out, a.scale, a.shift, a.gap_partial, a.act, a.H, a.W, a.C, q.Ho, q.Wo, q.pad, q.CV, q.CVc, q.PL, q.strips,
-          q.band, q.bands, q.R, q.Wp, q.xoff, dw_phase()};
+          q.band, q.bands, q.R, q.Wp, q.xoff, dw_phase(), a.stat};
     dim3 grid(q.bands, ceil_div(q.CV, q.CVc), a.B);
     switch (a.k * 100 + a.stride * 10 + a.dil) {
       case 311: return launch_smem<3, 1, 1, 4>(a, s, grid, q.smem, st);
@@ -615,6 +675,7 @@ int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
         MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: (k=%d, stride=%d, dilation=%d) is not one of the MobileNetV3 shapes", a.k, a.stride, a.dil);
     }
   }
+  MTG_REQUIRE(!a.stat, MTG_ERR_UNSUPPORTED, "dwconv: BatchNorm statistics need the default kernel variant (MTGSEG_DW_VARIANT=0)");
   DwP p{};
   p.in = a.in; p.w = a.w; p.out = a.out; p.scale = a.scale; p.shift = a.shift; p.gap = a.gap_partial; p.act = a.act;
   p.H = a.H; p.W = a.W; p.C = a.C;

@@ -38,7 +38,7 @@ constexpr int BM = 128;           // UMMA M
 constexpr int MAX_STAGES = 8;
 constexpr int BAR_BYTES = 320;               // mbarriers + TMEM slot
 constexpr int OUT_BUFS = 2;                  // double-buffered output staging
-constexpr int SS_BYTES = 2 * 256 * 4;        // scale / shift of the current N tile
+constexpr int SS_BYTES = 2 * 256 * 4;        // scale / shift of the current N tile (+ as much again for the BatchNorm statistics)
 
 struct GemmKParams {
   int M, N, K;
@@ -65,6 +65,10 @@ struct GemmKParams {
   // multi-tap (3x3 / transposed-conv parity) geometry: A boxes {64 ch, W, HB rows, NB images} shifted by (dx, dy) per tap
   int B, H, W, HB, NB, h_tiles;
   signed char tap_dy[9], tap_dx[9];
+  // training: per-channel sum / sum of squares of the (bf16-rounded) outputs, accumulated per CTA in shared memory and added to
+  // stat[0..N) / stat[N..2N) with fp64 atomics when the CTA retires: the BatchNorm statistics come out of the conv epilogue
+  double* stat;
+  int ss_bytes;  // SS_BYTES, doubled when stat != nullptr
 };
 
 // acc[0..7] = x[0..7] * w[0..7] + acc[0..7] as four packed fp32x2 FMAs (FFMA2)
@@ -100,7 +104,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sRes = sOut + p.out_bytes;                  // res_bufs x res_slabs slabs
   float* sScale = reinterpret_cast<float*>(sRes + p.res_bufs * p.res_slabs * SLAB_BYTES);
   float* sShift = sScale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + SS_BYTES);
+  // (only when p.stat) per-CTA BatchNorm partial sums: one slot per (row group, column), each owned by exactly one epilogue
+  // thread, so they accumulate with plain adds in a fixed order: the statistics are run-to-run deterministic
+  const int SG = 512 / p.obox;  // row groups: 128-row slab / (256 threads / column pairs) == 8 warps x row groups of a 32-row slab
+  float* sSum = sShift + 256;   // [SG][BN]
+  float* sSq = sSum + SG * p.BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sScale) + p.ss_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* xform = bars + 2 * MAX_STAGES;
@@ -301,6 +310,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else if (p.act == ACT_NONE) convert([](float z) { return z; });
       else convert([&](float z) { return apply_act(z, p.act); });
     };
+    // ---- BatchNorm statistics of a staged slab (training): column sums of the bf16 values the TMA store writes --------------
+    if (p.stat)
+      for (int i = et; i < 2 * SG * p.BN; i += 256) sSum[i] = 0.f;  // visible after the first named barrier below (both modes have one)
+    // `nthreads` consecutive threads (index ti) share a slab of `nrows` rows (box-local row index = swizzle row): a thread owns
+    // one bf16 column pair and a group of rows; lanes of a warp read one 128-byte row segment -> conflict free
+    auto slab_stats = [&](const uint8_t* sbuf, int sl, int cols, int ti, int nthreads, int nrows, int row_limit, int group_base) {
+      const int pairs = OB >> 1, groups = nthreads / pairs, rpg = nrows / groups;
+      const int cp = ti % pairs, grp = ti / pairs;
+      if (cp * 2 >= cols) return;
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      const int chunk = cp >> 2, within = (cp & 3) * 4;
+      for (int i = 0; i < rpg; ++i) {
+        const int row = grp * rpg + i;
+        if (row >= row_limit) break;
+        const int rxx = OB == 64 ? (row & 7) : (OB == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + row * opitch + ((chunk ^ rxx) << 4) + within);
+        const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xFFFF0000u);
+        s0 += a; s1 += b;
+        q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+      }
+      const int slot = (group_base + grp) * p.BN + sl * OB + cp * 2;  // this thread's own slot: no atomics
+      sSum[slot] += s0; sSum[slot + 1] += s1;
+      sSq[slot] += q0; sSq[slot + 1] += q1;
+    };
+    // all 256 epilogue threads: add this CTA's sums of N tile `n_tile` to the global fp64 accumulators, clear the local ones
+    auto flush_stats = [&](int n_tile) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et < p.BN) {
+        const int n = n_tile * p.BN + et;
+        float a = 0.f, b = 0.f;
+        for (int g = 0; g < SG; ++g) {
+          a += sSum[g * p.BN + et]; b += sSq[g * p.BN + et];
+          sSum[g * p.BN + et] = 0.f; sSq[g * p.BN + et] = 0.f;
+        }
+        if (n < p.N) {
+          atomicAdd(p.stat + n, static_cast<double>(a));
+          atomicAdd(p.stat + p.N + n, static_cast<double>(b));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     if (!kConv3x3 && p.epi_mode == 1) {
       // ---- mode 1: decoupled warps.  Set `wset` owns the tiles with (tile counter & 1) == wset and the TMEM buffer of the
       // same index, so two tiles are in their epilogue at once; each warp converts its 32 rows of every slab into its own
@@ -344,11 +394,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tma_store_2d(&tmO, sbuf, n_tile * p.BN + sl * OB, m_tile * BM + q * 32);
             ptx::bulk_commit();
           }
+          if (p.stat) slab_stats(sbuf, sl, cols, lane, 32, 32, 32, (warp - 2) * (64 / OB));  // (the next use of sbuf starts with a __syncwarp)
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty[buf]);
         if (p.res_slabs) ptx::mbar_arrive(&res_free[wset]);
       }
+      if (p.stat) flush_stats(blockIdx.x % p.n_tiles);
       if (lane == 0) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
     } else {
       // ---- mode 0: all 8 warps work on one slab at a time (4 lane quarters x 2 column halves), one leader thread stores
@@ -376,6 +428,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // bar.sync of the previous iteration)
         if (p.res_slabs && p.res_bufs == 2 && leader && tile + static_cast<int>(gridDim.x) < total_tiles) load_residual(tile + gridDim.x, rb ^ 1);
         if (n_tile != cur_ntile) {  // folded-BN constants of this N tile -> smem (visible after the first bar.sync below)
+          if (p.stat && cur_ntile >= 0) flush_stats(cur_ntile);
           cur_ntile = n_tile;
           for (int c = et; c < p.BN; c += 256) {
             const int n = n_tile * p.BN + c;
@@ -403,6 +456,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else ptx::tma_store_2d(&tmO, sbuf, c0, oc1);
             ptx::bulk_commit();
           }
+          // (the slab is reused two slabs later, behind the next slab's first barrier.)  3x3: accumulator rows beyond the TMA box
+          // were computed from stale shared memory and are never stored: they must not be counted either
+          if (p.stat) slab_stats(sbuf, sl, cols, et, 256, BM, kConv3x3 ? p.NB * p.HB * p.W : BM, 0);
         }
         // single residual buffer: every epilogue thread passed the last bar.sync after its final read of the tile (and
         // executed fence.proxy.async before it), so the buffer may be refilled now; the next mainloop hides the load
@@ -410,6 +466,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty[buf]);
       }
+      if (p.stat && cur_ntile >= 0) flush_stats(cur_ntile);
       if (leader) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
     }
   } else if (kAScale) {
@@ -619,7 +676,7 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const long long total_tiles = static_cast<long long>(kp.m_tiles) * kp.n_tiles;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = static_cast<int>(total_tiles);
-  if (kp.b_res) {  // resident weights: a CTA must keep one N tile for its whole life -> grid is a multiple of n_tiles
+  if (kp.b_res || kp.stat) {  // resident weights / per-CTA statistics: a CTA keeps one N tile for its whole life -> grid is a multiple of n_tiles
     grid = grid / kp.n_tiles * kp.n_tiles;
     if (grid < kp.n_tiles) grid = kp.n_tiles;
   }
@@ -686,11 +743,13 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   kp.ksteps_last = ceil_div(g.K - (kp.kb_per_tap - 1) * BK, 16);
   kp.scale = g.scale; kp.shift = g.shift; kp.act = g.act;
   kp.residual = g.residual; kp.out = g.out; kp.a_scale = g.a_scale; kp.hw = g.hw;
+  kp.stat = g.stat;
   int tmem = 32;
   while (tmem < 2 * kp.BN) tmem <<= 1;
   kp.tmem_cols = tmem;
 
   kp.obox = (g.conv3x3 || kp.BN > 32) ? 64 : (kp.BN > 16 ? 32 : 16);  // narrow layers stage narrow slabs: more CTAs per SM
+  kp.ss_bytes = SS_BYTES + (g.stat ? 2 * (512 / kp.obox) * kp.BN * 4 : 0);  // + [2][row groups][BN] partial sums
   kp.res_slabs = g.residual ? ceil_div(kp.BN, kp.obox) : 0;
   MTG_REQUIRE(!(g.conv3x3 && g.residual), MTG_ERR_UNSUPPORTED, "conv_gemm: residual with conv3x3 is not supported");
   // B-stationary: with few k-blocks the weights of one N tile fit in shared memory next to the A ring; every CTA then
@@ -777,7 +836,7 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   // ring depth for a given amount of output staging: enough stages that two co-resident CTAs keep >= ~64 KB of loads in
   // flight per SM (HBM latency x bandwidth); prefer two co-resident CTAs over a deeper ring when that is what it costs
   auto plan = [&](size_t out_bytes, int& stages_out, size_t& need_out) {
-    const size_t fixed = 2048 /*two 1024-byte alignments*/ + out_bytes + static_cast<size_t>(kp.res_bufs) * kp.res_slabs * slab_bytes + SS_BYTES + BAR_BYTES + b_res_bytes;
+    const size_t fixed = 2048 /*two 1024-byte alignments*/ + out_bytes + static_cast<size_t>(kp.res_bufs) * kp.res_slabs * slab_bytes + kp.ss_bytes + BAR_BYTES + b_res_bytes;
     int stages = kp.num_kb >= 8 ? 6 : 4;
     if (stage_bytes <= 16 * 1024) stages = 8;
     while (stages > 2 && stages * static_cast<size_t>(stage_bytes) + fixed > 227 * 1024) --stages;

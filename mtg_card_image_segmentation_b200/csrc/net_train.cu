@@ -32,6 +32,8 @@ struct Bump {
 struct LayerBufs {
   bf16* z = nullptr; bf16* y = nullptr;
   float* scale = nullptr; float* shift = nullptr; float* mean = nullptr; float* rstd = nullptr;
+  double* stat = nullptr;   // [2][C] sum z, sum z^2 (filled by the producing kernel's epilogue)
+  double* bstat = nullptr;  // [2][C] sum dyh, sum dyh*xhat (backward)
   int C = 0, H = 0, W = 0;  // output geometry
 };
 struct BlockBufs {
@@ -43,12 +45,12 @@ struct TrainBufs {
   LayerBufs stem, last, cbr;
   BlockBufs blk[kNumBlocks];
   float* hsum = nullptr; float* hscale = nullptr; float* lowres = nullptr;
-  float* partial = nullptr;                 // BN reduction scratch
+  uint8_t* stat_arena = nullptr; size_t stat_bytes = 0;    // all layers' forward accumulators: one memset per forward
+  uint8_t* bstat_arena = nullptr; size_t bstat_bytes = 0;  // all layers' backward accumulators: one memset per backward
   float* ones = nullptr; float* zeros = nullptr;  // [max(B*960, 960)] constants
   // backward scratch
   bf16* g[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // activation-sized gradient buffers
   bf16* dzpool[4] = {nullptr, nullptr, nullptr, nullptr};  // dz buffers: rotated so that the side-stream wgrad of one layer may still read its dz while the main stream produces the next
-  float* c1 = nullptr; float* c2 = nullptr;                    // BN backward coefficients [960]
   float* pooled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [B][16][960] / [B][960] SE backward vectors
   float* d_o = nullptr; float* dh2 = nullptr;
   int Hl = 0, Wl = 0, Hh = 0, Wh = 0;
@@ -64,15 +66,22 @@ void layout(const NetPlan& P, int B, uint8_t* ws, TrainBufs& T) {
   Bump b;
   auto bf = [&](size_t elems) { return reinterpret_cast<bf16*>(ws + b.take(elems * sizeof(bf16))); };
   auto f32 = [&](size_t elems) { return reinterpret_cast<float*>(ws + b.take(elems * sizeof(float))); };
+  // BatchNorm accumulators of all 47 layers, contiguous (<= 2 x 16 bytes x 960 channels per layer)
+  constexpr size_t kStatBytes = 47 * 2 * 960 * sizeof(double);
+  T.stat_arena = ws + b.take(kStatBytes); T.stat_bytes = kStatBytes;
+  T.bstat_arena = ws + b.take(kStatBytes); T.bstat_bytes = kStatBytes;
+  size_t stat_off = 0;
   auto layer = [&](LayerBufs& L, int C, int H, int W) {
     L.C = C; L.H = H; L.W = W;
     const size_t n = static_cast<size_t>(B) * H * W * C;
     L.z = bf(n); L.y = bf(n);
     L.scale = f32(C); L.shift = f32(C); L.mean = f32(C); L.rstd = f32(C);
+    L.stat = reinterpret_cast<double*>(T.stat_arena + stat_off);
+    L.bstat = reinterpret_cast<double*>(T.bstat_arena + stat_off);
+    stat_off += 2 * static_cast<size_t>(C) * sizeof(double);
   };
   int H = conv_out(P.desc.in_h, 3, 2, 1), W = conv_out(P.desc.in_w, 3, 2, 1);
   size_t max_act = static_cast<size_t>(B) * H * W * 16;
-  size_t max_partial = bn_partial_floats(B, H * W, 16);
   layer(T.stem, 16, H, W);
   for (int i = 0; i < kNumBlocks; ++i) {
     const BlockCfg& c = P.blocks[i].cfg;
@@ -80,13 +89,11 @@ void layout(const NetPlan& P, int B, uint8_t* ws, TrainBufs& T) {
     K.Hin = H; K.Win = W;
     if (P.blocks[i].has_expand) {
       layer(K.expand, c.cexp, H, W);
-      max_partial = max_partial > bn_partial_floats(B, H * W, c.cexp) ? max_partial : bn_partial_floats(B, H * W, c.cexp);
     }
     max_act = max_act > static_cast<size_t>(B) * H * W * c.cexp ? max_act : static_cast<size_t>(B) * H * W * c.cexp;
     const int stride = c.dil > 1 ? 1 : c.stride;
     const int Ho = conv_out(H, c.k, stride, c.dil), Wo = conv_out(W, c.k, stride, c.dil);
     layer(K.dw, c.cexp, Ho, Wo);
-    max_partial = max_partial > bn_partial_floats(B, Ho * Wo, c.cexp) ? max_partial : bn_partial_floats(B, Ho * Wo, c.cexp);
     if (c.se) {
       K.gap_chunks = bn_chunks(Ho * Wo, c.cexp);
       if (K.gap_chunks > 16) K.gap_chunks = 16;
@@ -96,24 +103,20 @@ void layout(const NetPlan& P, int B, uint8_t* ws, TrainBufs& T) {
     }
     H = Ho; W = Wo;
     layer(K.project, c.cout, H, W);
-    max_partial = max_partial > bn_partial_floats(B, H * W, c.cout) ? max_partial : bn_partial_floats(B, H * W, c.cout);
     if (i == 3) { T.Hl = H; T.Wl = W; }
   }
   T.Hh = H; T.Wh = W;
   const int ic = P.desc.inter_channels, nc = P.desc.num_classes;
   layer(T.last, 960, H, W);
   layer(T.cbr, ic, H, W);
-  max_partial = max_partial > bn_partial_floats(B, H * W, 960) ? max_partial : bn_partial_floats(B, H * W, 960);
   T.hsum = f32(static_cast<size_t>(B) * 960);
   T.hscale = f32(static_cast<size_t>(B) * ic);
   T.lowres = f32(static_cast<size_t>(B) * T.Hl * T.Wl * nc);
-  T.partial = f32(max_partial);
   T.ones = f32(static_cast<size_t>(B) * 960);
   T.zeros = f32(static_cast<size_t>(B) * 960);
   for (int k = 0; k < 5; ++k) T.g[k] = bf(max_act);
   T.dzpool[0] = T.g[1];
   for (int k = 1; k < 4; ++k) T.dzpool[k] = bf(max_act);
-  T.c1 = f32(960); T.c2 = f32(960);
   for (int k = 0; k < 5; ++k) T.pooled[k] = f32(static_cast<size_t>(B) * 16 * 960);
   T.d_o = f32(static_cast<size_t>(B) * T.Hl * T.Wl * nc);
   T.dh2 = f32(static_cast<size_t>(B) * T.Hh * T.Wh * nc);
@@ -133,13 +136,13 @@ struct Ctx {
 
 // BatchNorm forward in training mode on an already computed z
 int bn_fwd(const Ctx& c, const ConvBnPlan& cp, const LayerBufs& L, int act, const bf16* residual, float* gap, int gap_chunks,
-           float momentum) {
+           float momentum, bool stats_done = true) {
   BnTrainFwdArgs a;
   a.z = L.z; a.y = L.y; a.residual = residual;
   a.gamma = c.param(cp.gamma); a.beta = c.param(cp.beta); a.eps = cp.eps; a.momentum = momentum;
   a.running_mean = c.param(cp.mean); a.running_var = c.param(cp.var);
   a.num_batches_tracked = static_cast<long long*>(c.io.params[cp.var + 1]);
-  a.scale = L.scale; a.shift = L.shift; a.save_mean = L.mean; a.save_rstd = L.rstd; a.partial = c.T.partial;
+  a.scale = L.scale; a.shift = L.shift; a.save_mean = L.mean; a.save_rstd = L.rstd; a.stat = L.stat; a.stats_done = stats_done;
   a.gap = gap; a.gap_chunks = gap_chunks; a.act = act; a.B = c.B; a.HW = L.H * L.W; a.C = L.C;
   return launch_bn_train_fwd(a, c.st);
 }
@@ -148,8 +151,8 @@ int bn_bwd(const Ctx& c, const ConvBnPlan& cp, const LayerBufs& L, int act, cons
            const float* se_dmean) {
   BnTrainBwdArgs a;
   a.z = L.z; a.dy = dy; a.dz = dz; a.scale = L.scale; a.shift = L.shift; a.save_mean = L.mean; a.save_rstd = L.rstd;
-  a.se_s = se_s; a.se_dmean = se_dmean; a.partial = c.T.partial;
-  a.dgamma = c.grad(cp.gamma); a.dbeta = c.grad(cp.beta); a.c1 = c.T.c1; a.c2 = c.T.c2;
+  a.se_s = se_s; a.se_dmean = se_dmean; a.bstat = L.bstat; a.bstat_zeroed = true;
+  a.dgamma = c.grad(cp.gamma); a.dbeta = c.grad(cp.beta);
   a.act = act; a.B = c.B; a.HW = L.H * L.W; a.C = L.C;
   MTG_REQUIRE(a.dgamma && a.dbeta, MTG_ERR_ARG, "backward: missing gradient buffer for a BatchNorm parameter");
   return launch_bn_train_bwd(a, c.st);
@@ -163,10 +166,12 @@ int wgrad(const Ctx& c, WgradArgs& w, int hw) {
   return launch_wgrad_tc(w, c.B, c.st);
 }
 
+// `stat`: the BatchNorm accumulators of the layer this conv feeds (forward only): filled by the GEMM epilogue
 int conv1x1_raw(const Ctx& c, const bf16* a, const bf16* w, bf16* out, int M, int N, int K, const float* a_scale, int hw,
-                const bf16* residual) {
+                const bf16* residual, double* stat = nullptr) {
   ConvGemmArgs g;
   g.a = a; g.w = w; g.out = out; g.M = M; g.N = N; g.K = K; g.act = ACT_NONE; g.a_scale = a_scale; g.hw = hw; g.residual = residual;
+  g.stat = stat;
   return launch_conv_gemm(g, c.st);
 }
 
@@ -181,18 +186,22 @@ size_t train_workspace_bytes(const NetPlan& P, int batch) {
 int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
   TrainBufs T;
   layout(P, io.batch, ws, T);
+  // MTGSEG_BN_EPI=0 (A/B): statistics from a separate pass over z instead of the conv epilogues
+  static const bool epi_stats = [] { const char* e = getenv("MTGSEG_BN_EPI"); return !(e && e[0] == '0'); }();
+  auto SD = [&](double* p) { return epi_stats ? p : nullptr; };
   MTG_REQUIRE(T.bytes <= ws_bytes, MTG_ERR_WORKSPACE, "forward_train: workspace too small: need %zu bytes, got %zu", T.bytes, ws_bytes);
   const int B = io.batch;
   Ctx c{P, io, T, st, B};
   const float mom_bb = 1e-2f, mom_head = 0.1f;
   RC(launch_fill_f32(T.ones, 1.f, static_cast<size_t>(B) * 960, st));
   RC(launch_fill_f32(T.zeros, 0.f, static_cast<size_t>(B) * 960, st));
+  MTG_CUDA(cudaMemsetAsync(T.stat_arena, 0, T.stat_bytes, st));
   {
     StemArgs a;
     a.x = io.x; a.w = c.wf(P.stem.w_off); a.scale = T.ones; a.shift = T.zeros; a.out = T.stem.z;
     a.B = B; a.H = P.desc.in_h; a.W = P.desc.in_w; a.act = ACT_NONE;
     RC(launch_stem(a, st));
-    RC(bn_fwd(c, P.stem, T.stem, ACT_HSWISH, nullptr, nullptr, 1, mom_bb));
+    RC(bn_fwd(c, P.stem, T.stem, ACT_HSWISH, nullptr, nullptr, 1, mom_bb, /*stats_done=*/false));
   }
   const bf16* t = T.stem.y;
   for (int i = 0; i < kNumBlocks; ++i) {
@@ -202,8 +211,8 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
     const bf16* inp = t;
     const bf16* e = t;
     if (b.has_expand) {
-      RC(conv1x1_raw(c, t, c.wb(b.expand.w_off), K.expand.z, B * K.Hin * K.Win, cf.cexp, cf.cin, nullptr, 0, nullptr));
-      RC(bn_fwd(c, b.expand, K.expand, cf.act, nullptr, nullptr, 1, mom_bb));
+      RC(conv1x1_raw(c, t, c.wb(b.expand.w_off), K.expand.z, B * K.Hin * K.Win, cf.cexp, cf.cin, nullptr, 0, nullptr, SD(K.expand.stat)));
+      RC(bn_fwd(c, b.expand, K.expand, cf.act, nullptr, nullptr, 1, mom_bb, epi_stats));
       e = K.expand.y;
     }
     {
@@ -212,8 +221,9 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
       a.in = e; a.w = c.wb(b.dw.w_off); a.out = K.dw.z; a.scale = T.ones; a.shift = T.zeros; a.act = ACT_NONE;
       a.B = B; a.H = K.Hin; a.W = K.Win; a.C = cf.cexp; a.k = cf.k; a.stride = stride; a.dil = cf.dil;
       a.gap_partial = nullptr; a.chunks = dwconv_chunks(K.Hin, K.Win, cf.cexp, cf.k, stride, cf.dil, false);
+      a.stat = SD(K.dw.stat);
       RC(launch_dwconv(a, st));
-      RC(bn_fwd(c, b.dw, K.dw, cf.act, nullptr, cf.se ? K.gap : nullptr, K.gap_chunks, mom_bb));
+      RC(bn_fwd(c, b.dw, K.dw, cf.act, nullptr, cf.se ? K.gap : nullptr, K.gap_chunks, mom_bb, epi_stats));
     }
     if (cf.se) {
       SeMlpArgs s;
@@ -223,21 +233,22 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
       RC(launch_se_mlp(s, st));
     }
     RC(conv1x1_raw(c, K.dw.y, c.wb(b.project.w_off), K.project.z, B * K.dw.H * K.dw.W, cf.cout, cf.cexp, cf.se ? K.s : nullptr,
-                   K.dw.H * K.dw.W, nullptr));
+                   K.dw.H * K.dw.W, nullptr, SD(K.project.stat)));
     const bool res = cf.stride == 1 && cf.cin == cf.cout;
-    RC(bn_fwd(c, b.project, K.project, ACT_NONE, res ? inp : nullptr, nullptr, 1, mom_bb));
+    RC(bn_fwd(c, b.project, K.project, ACT_NONE, res ? inp : nullptr, nullptr, 1, mom_bb, epi_stats));
     t = K.project.y;
   }
   const int ic = P.desc.inter_channels, nc = P.desc.num_classes;
   const int Hh = T.Hh, Wh = T.Wh, Mh = B * Hh * Wh;
-  RC(conv1x1_raw(c, t, c.wb(P.last.w_off), T.last.z, Mh, 960, 160, nullptr, 0, nullptr));
-  RC(bn_fwd(c, P.last, T.last, ACT_HSWISH, nullptr, T.hsum, 1, mom_bb));  // pooled sums of `high` for the scale branch
+  RC(conv1x1_raw(c, t, c.wb(P.last.w_off), T.last.z, Mh, 960, 160, nullptr, 0, nullptr, SD(T.last.stat)));
+  RC(bn_fwd(c, P.last, T.last, ACT_HSWISH, nullptr, T.hsum, 1, mom_bb, epi_stats));  // pooled sums of `high` for the scale branch
   {
     ConvGemmArgs h;
     h.a = T.last.y; h.w = c.wb(P.cbr.w_off); h.out = T.cbr.z; h.M = Mh; h.N = ic; h.K = 960; h.act = ACT_NONE;
     h.conv3x3 = 1; h.B = B; h.H = Hh; h.W = Wh;
+    h.stat = SD(T.cbr.stat);
     RC(launch_conv_gemm(h, st));
-    RC(bn_fwd(c, P.cbr, T.cbr, ACT_RELU, nullptr, nullptr, 1, mom_head));
+    RC(bn_fwd(c, P.cbr, T.cbr, ACT_RELU, nullptr, nullptr, 1, mom_head, epi_stats));
     SeMlpArgs s;
     s.sums = T.hsum; s.chunks = 1; s.B = B; s.C = 960; s.SQ = ic; s.HW = Hh * Wh;
     s.w1 = c.wb(P.scale_w_off); s.b1 = nullptr; s.act1 = ACT_SIGMOID; s.w2 = nullptr; s.out = T.hscale;
@@ -322,6 +333,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   };
   MTG_REQUIRE(need(P.high_w) && need(P.high_b) && need(P.low_w) && need(P.low_b) && need(P.scale_w) && need(P.cbr.w_idx) &&
                   need(P.last.w_idx) && need(P.stem.w_idx), MTG_ERR_ARG, "backward: missing gradient buffers");
+  MTG_CUDA(cudaMemsetAsync(T.bstat_arena, 0, T.bstat_bytes, st));
 
   // ---- head tail ------------------------------------------------------------------------------------
   // dlogits [B][NC][H][W] -> d_o [B][Hl*Wl][NC] -> dh2 [B][Hh*Wh][NC]

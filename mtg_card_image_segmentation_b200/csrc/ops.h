@@ -23,6 +23,7 @@ struct ConvGemmArgs {
   int tap_dy[9] = {0}, tap_dx[9] = {0};
   long long out_sx = 0, out_sy = 0, out_sn = 0;  // output strides in elements (0 -> dense NHWC); lets a parity class of a
                                                  // stride-2 transposed conv write every other pixel of the full-size tensor
+  double* stat = nullptr;  // training: [2][N] fp64, += per-channel sum / sum of squares of the stored outputs (zero it first)
 };
 int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st);
 
@@ -37,6 +38,7 @@ struct DwConvArgs {
   int B = 0, H = 0, W = 0, C = 0, k = 3, stride = 1, dil = 1;
   float* gap_partial = nullptr;  // optional [B][chunks][C] per-chunk channel sums of the output
   int chunks = 1;                // pixel chunks per image (grid.x); see dwconv_chunks()
+  double* stat = nullptr;        // training: [2][C] fp64, += per-channel sum / sum of squares of the stored outputs (zero it first)
 };
 int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap);
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st);
@@ -120,7 +122,8 @@ struct BnTrainFwdArgs {
   float eps = 1e-3f, momentum = 1e-2f;
   float* running_mean = nullptr; float* running_var = nullptr; long long* num_batches_tracked = nullptr;  // updated in place
   float* scale = nullptr; float* shift = nullptr; float* save_mean = nullptr; float* save_rstd = nullptr;  // [C] each (saved for bwd)
-  float* partial = nullptr;     // scratch, bn_partial_floats()
+  double* stat = nullptr;       // [2][C] fp64 accumulators: sum z, sum z^2
+  bool stats_done = false;      // true: the producing conv kernel already accumulated `stat` from its epilogue (zeroed before it ran)
   float* gap = nullptr; int gap_chunks = 1;  // optional [B][gap_chunks][C] channel sums of y (squeeze-excite pool)
   int act = ACT_NONE, B = 0, HW = 0, C = 0;
 };
@@ -129,7 +132,9 @@ struct BnTrainBwdArgs {
   const bf16* z = nullptr; const bf16* dy = nullptr; bf16* dz = nullptr;
   const float* scale = nullptr; const float* shift = nullptr; const float* save_mean = nullptr; const float* save_rstd = nullptr;
   const float* se_s = nullptr; const float* se_dmean = nullptr;  // optional [B][C]: dy' = dy*se_s + se_dmean/HW
-  float* partial = nullptr; float* dgamma = nullptr; float* dbeta = nullptr; float* c1 = nullptr; float* c2 = nullptr;
+  double* bstat = nullptr;      // [2][C] fp64 accumulators: sum dyh, sum dyh*xhat
+  bool bstat_zeroed = false;    // true: the caller cleared `bstat` (one memset for all layers of a step)
+  float* dgamma = nullptr; float* dbeta = nullptr;
   int act = ACT_NONE, B = 0, HW = 0, C = 0;
 };
 int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st);

@@ -269,9 +269,11 @@ def test_batch_256_graph_replay_matches_per_image_calls_and_oracle():
     and resident-weight GEMM paths that small batches never reach).  Every image must carry the same bits as a batch-1 call, and
     eight images spread over both sub-batches are held to the oracle."""
     from mtg_card_image_segmentation_b200.engine import GraphedInference
-    xs, ms = O.synthetic_cards(64, seed=2024)
-    sd = O.calibrate_running_stats(O.make_weights(31), xs[:8])
-    order = torch.randperm(256, generator=torch.Generator().manual_seed(1)) % 64
+    xs, ms = O.synthetic_cards(32, seed=2024)
+    # running statistics from the cards that are evaluated (like every fixture of this file): on other cards a random-init
+    # network amplifies rounding differences by 2-4x, which says nothing about the kernels
+    sd = O.calibrate_running_stats(O.make_weights(31), xs[:32])
+    order = torch.randperm(256, generator=torch.Generator().manual_seed(1)) % 32
     x256 = xs[order].contiguous().cuda()
     model = _model(sd)
     with torch.no_grad():
@@ -285,7 +287,7 @@ def test_batch_256_graph_replay_matches_per_image_calls_and_oracle():
             assert torch.equal(single["logits"][0], z256[i]), f"image {i}: batch-256 replay differs from a batch-1 call"
             assert torch.equal(single["mask"][0], mask256[i])
         assert torch.equal(mask256.bool(), z256[:, 1] > z256[:, 0])
-        # duplicates of one card (the batch tiles 64 cards) are bit-identical wherever they sit in the batch
+        # duplicates of one card (the batch tiles 32 cards) are bit-identical wherever they sit in the batch
         first_of = {}
         for pos, card in enumerate(order.tolist()):
             if card in first_of:
