@@ -39,6 +39,7 @@ struct LayerBufs {
 struct BlockBufs {
   LayerBufs expand, dw, project;
   float* gap = nullptr; int gap_chunks = 1; float* hid = nullptr; float* s = nullptr;
+  float* dpre2 = nullptr; float* dpre1 = nullptr;  // backward: pre-activation gradients of the SE MLP, read by the side stream
   int Hin = 0, Win = 0;
 };
 struct TrainBufs {
@@ -100,6 +101,8 @@ void layout(const NetPlan& P, int B, uint8_t* ws, TrainBufs& T) {
       K.gap = f32(static_cast<size_t>(B) * K.gap_chunks * c.cexp);
       K.hid = f32(static_cast<size_t>(B) * P.blocks[i].sq);
       K.s = f32(static_cast<size_t>(B) * c.cexp);
+      K.dpre2 = f32(static_cast<size_t>(B) * c.cexp);
+      K.dpre1 = f32(static_cast<size_t>(B) * P.blocks[i].sq);
     }
     H = Ho; W = Wo;
     layer(K.project, c.cout, H, W);
@@ -276,7 +279,7 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
 // ---------------------------------------------------------------------------------------------------------
 struct SideStream {
   cudaStream_t s = nullptr;
-  cudaEvent_t ready[4] = {}, freed[4] = {}, done = nullptr;
+  cudaEvent_t ready[4] = {}, freed[4] = {}, done = nullptr, se_ready = nullptr;
   bool ok = false;
 };
 SideStream* side_stream() {
@@ -295,6 +298,7 @@ SideStream* side_stream() {
       if (cudaEventCreateWithFlags(&S.freed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     if (cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&S.se_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     S.ok = true;
   }
   return &S;
@@ -424,13 +428,18 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
       SeBwdArgs a;
       a.ds_partial = ds_part; a.chunks = chunks; a.s = K.s; a.hid = K.hid;
       a.w1 = c.param(b.fc1_w); a.w2 = c.param(b.fc2_w);
-      a.dpre2 = T.pooled[1]; a.dpre1 = T.pooled[2]; a.dmean = T.pooled[3];
+      a.dpre2 = K.dpre2; a.dpre1 = K.dpre1; a.dmean = T.pooled[3];
       a.B = B; a.C = cf.cexp; a.SQ = b.sq;
       RC(launch_se_bwd(a, st));
       MTG_REQUIRE(need(b.fc1_w) && need(b.fc1_b) && need(b.fc2_w) && need(b.fc2_b), MTG_ERR_ARG, "backward: missing SE gradient buffers");
-      RC(launch_outer_sum(T.pooled[1], K.hid, 1, 1.f, c.grad(b.fc2_w), c.grad(b.fc2_b), B, cf.cexp, b.sq, st));
-      RC(launch_outer_sum(T.pooled[2], K.gap, chunks, 1.f / static_cast<float>(HWo), c.grad(b.fc1_w), c.grad(b.fc1_b), B, b.sq,
-                          cf.cexp, st));
+      // the FC weight gradients only need dpre2 / dpre1 (per-block buffers) and saved forward state: side stream
+      if (side) {
+        cudaEventRecord(side->se_ready, st);
+        cudaStreamWaitEvent(side->s, side->se_ready, 0);
+      }
+      RC(launch_outer_sum(K.dpre2, K.hid, 1, 1.f, c.grad(b.fc2_w), c.grad(b.fc2_b), B, cf.cexp, b.sq, cs.st));
+      RC(launch_outer_sum(K.dpre1, K.gap, chunks, 1.f / static_cast<float>(HWo), c.grad(b.fc1_w), c.grad(b.fc1_b), B, b.sq,
+                          cf.cexp, cs.st));
       se_s = K.s;
       se_dmean = T.pooled[3];
     }

@@ -52,8 +52,13 @@ __global__ void __launch_bounds__(256) dot_pool_kernel(const bf16* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// SE MLP backward, one CTA per image.  Forward: mean -> hid = relu(W1 mean + b1) -> s = hsig(W2 hid + b2)
-// (or, single layer: s = sigmoid(W1 mean)).  In: ds partial sums.  Out: dpre2[n][C], dpre1[n][SQ], dmean[n][C].
+// SE MLP backward.  Forward: mean -> hid = relu(W1 mean + b1) -> s = hsig(W2 hid + b2) (or, single layer: s = sigmoid(W1 mean)).
+// In: ds partial sums.  Out: dpre2[n][C], dpre1[n][SQ], dmean[n][C].  Two launches, each a (64 outputs x image) grid so that
+// B = 32 fills the machine (one CTA per image left 116 SMs idle and walked 920 KB of weights alone: 32 us per block):
+//   hidden: dpre2 = hsig'(s) * ds ;  dpre1[j] = relu'(hid[j]) * sum_c W2[c][j] dpre2[c]
+//   mean  : dmean[c] = sum_j W1[j][c] dpre1[j]           (single-layer form: dpre1[j] = s (1 - s) ds[j] first)
+// Threads are (output, reduction group) pairs: a warp reads 32 consecutive outputs of one weight row (coalesced), the four
+// groups split the reduction range and meet in shared memory in fixed order.
 // ---------------------------------------------------------------------------------------------------------
 struct SeBwdP {
   const float* ds_partial; int chunks;
@@ -62,65 +67,73 @@ struct SeBwdP {
   float* dpre2; float* dpre1; float* dmean;
   int C, SQ, single;                 // single: s = sigmoid(W1 mean), C = pooled channels, SQ = outputs
 };
-// out[o] = sum_r w[r * ldr + o * ldo] * x[r], o < O, r < R : threads are (o, group) pairs, groups split the
-// reduction range, partial sums meet in shared memory (fixed order)
-__device__ __forceinline__ void grouped_matvec(const float* __restrict__ w, int ldr, int ldo, const float* x, int R, int O,
-                                               float* scratch, float* out_smem) {
-  const int Op = (O + 31) & ~31;
-  const int G = max(1, static_cast<int>(blockDim.x) / Op);
-  const int o = threadIdx.x % Op, grp = threadIdx.x / Op;
+constexpr int SE_TILE = 64;  // outputs per CTA
+
+// out[o0 + o] = sum_r w[r * ld + o0 + o] * x[r] for o < 64, all 256 threads; result valid in threads 0..63
+__device__ __forceinline__ float tile_matvec(const float* __restrict__ w, int ld, int o0, int O, const float* x, int R, float* scratch) {
+  const int o = threadIdx.x & 63, grp = threadIdx.x >> 6;
   float a = 0.f;
-  if (o < O && grp < G)
-    for (int r = grp; r < R; r += G) a = fmaf(w[static_cast<size_t>(r) * ldr + static_cast<size_t>(o) * ldo], x[r], a);
-  if (grp < G) scratch[grp * Op + o] = a;
-  __syncthreads();
-  if (threadIdx.x < O) {
-    float t = 0.f;
-    for (int gq = 0; gq < G; ++gq) t += scratch[gq * Op + threadIdx.x];
-    out_smem[threadIdx.x] = t;
+  if (o0 + o < O) {
+    const float* wp = w + o0 + o;
+    int r = grp;
+    for (; r + 12 < R; r += 16) {  // four independent loads in flight per thread
+      const float w0 = __ldg(wp + static_cast<size_t>(r) * ld), w1 = __ldg(wp + static_cast<size_t>(r + 4) * ld);
+      const float w2 = __ldg(wp + static_cast<size_t>(r + 8) * ld), w3 = __ldg(wp + static_cast<size_t>(r + 12) * ld);
+      a = fmaf(w0, x[r], a); a = fmaf(w1, x[r + 4], a); a = fmaf(w2, x[r + 8], a); a = fmaf(w3, x[r + 12], a);
+    }
+    for (; r < R; r += 4) a = fmaf(__ldg(wp + static_cast<size_t>(r) * ld), x[r], a);
   }
+  scratch[grp * 64 + o] = a;
   __syncthreads();
+  return scratch[o] + scratch[64 + o] + scratch[128 + o] + scratch[192 + o];
 }
 
-__global__ void __launch_bounds__(1024) se_bwd_kernel(const SeBwdP p) {
+// grid (ceil(SQ / 64), B): two-layer form only
+__global__ void __launch_bounds__(256) se_bwd_hidden_kernel(const SeBwdP p) {
   extern __shared__ float sm[];
-  const int n = blockIdx.x;
-  float* va = sm;                 // [max(C, SQ)]
-  float* vb = va + max(p.C, p.SQ);  // [max(C, SQ)]
-  float* scratch = vb + max(p.C, p.SQ);  // [1024 + 32]
-  if (p.single) {
-    // s[n][j] (SQ outputs) = sigmoid(sum_c w1[j][c] mean[c]);  ds given per output j
-    for (int j = threadIdx.x; j < p.SQ; j += blockDim.x) {
-      float d = 0.f;
-      for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.SQ + j];
-      const float sv = p.s[static_cast<size_t>(n) * p.SQ + j];
-      d *= sv * (1.f - sv);
-      va[j] = d;
-      p.dpre1[static_cast<size_t>(n) * p.SQ + j] = d;
-    }
-    __syncthreads();
-    grouped_matvec(p.w1, p.C, 1, va, p.SQ, p.C, scratch, vb);  // dmean[c] = sum_j w1[j][c] dpre[j]
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) p.dmean[static_cast<size_t>(n) * p.C + c] = vb[c];
-    return;
-  }
+  float* dp2 = sm;            // [C]
+  float* scratch = sm + p.C;  // [256]
+  const int n = blockIdx.y;
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     float d = 0.f;
     for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.C + c];
     const float sv = p.s[static_cast<size_t>(n) * p.C + c];
     d = (sv > 0.f && sv < 1.f) ? d * (1.f / 6.f) : 0.f;  // hardsigmoid'
-    va[c] = d;
-    p.dpre2[static_cast<size_t>(n) * p.C + c] = d;
+    dp2[c] = d;
+    if (blockIdx.x == 0) p.dpre2[static_cast<size_t>(n) * p.C + c] = d;
   }
   __syncthreads();
-  grouped_matvec(p.w2, p.SQ, 1, va, p.C, p.SQ, scratch, vb);  // dhid[j] = sum_c w2[c][j] dpre2[c]
+  const int j0 = blockIdx.x * SE_TILE;
+  const float v = tile_matvec(p.w2, p.SQ, j0, p.SQ, dp2, p.C, scratch);  // dhid[j] = sum_c w2[c][j] dpre2[c]
+  const int j = j0 + threadIdx.x;
+  if (threadIdx.x < SE_TILE && j < p.SQ)
+    p.dpre1[static_cast<size_t>(n) * p.SQ + j] = p.hid[static_cast<size_t>(n) * p.SQ + j] > 0.f ? v : 0.f;  // relu'
+}
+
+// grid (ceil(C / 64), B)
+__global__ void __launch_bounds__(256) se_bwd_mean_kernel(const SeBwdP p) {
+  extern __shared__ float sm[];
+  float* dp1 = sm;             // [SQ]
+  float* scratch = sm + p.SQ;  // [256]
+  const int n = blockIdx.y;
   for (int j = threadIdx.x; j < p.SQ; j += blockDim.x) {
-    const float a = p.hid[static_cast<size_t>(n) * p.SQ + j] > 0.f ? vb[j] : 0.f;  // relu'
-    vb[j] = a;
-    p.dpre1[static_cast<size_t>(n) * p.SQ + j] = a;
+    float d;
+    if (p.single) {  // s[n][j] = sigmoid(sum_c w1[j][c] mean[c]); ds given per output j
+      d = 0.f;
+      for (int k = 0; k < p.chunks; ++k) d += p.ds_partial[(static_cast<size_t>(n) * p.chunks + k) * p.SQ + j];
+      const float sv = p.s[static_cast<size_t>(n) * p.SQ + j];
+      d *= sv * (1.f - sv);
+      if (blockIdx.x == 0) p.dpre1[static_cast<size_t>(n) * p.SQ + j] = d;
+    } else {
+      d = p.dpre1[static_cast<size_t>(n) * p.SQ + j];
+    }
+    dp1[j] = d;
   }
   __syncthreads();
-  grouped_matvec(p.w1, p.C, 1, vb, p.SQ, p.C, scratch, va);  // dmean[c] = sum_j w1[j][c] dpre1[j]
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) p.dmean[static_cast<size_t>(n) * p.C + c] = va[c];
+  const int c0 = blockIdx.x * SE_TILE;
+  const float v = tile_matvec(p.w1, p.C, c0, p.C, dp1, p.SQ, scratch);  // dmean[c] = sum_j w1[j][c] dpre1[j]
+  const int c = c0 + threadIdx.x;
+  if (threadIdx.x < SE_TILE && c < p.C) p.dmean[static_cast<size_t>(n) * p.C + c] = v;
 }
 
 // dW[i][j] = sum_n u[n][i] * v[n][j] * vscale ; optional dbias[i] = sum_n u[n][i].   v may be chunked partial sums.
@@ -230,9 +243,13 @@ struct HeadBwdP {
   int Hh, Wh, Hl, Wl, IC, LC, NC;
 };
 constexpr int MAX_NC = 8;
+// grid (B, segments): a CTA owns 1/segments of the image's pixels (one CTA per image: 32 CTAs walking 300 + 1200 pixels serially, 171 us)
 __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
   const int n = blockIdx.x;
   const int nh = p.Hh * p.Wh, nl = p.Hl * p.Wl;
+  const int seg = blockIdx.y, nseg = gridDim.y;
+  const int h_lo = static_cast<int>(static_cast<long long>(nh) * seg / nseg), h_hi = static_cast<int>(static_cast<long long>(nh) * (seg + 1) / nseg);
+  const int l_lo = static_cast<int>(static_cast<long long>(nl) * seg / nseg), l_hi = static_cast<int>(static_cast<long long>(nl) * (seg + 1) / nseg);
   // part 1: thread (i, grp) owns inter channel i over every (blockDim/IC)-th high-res pixel
   const int g1 = max(1, static_cast<int>(blockDim.x) / p.IC);
   for (int i = threadIdx.x % p.IC, grp = threadIdx.x / p.IC; grp < g1; grp = g1) {
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
 #pragma unroll
     for (int c = 0; c < MAX_NC; ++c) { wh[c] = c < p.NC ? p.w_high[c * p.IC + i] : 0.f; dwh[c] = 0.f; }
     float dsv = 0.f;
-    for (int px = grp; px < nh; px += g1) {
+    for (int px = h_lo + grp; px < h_hi; px += g1) {
       const size_t row = static_cast<size_t>(n) * nh + px;
       const float cv = __bfloat162float(p.cbr[row * p.IC + i]);
       float dt = 0.f;
@@ -266,7 +283,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
     float wl[MAX_NC], dwl[MAX_NC];
 #pragma unroll
     for (int c = 0; c < MAX_NC; ++c) { wl[c] = c < p.NC ? p.w_low[c * p.LC + k] : 0.f; dwl[c] = 0.f; }
-    for (int q = grp; q < nl; q += g2) {
+    for (int q = l_lo + grp; q < l_hi; q += g2) {
       const size_t row = static_cast<size_t>(n) * nl + q;
       const float lv = __bfloat162float(p.low[row * p.LC + k]);
       float dl = 0.f;
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
   // part 3: bias gradients
   if (threadIdx.x < p.NC) {
     float b = 0.f;
-    for (int q = 0; q < nl; ++q) b += p.d_o[(static_cast<size_t>(n) * nl + q) * p.NC + threadIdx.x];
+    for (int q = l_lo; q < l_hi; ++q) b += p.d_o[(static_cast<size_t>(n) * nl + q) * p.NC + threadIdx.x];
     atomicAdd(p.db_high + threadIdx.x, b);
     atomicAdd(p.db_low + threadIdx.x, b);
   }
@@ -360,9 +377,13 @@ int launch_dot_pool(const bf16* a, const bf16* b, float* out, int B, int HW, int
 int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.ds_partial && a.s && a.w1 && a.dpre1 && a.dmean, MTG_ERR_ARG, "se_bwd: null pointer");
   SeBwdP p{a.ds_partial, a.chunks, a.s, a.hid, a.w1, a.w2, a.dpre2, a.dpre1, a.dmean, a.C, a.SQ, a.w2 ? 0 : 1};
-  MTG_REQUIRE(a.C <= 1024 && a.SQ <= 1024, MTG_ERR_UNSUPPORTED, "se_bwd: C / SQ above 1024");
-  const int mx = a.C > a.SQ ? a.C : a.SQ;
-  se_bwd_kernel<<<a.B, 1024, sizeof(float) * (2 * mx + 1024 + 64), st>>>(p);
+  MTG_REQUIRE(a.C <= 4096 && a.SQ <= 4096, MTG_ERR_UNSUPPORTED, "se_bwd: C / SQ above 4096");
+  if (a.w2) {
+    MTG_REQUIRE(a.hid && a.dpre2, MTG_ERR_ARG, "se_bwd: the two-layer form needs hid and dpre2");
+    se_bwd_hidden_kernel<<<dim3(ceil_div(a.SQ, SE_TILE), a.B), 256, sizeof(float) * (a.C + 256), st>>>(p);
+    MTG_LAUNCH_CHECK();
+  }
+  se_bwd_mean_kernel<<<dim3(ceil_div(a.C, SE_TILE), a.B), 256, sizeof(float) * (a.SQ + 256), st>>>(p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -392,7 +413,7 @@ int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.NC >= 1 && a.NC <= MAX_NC, MTG_ERR_UNSUPPORTED, "head_bwd: num_classes out of range");
   HeadBwdP p{a.d_o, a.dh2, a.cbr, a.s, a.low, a.w_high, a.w_low, a.dcbr, a.ds, a.dlow, a.dw_high, a.dw_low, a.db_high, a.db_low,
              a.Hh, a.Wh, a.Hl, a.Wl, a.IC, a.LC, a.NC};
-  head_bwd_kernel<<<a.B, 256, 0, st>>>(p);
+  head_bwd_kernel<<<dim3(a.B, a.B >= 128 ? 2 : 8), 256, 0, st>>>(p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
