@@ -3,7 +3,7 @@
 B=256 synthetic card images at config.py resolution (320x240), bf16 activations, random-init weights, 1..8 B200.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (staged unmodified reference; oracle port if absent), rank 0 only
 
 One JSON line on stdout (rank 0).  `value` = images/s with the batch already resident in HBM (CUDA-graph replay
 of the ~60-kernel forward, CUDA events, max over ranks); `e2e` = the same through the public API
@@ -94,29 +94,70 @@ def synthetic_batch(batch, rank):
     return x.repeat(reps, 1, 1, 1)[:batch].contiguous(), m.repeat(reps, 1, 1)[:batch].contiguous()
 
 
+_REF = {}
+
+
+def reference_modules():
+    """The UNMODIFIED reference (train/model.py, utils.py, train.py) from the staged copy oracle/_ref (oracle/make_ref.py, made
+    by __graft_entry__.build(); it travels to the GPU box with the snapshot), or None when it is not staged."""
+    if "mods" not in _REF:
+        from oracle import ref_loader as R
+        _REF["mods"] = R.load_reference(("config", "model", "utils", "train"), staged_only=True) if R.ref_dir(staged_only=True) else None
+    return _REF["mods"]
+
+
 def cpu_reference_forward(batch, steps, warmup, threads):
-    """The reference's CPU path for this workload: fp32 eval forward of the same network (oracle port of
-    train/model.py + torchvision, oneDNN convolutions) on `threads` host cores. Returns images/s and ms/step."""
+    """The reference's CPU path for this workload: fp32 eval forward of train/model.py's network on `threads` host cores -- the
+    reference's own `create_model` when it is staged (kind "reference"), else the oracle port (kind "port"; same ATen / oneDNN
+    kernels underneath).  Returns images/s, ms/step and the kind."""
     from oracle import lraspp_oracle as O
     torch.set_num_threads(threads)
-    sd = O.make_weights(0)
     x, _ = O.synthetic_cards(min(batch, 8), seed=1234, height=H, width=W)
     x = x.repeat((batch + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:batch].contiguous()
+    mods = reference_modules()
+    if mods is not None:
+        torch.manual_seed(0)
+        net = mods["model"].create_model(num_classes=2, pretrained=False).eval()
+        fwd, kind = (lambda: net(x)), "reference"
+    else:
+        sd = O.make_weights(0)
+        fwd, kind = (lambda: O.forward(sd, x)), "port"
     with torch.no_grad():
         for _ in range(warmup):
-            O.forward(sd, x)
+            fwd()
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.forward(sd, x)
+            fwd()
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3
+    return batch * steps / dt, dt / steps * 1e3, kind
 
 
 def cpu_reference_train_step(batch, steps, warmup, threads):
-    """The reference's CPU training step (train/train.py:89-111 without autocast): fp32 train-mode forward of the oracle port,
-    Dice/CE loss, autograd backward, torch.optim.AdamW(lr 1e-3, wd 1e-4) on the 178 tensors. Returns images/s and ms/step."""
+    """The reference's CPU training step (train/train.py:89-111; autocast('cuda') and GradScaler are no-ops on the CPU): the
+    reference's own model, CombinedLoss and create_optimizer when staged, else the oracle port with torch.optim.AdamW(lr 1e-3,
+    wd 1e-4) on the 178 tensors.  Returns images/s, ms/step and the kind."""
     from oracle import lraspp_oracle as O
     torch.set_num_threads(threads)
+    mods = reference_modules()
+    if mods is not None:
+        Config = mods["config"].Config
+        torch.manual_seed(0)
+        net = mods["model"].create_model(num_classes=2, pretrained=False).train()
+        crit = mods["utils"].CombinedLoss(dice_weight=Config.DICE_WEIGHT, ce_weight=Config.BCE_WEIGHT)
+        ropt = mods["train"].create_optimizer(net, Config)
+        x, m = O.synthetic_cards(min(batch, 8), seed=1234, height=H, width=W)
+        reps = (batch + x.shape[0] - 1) // x.shape[0]
+        x, m = x.repeat(reps, 1, 1, 1)[:batch].contiguous(), m.repeat(reps, 1, 1)[:batch].contiguous()
+        dt = 0.0
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            ropt.zero_grad()
+            loss = crit(net(x), m)
+            loss.backward()
+            ropt.step()
+            if i >= warmup:
+                dt += time.perf_counter() - t0
+        return batch * steps / dt, dt / steps * 1e3, "reference"
     sd = O.make_weights(0)
     sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
     opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=1e-3, weight_decay=1e-4)
@@ -136,24 +177,33 @@ def cpu_reference_train_step(batch, steps, warmup, threads):
                 sd[k].copy_(v)
         if i >= warmup:
             dt += time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3
+    return batch * steps / dt, dt / steps * 1e3, "port"
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of configs[1] (fp32 eval forward, B=256 at 320x240) on all host
+    cores.  A step is the whole B=256 batch unless the run would not finish in a few minutes on this host: then a step is a
+    bounded sample of it (B=128 / 64 / 32), and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_b = 32
-    ips, ms = cpu_reference_forward(sample_b, max(1, args.steps), max(1, min(args.warmup, 3)), threads)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    probe_ips, _, _ = cpu_reference_forward(32, 1, 1, threads)
+    sample_b = args.batch
+    while sample_b > 32 and (steps + warmup) * sample_b / probe_ips > 150.0:
+        sample_b //= 2
+    ips, ms, kind = cpu_reference_forward(sample_b, steps, warmup, threads)
+    what = f"whole batch of {sample_b}" if sample_b == args.batch else f"bounded sample of B={sample_b} per step (of the B={args.batch} workload)"
+    impl = "the reference's create_model (staged unmodified train/model.py + torchvision)" if kind == "reference" else "oracle port"
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"train/model.py eval forward, {H}x{W}, bounded sample of B={sample_b} per step (of the B=256 workload)",
-                   "device": "host CPU"},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x B={sample_b} fp32 eval forward, oracle port (torch {torch.__version__} oneDNN)"},
+        "config": {"workload": f"configs[1] on the host: train/model.py eval forward, {H}x{W}, {what}, fp32 (the reference has no "
+                               "bf16 CPU path)", "batch_per_step": sample_b, "device": "host CPU"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{steps} steps x B={sample_b} fp32 eval forward, {impl} (torch {torch.__version__} oneDNN), {warmup} warm-up"},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -321,42 +371,79 @@ def run_ours(args):
                 with open(args.layers_out, "w") as f:
                     json.dump({"batch": B, "layers": layers, "families": roofline["families"]}, f, indent=1)
 
-    # ---------------- training step: fwd + CombinedLoss + bwd (+ grad all-reduce) + AdamW --------------------------
-    # configs[2]: batch 32 per GPU (train/config.py:26); configs[3]: data parallel at GLOBAL batch 256 (256/N per GPU)
-    def train_leg(TB, label):
+    def single_gpu_global256():
+        """ms per step of the global-batch-256 step on this GPU alone (no exchange): the N = 1 point of configs[3]."""
+        from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
         from mtg_card_image_segmentation_b200.optim import FusedAdamW
-        from mtg_card_image_segmentation_b200.parallel import average_gradients
+        tm = M.create_model(2, pretrained=False).to(dev).train()
+        op = FusedAdamW(tm.parameters(), lr=1e-3, weight_decay=1e-4)
+        cr = M.CombinedLoss(0.5, 0.5)
+        reps = (256 + B - 1) // B
+        xt = x.repeat(reps, 1, 1, 1)[:256].contiguous()
+        mt = m_host.repeat(reps, 1, 1)[:256].to(dev)
+
+        def step():
+            op.zero_grad(set_to_none=True)
+            loss = cr(tm(xt), mt)
+            loss.backward()
+            op.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        del tm, op
+        torch.cuda.empty_cache()
+        return ms
+
+    # ---------------- training step: fwd + CombinedLoss + bwd (+ bucketed gradient exchange) + AdamW ------------------------
+    # configs[2]: batch 32 per GPU (train/config.py:26); configs[3]: data parallel at GLOBAL batch 256 (256/N per GPU)
+    def train_leg(TB, label, single_gpu_base=False):
+        from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+        from mtg_card_image_segmentation_b200.optim import FusedAdamW
+        from mtg_card_image_segmentation_b200 import parallel as PAR
         tmodel = M.create_model(2, pretrained=False).to(dev).train()
         opt = FusedAdamW(tmodel.parameters(), lr=1e-3, weight_decay=1e-4)  # train/config.py:28-29
         crit = M.CombinedLoss(0.5, 0.5)
         reps = (TB + B - 1) // B
         xt = x.repeat(reps, 1, 1, 1)[:TB].contiguous() if TB > B else x[:TB].contiguous()
         mt = (m_host.repeat(reps, 1, 1)[:TB] if TB > B else m_host[:TB]).to(dev)
+        if world > 1:
+            PAR.enable_gradient_exchange(tmodel)  # the library's NCCL communicator: bucketed all-reduce inside backward
 
         def train_step():
             opt.zero_grad(set_to_none=True)
             out = tmodel(xt)
             loss = crit(out, mt)
-            loss.backward()
-            average_gradients(tmodel.last_flat_grad)  # data parallel: one all-reduce of the flat gradient buffer
+            loss.backward()  # N > 1: returns rank-averaged gradients (4 buckets, overlapped with the backward pass)
             opt.step()
             return loss
 
-        for _ in range(3):
-            train_step()
-        barrier()
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            barrier()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(n):
+                last = fn()
+            t1e.record()
+            barrier()
+            tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return tt.item() / n, last
+
+        tsteps = max(50, args.steps) if TB <= 64 else max(20, args.steps // 2)
         l0 = lib.mtgseg_launch_count()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tsteps = max(5, args.steps // 4)
-        t0e.record()
-        for _ in range(tsteps):
-            last = train_step()
-        t1e.record()
-        launches_per_step = int((lib.mtgseg_launch_count() - l0) // tsteps)
-        barrier()
-        tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
-        # Host time to ENQUEUE one step, measured outside the timed region on steps that start from an idle, synchronised
-        # device (inside a free-running loop the launch queue fills and the host time converges to the device time).
+        eager_ms, last = timed(train_step, tsteps)
+        launches_per_step = int((lib.mtgseg_launch_count() - l0) // (tsteps + 3))
+        # Host time to ENQUEUE one step, on steps that start from an idle, synchronised device
         host_ms = []
         for _ in range(3):
             torch.cuda.synchronize()
@@ -365,55 +452,51 @@ def run_ours(args):
             host_ms.append(1e3 * (time.perf_counter() - h0))
         torch.cuda.synchronize()
         host_ms = min(host_ms)
+        # the same step captured once and replayed as ONE CUDA graph (engine.GraphedTrainStep): re-pack, forward, loss, backward
+        # incl. the bucketed NCCL exchange at N > 1, AdamW.  This is the step the headline training numbers are quoted on.
+        graphed, gs = None, None
+        try:  # a failure here is reported in the line, it must not take the headline down with it
+            gs = GraphedTrainStep(tmodel, crit, opt, xt, mt)
+            gms, gl = timed(lambda: gs.step(xt, mt), tsteps)
+            graphed = {"api": "engine.GraphedTrainStep(model, criterion, optimizer, x, y).step(x, y)", "ms_per_step": gms,
+                       "value": world * TB / (gms * 1e-3), "unit": UNIT, "loss": float(gl.item()), "launches_per_replay": gs.launches_per_replay}
+        except Exception as e:  # noqa: BLE001
+            graphed = {"error": f"{type(e).__name__}: {str(e).splitlines()[0] if str(e) else ''}"}
+        # exposed communication = step time with the exchange minus the same step without it (same capture / eager mode);
+        # isolated = the whole 16.8 MB buffer averaged alone on an idle GPU (what a non-overlapped exchange would add)
+        exposed_ms = isolated_ms = None
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        # exposed communication: the gradient all-reduce is not overlapped with the backward pass, so its isolated time IS the
-        # exposed time; measured on the flat buffer of the last step, max over ranks
-        allreduce_ms = None
-        if world > 1:
+            del gs
+            gs = None
+            tmodel.data_parallel = False
+            try:
+                g0 = GraphedTrainStep(tmodel, crit, opt, xt, mt, allow_unsynchronised=True) if graphed and "error" not in graphed else None
+            except Exception:  # noqa: BLE001
+                g0 = None
+            if g0 is not None:
+                base_ms, _ = timed(lambda: g0.step(xt, mt), tsteps)
+                exposed_ms = graphed["ms_per_step"] - base_ms
+                del g0
+            else:
+                base_ms, _ = timed(train_step, tsteps)
+                exposed_ms = eager_ms - base_ms
+            tmodel.data_parallel = True
             flat = tmodel.last_flat_grad
-            for _ in range(3):
-                average_gradients(flat)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            a0.record()
-            for _ in range(10):
-                average_gradients(flat)
-            a1.record()
-            torch.cuda.synchronize()
-            at = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
-            dist.all_reduce(at, op=dist.ReduceOp.MAX)
-            allreduce_ms = at.item()
-        # the same step captured once and replayed as one CUDA graph (engine.GraphedTrainStep; single-GPU only: the
-        # data-parallel step keeps the eager all-reduce).  Same work per step: re-pack, forward, loss, backward, AdamW.
-        graphed = None
-        if world == 1:
-            try:  # a secondary leg: a failure here is reported in the line, it must not take the headline down with it
-                from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
-                gs = GraphedTrainStep(tmodel, crit, opt, xt, mt)
-                for _ in range(3):
-                    gs.step(xt, mt)
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                g0.record()
-                for _ in range(tsteps):
-                    gl = gs.step(xt, mt)  # includes the device-to-device copy of the batch into the captured buffers
-                g1.record()
-                torch.cuda.synchronize()
-                gms = g0.elapsed_time(g1) / tsteps
-                graphed = {"api": "engine.GraphedTrainStep(model, criterion, optimizer, x, y).step(x, y)", "ms_per_step": gms,
-                           "value": TB / (gms * 1e-3), "unit": UNIT, "loss": float(gl.item()), "launches_per_replay": gs.launches_per_replay}
-                del gs
-            except Exception as e:  # noqa: BLE001
-                graphed = {"error": f"{type(e).__name__}: {str(e).splitlines()[0] if str(e) else ''}"}
+            iso = lambda: PAR.N.check(lib.mtgseg_dp_allreduce_avg(flat.data_ptr(), flat.numel(), torch.cuda.current_stream().cuda_stream), "allreduce")
+            isolated_ms, _ = timed(lambda: iso(), 20)
+        best_ms = min(eager_ms, graphed["ms_per_step"]) if graphed and "error" not in graphed else eager_ms
         res = {"metric": "training images/sec (fwd + Dice/CE loss + bwd + AdamW)", "workload": label,
-               "value": world * TB * tsteps / (tt.item() * 1e-3), "unit": UNIT, "ms_per_step": tt.item() / tsteps, "steps": tsteps,
+               "value": world * TB / (best_ms * 1e-3), "unit": UNIT, "ms_per_step": best_ms, "steps": tsteps,
+               "mode": "cuda_graph" if best_ms != eager_ms else "eager",
+               "eager": {"ms_per_step": eager_ms, "value": world * TB / (eager_ms * 1e-3), "host_enqueue_ms_per_step": host_ms,
+                         "gpu_launches_per_step": launches_per_step},
                "batch_per_gpu": TB, "global_batch": TB * world, "loss": float(last.item()),
-               "allreduce_ms": allreduce_ms,  # isolated (= exposed) all-reduce + averaging of the flat fp32 gradient; null at N=1
-               "host_enqueue_ms_per_step": host_ms,  # >= ms_per_step would mean the step is host-launch bound on this box
-               "gpu_launches_per_step": launches_per_step,
-               "graphed": graphed,  # null under torchrun
-               "parallelism": f"data parallel x{world}, per-replica BatchNorm, one NCCL all-reduce of the 16.8 MB flat fp32 gradient"}
+               "exposed_comm_ms": exposed_ms,   # N > 1: step with the bucketed exchange minus the same step without it
+               "allreduce_isolated_ms": isolated_ms,  # the 16.8 MB buffer averaged alone (not overlapped), for comparison
+               "graphed": graphed,
+               "parallelism": f"data parallel x{world}, per-replica BatchNorm; gradients averaged inside mtgseg_backward: 4 NCCL buckets "
+                              "(head+features[16] 1.4 M floats, blocks 14-15 1.6 M, blocks 8-13 1.1 M, stem+blocks 1-7 0.1 M) on a "
+                              "communication stream, each fired when its last gradient exists" if world > 1 else "single GPU"}
         del tmodel, opt
         torch.cuda.empty_cache()
         return res
@@ -423,6 +506,16 @@ def run_ours(args):
         train = train_leg(args.train_batch, "configs[2]: train/train.py step, batch 32 per GPU")
         if 256 % world == 0:
             train_dp = train_leg(256 // world, f"configs[3]: data-parallel step, global batch 256 = {256 // world} per GPU")
+            if world > 1:
+                # the N = 1 base of configs[3] (global batch 256 on ONE GPU), timed on rank 0 in the same run while the others wait
+                base = None
+                barrier()
+                if rank == 0:
+                    base = single_gpu_global256()
+                barrier()
+                if rank == 0 and base:
+                    train_dp["single_gpu_global256_ms"] = base
+                    train_dp["scaling_vs_n1"] = base / train_dp["ms_per_step"]
 
     # ---------------- configs[0] on the GPU: batch-1 latency (the reference's own CPU-runnable case, timed on the CPU below) ----
     latency_b1 = None
@@ -474,17 +567,95 @@ def run_ours(args):
                              "frac": flop_img * PB / (ms * 1e-3) / 1e12 / tf_peak, "flop_per_image": flop_img}}
         del head, feat
 
+    # ---------------- fp32-exact inference path (train/evaluate.py:66: float32, no autocast; 1e-4 of the reference) ----------
+    fp32_leg = None
+    if rank == 0 and not args.no_fp32:
+        FB = min(B, 64)
+        xf = x[:FB].contiguous()
+        with torch.no_grad():
+            gf = GraphedInference(model, xf, logits_dtype=torch.float32, precision="fp32")
+            for _ in range(3):
+                gf.replay()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            fsteps = max(5, args.steps // 5)
+            f0.record()
+            for _ in range(fsteps):
+                gf.replay()
+            f1.record()
+            torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / fsteps
+        flop_img = 1_741_498_560.0  # algorithmic forward FLOPs per image (convolutions)
+        ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # fp32 FMA issue peak of the part: 148 SMs x 128 lanes x 2 FLOP x 1.965 GHz
+        fp32_leg = {"metric": "fp32-exact inference images/sec (IEEE fp32 end to end, CUDA-core FFMA; logits within 1e-4 of the reference)",
+                    "value": FB / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "batch": FB, "launches": gf.launches_per_replay,
+                    "roofline": {"bound": "fp32 FFMA issue", "achieved": flop_img * FB / (fms * 1e-3) / 1e12, "peak": ffma_peak,
+                                 "unit": "TFLOP/s", "frac": flop_img * FB / (fms * 1e-3) / 1e12 / ffma_peak,
+                                 "peak_source": "computed: 148 SMs x 128 fp32 lanes x 2 x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)"}}
+        del gf
+
+    # ---------------- the bar of SURVEY.md 2.3: the UNMODIFIED reference through PyTorch eager / cuDNN on this same B200 --------
+    torch_eager = None
+    if rank == 0 and not args.no_eager:
+        try:
+            mods = reference_modules()
+            if mods is None:
+                torch_eager = {"unavailable": "oracle/_ref not staged (python oracle/make_ref.py in the build container)"}
+            else:
+                Config = mods["config"].Config
+                torch.manual_seed(0)
+                ref = mods["model"].create_model(num_classes=2, pretrained=False).to(dev).to(memory_format=torch.channels_last)
+                xe = x.contiguous(memory_format=torch.channels_last)
+
+                def ev_time(fn, n, warm=3):
+                    for _ in range(warm):
+                        fn()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    a.record()
+                    for _ in range(n):
+                        fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    return a.elapsed_time(b) / n
+                ref.eval()
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    inf_ms = ev_time(lambda: ref(xe), max(5, args.steps // 5))
+                ref.train()
+                crit_r = mods["utils"].CombinedLoss(dice_weight=Config.DICE_WEIGHT, ce_weight=Config.BCE_WEIGHT)
+                opt_r = mods["train"].create_optimizer(ref, Config)
+                xt32, mt32 = xe[:32].contiguous(memory_format=torch.channels_last), m_host[:32].to(dev)
+
+                def ref_step():
+                    opt_r.zero_grad()
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        loss = crit_r(ref(xt32), mt32)
+                    loss.backward()
+                    opt_r.step()
+                tr_ms = ev_time(ref_step, max(10, args.steps // 2))
+                torch_eager = {"what": "the unmodified reference model (staged train/model.py + torchvision) on this GPU: PyTorch eager, "
+                                       "cuDNN, channels_last, torch.autocast(bfloat16); informational (SURVEY.md 2.3 'bar to beat')",
+                               "inference_b256": {"value": B / (inf_ms * 1e-3), "unit": UNIT, "ms_per_step": inf_ms,
+                                                  "ours_over_eager": value / world / (B / (inf_ms * 1e-3))},
+                               "train_step_b32": {"value": 32 / (tr_ms * 1e-3), "unit": UNIT, "ms_per_step": tr_ms,
+                                                  "ours_over_eager": (train["value"] / world / (32 / (tr_ms * 1e-3))) if train else None}}
+                del ref, opt_r
+                torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001  (informational leg)
+            torch_eager = {"error": f"{type(e).__name__}: {str(e).splitlines()[0] if str(e) else ''}"}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        ips, ms = cpu_reference_forward(32, 3, 1, threads)
-        ips1, ms1 = cpu_reference_forward(1, 20, 5, threads)  # configs[0]: batch 1, fp32, config.py resolution
-        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "3 steps x B=32 fp32 eval forward at 320x240, oracle port (torch oneDNN), 1 warm-up",
+        ips, ms, kind = cpu_reference_forward(32, 3, 1, threads)
+        ips1, ms1, _ = cpu_reference_forward(1, 20, 5, threads)  # configs[0]: batch 1, fp32, config.py resolution
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "3 steps x B=32 fp32 eval forward at 320x240 (bounded sample of the B=256 workload), "
+                         + ("the reference's own create_model (staged copy)" if kind == "reference" else "oracle port") + " (torch oneDNN), 1 warm-up",
                "config0_batch1": {"value": ips1, "unit": UNIT, "ms_per_image": ms1, "sample": "20 x B=1 fp32 eval forward, 5 warm-up"}}
         if not args.no_train:
-            tips, tms = cpu_reference_train_step(32, 2, 1, threads)  # configs[2] on the host cores, beside the `train` leg
+            tips, tms, _ = cpu_reference_train_step(32, 2, 1, threads)  # configs[2] on the host cores, beside the `train` leg
             cpu["train_step_batch32"] = {"value": tips, "unit": UNIT, "ms_per_step": tms,
                                          "sample": "2 steps x B=32 fp32 train step (fwd + Dice/CE + autograd bwd + torch AdamW), 1 warm-up"}
 
@@ -509,6 +680,7 @@ def run_ours(args):
                                     "note": "same calls fed raw uint8 HWC frames; (v/255-mean)/std fused into the stem kernel"}},
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "latency_batch1": latency_b1, "train": train, "train_global256": train_dp, "pose_head": pose,
+            "fp32_exact": fp32_leg, "torch_eager_gpu": torch_eager,
         }
         emit(line)
     if world > 1:
@@ -546,6 +718,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--no-pose", action="store_true", help="skip the pose-head leg")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-exact inference leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager (unmodified reference on this GPU) leg")
     ap.add_argument("--pose-batch", type=int, default=16)
     ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step (train/config.py:26)")
     ap.add_argument("--layers-out", default=None, help="write the per-layer profile (JSON) here")

@@ -105,7 +105,24 @@ int mtgseg_forward_train(const mtgseg_net_desc* desc, const float* x, const void
                          void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, int batch, void* stream);
 int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, float* const* grads,
                     int n_params, const void* dlogits, int dlogits_dtype, void* workspace, size_t workspace_bytes, int batch,
-                    void* stream);
+                    float* flat_grad, size_t flat_floats, int dp_allreduce, void* stream);
+
+/* Data-parallel training (one process per GPU; the reference trains on one device, train/config.py:61): the single exchange of
+ * a step is the average of the fp32 gradients over the ranks.  mtgseg_backward(..., flat_grad, flat_floats, dp_allreduce = 1)
+ * requires grads[] to be views of ONE flat buffer in state_dict order and averages it with NCCL in four buckets (head +
+ * features[16]; blocks 14-15; blocks 8-13; stem + blocks 1-7), each launched on a communication stream as soon as its last
+ * gradient has been produced, i.e. overlapped with the rest of the backward pass; `stream` waits for the exchange before the
+ * call's work is complete.  BatchNorm statistics stay per replica (the reference has no SyncBN).
+ *   mtgseg_dp_unique_id  rank 0: 128-byte NCCL unique id, to be broadcast by the host layer (torch.distributed / MPI / files)
+ *   mtgseg_dp_init       every rank, collectively: this library's own communicator on the CURRENT device
+ *   mtgseg_dp_world      ranks of the communicator, 0 before init
+ *   mtgseg_dp_allreduce_avg  the same exchange on a caller-owned buffer (tests, isolated timing), ordered after `stream`
+ * NCCL is resolved from the process at run time (libnccl.so.2); everything is stream-ordered and CUDA-graph capturable. */
+int mtgseg_dp_unique_id(void* out128);
+int mtgseg_dp_init(const void* id128, int rank, int world);
+int mtgseg_dp_world(void);
+int mtgseg_dp_shutdown(void);
+int mtgseg_dp_allreduce_avg(float* buf, size_t n, void* stream);
 int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int step, const float* inv_scale, const float* found_inf, void* stream);
 /* CUDA-graph form of the same step (train/train.py:105 inside a captured training step): the scalars of a captured launch

@@ -46,7 +46,12 @@ SIGNATURES = {
     "mtgseg_forward_infer_f32": (_i, [_ND, _vp, C.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "mtgseg_train_workspace_bytes": (_sz, [_ND, _i]),
     "mtgseg_forward_train": (_i, [_ND, _vp, _vp, C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
-    "mtgseg_backward": (_i, [_ND, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
+    "mtgseg_backward": (_i, [_ND, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp]),
+    "mtgseg_dp_unique_id": (_i, [_vp]),
+    "mtgseg_dp_init": (_i, [_vp, _i, _i]),
+    "mtgseg_dp_world": (_i, []),
+    "mtgseg_dp_shutdown": (_i, []),
+    "mtgseg_dp_allreduce_avg": (_i, [_vp, _sz, _vp]),
     "mtgseg_adamw_step": (_i, [_vp, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _vp, _vp]),
     "mtgseg_adamw_hyper": (_i, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp]),
     "mtgseg_adamw_step_dev": (_i, [_vp, _i, _vp, _vp]),

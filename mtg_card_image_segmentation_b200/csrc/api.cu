@@ -136,7 +136,7 @@ int mtgseg_forward_train(const mtgseg_net_desc* desc, const float* x, const void
 
 int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, float* const* grads,
                     int n_params, const void* dlogits, int dlogits_dtype, void* workspace, size_t workspace_bytes, int batch,
-                    void* stream) {
+                    float* flat_grad, size_t flat_floats, int dp_allreduce, void* stream) {
   NetPlan P;
   int rc = plan_for(desc, P);
   if (rc) return rc;
@@ -146,6 +146,8 @@ int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* pac
   TrainIO io;
   io.x = x; io.packed = packed; io.params = params; io.grads = grads; io.dlogits = dlogits; io.dlogits_dtype = dlogits_dtype;
   io.batch = batch;
+  io.flat_grad = flat_grad; io.flat_floats = flat_floats; io.dp = dp_allreduce;
+  MTG_REQUIRE(!dp_allreduce || (flat_grad && flat_floats > 0), MTG_ERR_ARG, "backward: dp_allreduce needs flat_grad / flat_floats");
   return run_train_backward(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, S(stream));
 }
 
@@ -261,6 +263,17 @@ int mtgseg_head_bwd(const float* d_lowres, const float* d_h2, const void* cbr, c
   a.dw_high = dw_high; a.dw_low = dw_low; a.db_high = db_high; a.db_low = db_low;
   a.B = B; a.Hh = Hh; a.Wh = Wh; a.Hl = Hl; a.Wl = Wl; a.IC = IC; a.LC = LC; a.NC = NC;
   return launch_head_bwd(a, S(stream));
+}
+
+int mtgseg_dp_unique_id(void* out128) { return dp_unique_id(out128); }
+int mtgseg_dp_init(const void* id128, int rank, int world) { return dp_init(id128, rank, world); }
+int mtgseg_dp_world(void) { return dp_world(); }
+int mtgseg_dp_shutdown(void) { return dp_shutdown(); }
+int mtgseg_dp_allreduce_avg(float* buf, size_t n, void* stream) {
+  MTG_REQUIRE(buf != nullptr, MTG_ERR_ARG, "dp_allreduce_avg: null pointer");
+  int rc = dp_fire_bucket(buf, n, S(stream), nullptr);
+  if (rc) return rc;
+  return dp_join(S(stream));
 }
 
 unsigned long long mtgseg_launch_count(void) { return launch_count(); }

@@ -84,7 +84,18 @@ struct TrainIO {
   const void* dlogits = nullptr; int dlogits_dtype = LOGITS_F32;  // backward input
   float* const* grads = nullptr;        // backward: 319 pointers, fp32 grad per state_dict entry (NULL for buffers); pre-zeroed
   int batch = 0;
+  // data parallel: grads[] are views of ONE flat buffer in state_dict order; backward averages it over the ranks in buckets on
+  // the communication stream (dp_nccl.cu), each fired when its last gradient has been produced
+  float* flat_grad = nullptr; size_t flat_floats = 0; int dp = 0;
 };
+
+// data-parallel gradient exchange (dp_nccl.cu)
+int dp_unique_id(void* out128);
+int dp_init(const void* id128, int rank, int world);
+int dp_world();
+int dp_shutdown();
+int dp_fire_bucket(float* buf, size_t n, cudaStream_t main, cudaStream_t side);
+int dp_join(cudaStream_t main);
 size_t train_workspace_bytes(const NetPlan& P, int batch);
 int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st);
 int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st);

@@ -338,6 +338,24 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   MTG_REQUIRE(need(P.high_w) && need(P.high_b) && need(P.low_w) && need(P.low_b) && need(P.scale_w) && need(P.cbr.w_idx) &&
                   need(P.last.w_idx) && need(P.stem.w_idx), MTG_ERR_ARG, "backward: missing gradient buffers");
   MTG_CUDA(cudaMemsetAsync(T.bstat_arena, 0, T.bstat_bytes, st));
+  // ---- data parallel: gradient buckets in reverse execution order -------------------------------------------
+  // grads[] are views of one flat buffer in state_dict order, so a bucket is the slice between the first parameter of its
+  // first layer and the first parameter of the next bucket.  A bucket is handed to the communication stream when both the main
+  // and the weight-gradient stream have issued everything that writes into it; the exchange of the head (1.4 M floats) and of
+  // blocks 14-15 (1.6 M) runs under the backward pass of the early, large layers; only the last 0.1 M floats are exposed.
+  auto first_param = [&](int blk) { return P.blocks[blk].has_expand ? P.blocks[blk].expand.w_idx : P.blocks[blk].dw.w_idx; };
+  float* bucket_hi = io.dp ? io.flat_grad + io.flat_floats : nullptr;
+  auto fire_bucket_from = [&](int param_idx) -> int {  // all-reduce [grads[param_idx], bucket_hi) and lower bucket_hi
+    if (!io.dp) return MTG_OK;
+    float* lo = io.grads[param_idx];
+    MTG_REQUIRE(lo != nullptr && lo >= io.flat_grad && lo <= bucket_hi, MTG_ERR_ARG,
+                "backward: gradient pointers are not views of the flat buffer in state_dict order");
+    const int rc = dp_fire_bucket(lo, static_cast<size_t>(bucket_hi - lo), st, side ? side->s : nullptr);
+    bucket_hi = lo;
+    return rc;
+  };
+  if (io.dp) MTG_REQUIRE(io.flat_grad != nullptr && io.grads[P.stem.w_idx] == io.flat_grad, MTG_ERR_ARG,
+                         "backward: data-parallel exchange needs the flat gradient buffer (state_dict order)");
 
   // ---- head tail ------------------------------------------------------------------------------------
   // dlogits [B][NC][H][W] -> d_o [B][Hl*Wl][NC] -> dh2 [B][Hh*Wh][NC]
@@ -393,6 +411,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   }
   bf16* d_out = T.g[0];  // gradient w.r.t. the current block's output
   RC(conv1x1_raw(c, dz_last, c.wb(P.last.wt_off), d_out, Mh, 160, 960, nullptr, 0, nullptr));
+  RC(fire_bucket_from(P.last.w_idx));  // bucket A: features[16] + the whole head
 
   // ---- inverted residual blocks, last to first -------------------------------------------------------
   // buffer roles: d_out = g[0] ; dz_p / dz_d = g[1] ; da / dy_e = g[2] ; dz_e = g[3] ; next d_out is written to g[3]->swap
@@ -484,6 +503,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
     if (d_inp == T.g[3]) { bf16* tmp = T.g[0]; T.g[0] = T.g[3]; T.g[3] = tmp; }
     else { bf16* tmp = T.g[0]; T.g[0] = T.g[2]; T.g[2] = tmp; }
     d_out = T.g[0];
+    if (i == 13 || i == 7) RC(fire_bucket_from(first_param(i)));  // bucket B: blocks 14-15 ; bucket C: blocks 8-13
   }
   // ---- stem -----------------------------------------------------------------------------------------
   bf16* dz_stem = new_dz();
@@ -491,10 +511,12 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   dz_to_side();
   RC(launch_stem_wgrad(io.x, dz_stem, c.grad(P.stem.w_idx), B, H, W, cs.st));
   dz_side_done();
+  RC(fire_bucket_from(P.stem.w_idx));  // bucket D: stem + blocks 1-7 (0.1 M floats: the only exposed exchange)
   if (side) {  // every gradient is complete before the caller's next kernel on `st` (optimizer, all-reduce)
     MTG_CUDA(cudaEventRecord(side->done, side->s));
     MTG_CUDA(cudaStreamWaitEvent(st, side->done, 0));
   }
+  if (io.dp) RC(dp_join(st));
   return MTG_OK;
 }
 

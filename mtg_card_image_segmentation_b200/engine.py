@@ -171,7 +171,7 @@ class SegEngine:
         """Identifies the forward whose activations the workspace holds and the weight arena it used (checked by backward)."""
         return (self._train_gen, self._pack_count)
 
-    def train_backward(self, tensors, is_param, x, dlogits, token=None):
+    def train_backward(self, tensors, is_param, x, dlogits, token=None, dp=False):
         """loss.backward(): returns (flat fp32 gradient buffer, list of per-state-entry views or None).  `token` =
         train_token() taken right after the forward this backward belongs to."""
         if token is not None and token != self.train_token():
@@ -196,7 +196,8 @@ class SegEngine:
             d = self.desc(H, W)
             rc = self.lib.mtgseg_backward(C.byref(d), x.data_ptr(), self._packed.data_ptr(), self._ptr_array(tensors),
                                           self._ptr_array(views), len(tensors), dlogits.data_ptr(), _TORCH_TO_LOGITS[dlogits.dtype],
-                                          self._train_ws.data_ptr(), self._train_ws.numel(), B, N.stream_ptr())
+                                          self._train_ws.data_ptr(), self._train_ws.numel(), B, flat.data_ptr(), flat.numel(),
+                                          1 if dp else 0, N.stream_ptr())
             N.check(rc, "mtgseg_backward")
         return flat, views
 
@@ -288,14 +289,17 @@ class GraphedTrainStep:
     BatchNorm statistics and optimizer state exactly as they were (the warm-up steps run on a snapshot that is restored).
     Construct it under the same ``torch.autocast`` context as the loop.  Not supported: GradScaler (bf16 needs none), several
     parameter groups, criteria other than this package's CombinedLoss / DiceLoss (the step calls the engine and the fused loss
-    kernel directly, without autograd), active pruning masks, data-parallel capture (use the eager step with ``parallel.average_gradients``)."""
+    kernel directly, without autograd), active pruning masks.  Data parallel: call ``parallel.enable_gradient_exchange(model)`` first;
+    the bucketed NCCL exchange is then part of the captured backward."""
 
-    def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3):
+    def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3, allow_unsynchronised=False):
         from .optim import FusedAdamW
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
             raise RuntimeError("GraphedTrainStep needs a FusedAdamW optimizer with one parameter group")
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            raise RuntimeError("GraphedTrainStep captures a single-GPU step; data-parallel training uses the eager step")
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
+                and not getattr(model, "data_parallel", False) and not allow_unsynchronised:
+            raise RuntimeError("GraphedTrainStep in a multi-process job needs parallel.enable_gradient_exchange(model) first: the "
+                               "captured step contains the bucketed NCCL gradient exchange of mtgseg_backward")
         if not model.training:
             raise RuntimeError("GraphedTrainStep: call model.train() first")
         if not example_x.is_cuda:
@@ -319,6 +323,7 @@ class GraphedTrainStep:
                 tuple(self.y.shape) != (self.x.shape[0],) + tuple(self.x.shape[2:]):
             raise RuntimeError("GraphedTrainStep: expected a (B,3,H,W) batch and int64 (B,H,W) targets on the same CUDA device")
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._opt_epoch = getattr(optimizer, "_state_epoch", 0)
         with torch.no_grad():
             snap = [t.detach().clone() for t in tensors]
             snap_opt = []
@@ -365,7 +370,7 @@ class GraphedTrainStep:
         tensors = model._state_tensors()
         logits, x32 = eng.train_forward(tensors, self.x, self._logits_dtype)
         loss3, dlogits = fused_loss(logits, self.y, *self._loss_weights, True)
-        flat, views = eng.train_backward(tensors, self._is_param, x32, dlogits)
+        flat, views = eng.train_backward(tensors, self._is_param, x32, dlogits, dp=getattr(model, "data_parallel", False))
         model.last_flat_grad = flat
         for t, v in zip(tensors, views):
             if v is not None:
@@ -382,6 +387,9 @@ class GraphedTrainStep:
         return self._captured_body()
 
     def step(self, x, y):
+        if getattr(self.optimizer, "_state_epoch", 0) != self._opt_epoch:
+            raise RuntimeError("optimizer.load_state_dict() replaced the moment tensors the captured AdamW launch updates: build a "
+                               "new GraphedTrainStep after loading a checkpoint")
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.optimizer.advance(self.hyper)

@@ -154,7 +154,7 @@ class _TrainStep(torch.autograd.Function):
     def backward(ctx, dlogits):
         model, tensors = ctx.model, ctx.tensors
         is_param = [id(t) in ctx.param_ids for t in tensors]
-        flat, views = model.engine().train_backward(tensors, is_param, ctx.x32, dlogits, ctx.token)
+        flat, views = model.engine().train_backward(tensors, is_param, ctx.x32, dlogits, ctx.token, dp=model.data_parallel)
         model.last_flat_grad = flat  # one contiguous buffer: a data-parallel driver all-reduces it in one call
         grads = [None] * len(ctx.param_ids)
         for t, v in zip(tensors, views):
@@ -184,6 +184,7 @@ class CardSegmentationModel(nn.Module):
         # (train/train.py:96,142) the tensor-core path (bf16 storage, fp32 accumulate); without autocast (train/evaluate.py:66)
         # IEEE float32 end to end, within 1e-4 of the reference.  "bf16" / "fp32" force one of them.
         self.inference_precision = "auto"
+        self.data_parallel = False  # parallel.enable_gradient_exchange: backward averages the gradients over the ranks itself
         self._ref_keys = list(self.state_dict().keys())  # the reference's 319-key layout (train/utils.py:227-280 checkpoints)
         self.last_flat_grad = None
 

@@ -23,8 +23,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _BARE = ("model", "utils", "config", "train", "evaluate", "dataset")
 
 
-def ref_dir() -> str | None:
-    for d in ("/root/reference/train", os.path.join(HERE, "_ref", "train")):
+def ref_dir(staged_only: bool = False) -> str | None:
+    """``staged_only``: only the byte-identical copy under oracle/_ref (bench.py and the GPU tests must not read
+    /root/reference at run time; the staged copy is what travels to the GPU box)."""
+    cands = (os.path.join(HERE, "_ref", "train"),) if staged_only else ("/root/reference/train", os.path.join(HERE, "_ref", "train"))
+    for d in cands:
         if os.path.isfile(os.path.join(d, "model.py")):
             return d
     return None
@@ -54,10 +57,10 @@ def _load(d, name):
     return mod
 
 
-def load_reference(names=("config", "model", "utils"), shim=None):
+def load_reference(names=("config", "model", "utils"), shim=None, staged_only: bool = False):
     """Returns {name: module}.  ``shim``: {bare name: replacement module} installed before the remaining names are imported.
     Previously registered bare-name modules are dropped first, so a shimmed and an unshimmed load do not see each other."""
-    d = ref_dir()
+    d = ref_dir(staged_only)
     if d is None:
         raise RuntimeError("the reference is neither at /root/reference nor staged in oracle/_ref (python oracle/make_ref.py)")
     _stubs()

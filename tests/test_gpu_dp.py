@@ -1,0 +1,111 @@
+"""Data-parallel training step on two GPUs (SURVEY.md §4 item v, §8e): the bucketed NCCL gradient exchange inside
+``mtgseg_backward`` (csrc/dp_nccl.cu).  Skipped on boxes with fewer than two devices (run with ``gpurun --gpus 2``).
+
+Checked, per rank: exchanged gradients == mean over the ranks of the un-exchanged per-shard gradients (the same CUDA backward run
+without the exchange); the mean agrees with the oracle's per-shard gradients averaged (the DDP semantics of SURVEY.md §8e: per-replica
+loss and BatchNorm, gradients averaged); the replicas' parameters stay bit-identical over optimizer steps; the CUDA-graph capture
+of the data-parallel step (which contains the NCCL launches) reproduces the eager step."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(__file__))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from oracle import lraspp_oracle as O
+        import mtg_card_image_segmentation_b200 as M
+        from mtg_card_image_segmentation_b200 import parallel as P
+        from mtg_card_image_segmentation_b200.engine import GraphedTrainStep
+        from mtg_card_image_segmentation_b200.optim import FusedAdamW
+        x, m = O.synthetic_cards(8, seed=31, height=64, width=48)
+        sd = O.calibrate_running_stats(O.make_weights(9), x)
+        sl = P.shard_batch(8, rank, world)
+        xs, ms = x[sl].to(dev), m[sl].to(dev)
+        crit = M.CombinedLoss()
+
+        def fresh():
+            mod = M.create_model(2, pretrained=False)
+            mod.load_state_dict(sd, strict=True)
+            return mod.to(dev).train()
+
+        def flat_grad(mod):
+            return torch.cat([p.grad.flatten() for p in mod.parameters()])
+        # 1. local gradients (no exchange), gathered and averaged by hand
+        local = fresh()
+        crit(local(xs), ms).backward()
+        g_local = flat_grad(local).clone()
+        gathered = [torch.empty_like(g_local) for _ in range(world)]
+        dist.all_gather(gathered, g_local)
+        want = torch.stack(gathered).mean(0)
+        # 2. the same step with the exchange inside backward
+        dp = P.enable_gradient_exchange(fresh())
+        assert dp.data_parallel and M._native.load().mtgseg_dp_world() == world
+        crit(dp(xs), ms).backward()
+        got = flat_grad(dp)
+        err = float((got - want).norm() / want.norm())
+        ok = err <= 1e-4  # the weight-gradient atomics reorder fp32 sums between the two runs; the exchange itself is exact
+        # every rank holds the same bits
+        allg = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(allg, got.contiguous())
+        ok = ok and all(torch.equal(allg[0], g) for g in allg)
+        # 3. oracle: per-shard gradients (each replica's own loss and batch statistics) averaged over the shards
+        cos_med = None
+        if rank == 0:
+            import statistics
+            acc = None
+            for r in range(world):
+                s = P.shard_batch(8, r, world)
+                sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+                O.combined_loss(O.forward(sdg, x[s], training=True, bn_updates={}, q=O.ste_bf16, wq=O.ste_bf16), m[s]).backward()
+                gr = {k: v.grad for k, v in sdg.items() if v.dtype.is_floating_point and "running" not in k}
+                acc = gr if acc is None else {k: acc[k] + gr[k] for k in gr}
+            cos = []
+            for name, p in dp.named_parameters():
+                r_ = (acc[name] / world).double().flatten()
+                g_ = p.grad.detach().cpu().double().flatten()
+                if float(r_.norm()) > 0:
+                    cos.append(float((g_ @ r_) / (g_.norm() * r_.norm()).clamp_min(1e-30)))
+            cos_med = statistics.median(cos)
+            ok = ok and cos_med >= 0.94  # the bar of test_train_step_vs_oracle at this shape (random-init gradients are chaotic)
+        # 4. optimizer steps keep the replicas identical; the captured data-parallel step reproduces the eager one
+        eager, graph = P.enable_gradient_exchange(fresh()), P.enable_gradient_exchange(fresh())
+        oe, og = FusedAdamW(eager.parameters(), lr=1e-3, weight_decay=1e-4), FusedAdamW(graph.parameters(), lr=1e-3, weight_decay=1e-4)
+        gstep = GraphedTrainStep(graph, crit, og, xs, ms)
+        le, lg = [], []
+        for _ in range(3):
+            oe.zero_grad(set_to_none=True)
+            loss = crit(eager(xs), ms)
+            loss.backward()
+            oe.step()
+            le.append(float(loss))
+            lg.append(float(gstep.step(xs, ms)))
+        ok = ok and le[0] == lg[0] and all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg))
+        pe = torch.cat([p.detach().flatten() for p in graph.parameters()])
+        allp = [torch.empty_like(pe) for _ in range(world)]
+        dist.all_gather(allp, pe)
+        ok = ok and all(torch.equal(allp[0], q) for q in allp)
+        out[rank] = (bool(ok), err, cos_med, le, lg, gstep.launches_per_replay)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_bucketed_gradient_exchange_two_ranks():
+    world = 2
+    with mp.Manager() as man:
+        out = man.dict()
+        mp.spawn(_worker, args=(world, 29631, out), nprocs=world, join=True)
+        res = dict(out)
+    print(res)
+    assert all(res[r][0] for r in range(world)), res

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(__file__))
 from oracle import lraspp_oracle as O  # noqa: E402
 from oracle import ref_loader as R  # noqa: E402
 
-needs_ref = pytest.mark.skipif(R.ref_dir() is None, reason="reference neither at /root/reference nor staged in oracle/_ref")
+needs_ref = pytest.mark.skipif(R.ref_dir(staged_only=True) is None, reason="reference not staged in oracle/_ref (python oracle/make_ref.py)")
 
 
 class _Loader(list):
@@ -58,7 +58,7 @@ def test_staged_reference_is_unmodified():
 def test_reference_train_validate_evaluate_on_the_drop_in():
     import mtg_card_image_segmentation_b200 as M
     from mtg_card_image_segmentation_b200 import evaluate as our_eval, model as our_model, utils as our_utils
-    mods = R.load_reference(("config", "train", "evaluate"), shim={"model": our_model, "utils": our_utils})
+    mods = R.load_reference(("config", "train", "evaluate"), shim={"model": our_model, "utils": our_utils}, staged_only=True)
     try:
         ref_train, ref_eval, Config = mods["train"], mods["evaluate"], mods["config"].Config
         assert ref_train.create_model is our_model.create_model and ref_train.CombinedLoss is our_utils.CombinedLoss
@@ -120,7 +120,7 @@ def test_parity_on_weights_trained_by_the_reference():
     import devops as D
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    mods = R.load_reference(("config", "model", "utils", "train"))
+    mods = R.load_reference(("config", "model", "utils", "train"), staged_only=True)
     try:
         ref_train, Config = mods["train"], mods["config"].Config
         dev = torch.device("cuda")
