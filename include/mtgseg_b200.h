@@ -235,7 +235,10 @@ int mtgseg_se_block_bwd(const void* da, const void* y, const float* s, const flo
                         float* scratch, int B, int HW, int C, int SQ, void* stream);
 /* backward of the head tail (train/model.py:137-142; forward = mtgseg_head_mix): d_lowres [B,Hl,Wl,NC] = gradient of the
  * low-resolution logits, d_h2 [B,Hh,Wh,NC] = its x2-bilinear transpose (mtgseg_upsample_bwd).  Writes dcbr [B,Hh,Wh,IC] bf16,
- * dlow [B,Hl,Wl,LC] bf16; ACCUMULATES (atomics; zero first) ds [B,IC], dw_high [NC,IC], dw_low [NC,LC], db_high [NC], db_low [NC]. */
+ * dlow [B,Hl,Wl,LC] bf16 and ds [B, mtgseg_head_bwd_segments(B), IC] fp32 = per-pixel-segment partial sums of dL/ds (summed in
+ * fixed order by the consumer: this value feeds the activation-gradient chain and must be reproducible); ACCUMULATES (atomics;
+ * zero first) the parameter gradients dw_high [NC,IC], dw_low [NC,LC], db_high [NC], db_low [NC]. */
+int mtgseg_head_bwd_segments(int B);
 int mtgseg_head_bwd(const float* d_lowres, const float* d_h2, const void* cbr, const float* s, const void* low, const float* w_high,
                     const float* w_low, void* dcbr, float* ds, void* dlow, float* dw_high, float* dw_low, float* db_high,
                     float* db_low, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC, int NC, void* stream);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mtgseg_upsample_bwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mtgseg_se_bwd_scratch_floats": (_sz, [_i, _i, _i]),
     "mtgseg_se_block_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mtgseg_head_bwd_segments": (_i, [_i]),
     "mtgseg_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mtgseg_pose_param_count": (_i, []),
     "mtgseg_pose_packed_bytes": (_sz, [C.POINTER(PoseDesc)]),

@@ -252,6 +252,8 @@ int mtgseg_se_block_bwd(const void* da, const void* y, const float* s, const flo
   return launch_outer_sum(dpre1, gap, gap_chunks, 1.f / static_cast<float>(HW), dw1, db1, B, SQ, C, S(stream));
 }
 
+int mtgseg_head_bwd_segments(int B) { return head_bwd_segments(B); }
+
 int mtgseg_head_bwd(const float* d_lowres, const float* d_h2, const void* cbr, const float* s, const void* low, const float* w_high,
                     const float* w_low, void* dcbr, float* ds, void* dlow, float* dw_high, float* dw_low, float* db_high,
                     float* db_low, int B, int Hh, int Wh, int Hl, int Wl, int IC, int LC, int NC, void* stream) {

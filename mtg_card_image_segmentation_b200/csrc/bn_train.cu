@@ -106,6 +106,8 @@ __device__ __forceinline__ void block_reduce_atomic(const Geo& g, const Lane& l,
 // Only for layers whose producer does not deliver the statistics from its epilogue (the stem, the per-op ABI entry).
 __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ z, double* __restrict__ stat, const Geo g) {
   __shared__ float red[256 * 8];
+  pdl_trigger();
+  pdl_wait();
   const Lane l = lane_of(g);
   const int chunk = blockIdx.x;
   float acc[2][8];
@@ -140,9 +142,11 @@ struct BnApplyP {
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const Geo g) {
   __shared__ float red[256 * 8];
   __shared__ float s_sc[128], s_sh[128];
+  pdl_trigger();
   const Lane l = lane_of(g);
   const int n = blockIdx.z, chunk = blockIdx.x;
   const bool writer = chunk == 0 && n == 0;
+  pdl_wait();
   if (writer && blockIdx.y == 0 && threadIdx.x == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
   // scale / shift of this CTA's channels: ONE thread per channel does the fp64 arithmetic (the fp64 issue rate is 1/64 of
   // fp32 here: done by every thread for its 8 channels it cost more than the whole streaming loop of a small layer)
@@ -258,8 +262,10 @@ template <bool kApply>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g) {
   __shared__ float red[256 * 8];
   __shared__ float s_c1[kApply ? 128 : 1], s_c2[kApply ? 128 : 1];
+  pdl_trigger();
   const Lane l = lane_of(g);
   const int chunk = blockIdx.x;
+  pdl_wait();
   if (kApply) {  // mean(dyh), mean(dyh*xhat) of this CTA's channels: one thread per channel does the fp64 part (see bn_apply_kernel)
     const int cw = g.CVc * 8;
     const bool writer = chunk == 0 && blockIdx.z == 0;
@@ -362,7 +368,7 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
   if (!a.stats_done) {  // the producer did not accumulate the statistics from its epilogue
     MTG_CUDA(cudaMemsetAsync(a.stat, 0, sizeof(double) * 2 * a.C, st));
     const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
-    bn_stats_kernel<<<rgrid, 256, 0, st>>>(a.z, a.stat, gr);
+    MTG_CUDA(launch_pdl(bn_stats_kernel, rgrid, dim3(256), 0, st, a.z, a.stat, gr));
     MTG_LAUNCH_CHECK();
   }
   Geo ga = g;
@@ -372,7 +378,7 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
   }
   BnApplyP ap{a.z, a.act, a.residual, a.y, a.gap, a.stat, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
               a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd};
-  bn_apply_kernel<<<grid, 256, 0, st>>>(ap, ga);
+  MTG_CUDA(launch_pdl(bn_apply_kernel, grid, dim3(256), 0, st, ap, ga));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -386,9 +392,9 @@ int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st) {
   BnBwdP p{a.z, a.dy, a.scale, a.shift, a.save_mean, a.save_rstd, a.act, a.se_s, a.se_dmean, 1.f / static_cast<float>(a.HW),
            a.bstat, static_cast<double>(a.B) * a.HW, a.dgamma, a.dbeta, a.dz};
   if (!a.bstat_zeroed) MTG_CUDA(cudaMemsetAsync(a.bstat, 0, sizeof(double) * 2 * a.C, st));
-  bn_bwd_kernel<false><<<rgrid, 256, 0, st>>>(p, gr);
+  MTG_CUDA(launch_pdl(bn_bwd_kernel<false>, rgrid, dim3(256), 0, st, p, gr));
   MTG_LAUNCH_CHECK();
-  bn_bwd_kernel<true><<<grid, 256, 0, st>>>(p, g);
+  MTG_CUDA(launch_pdl(bn_bwd_kernel<true>, grid, dim3(256), 0, st, p, g));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -44,6 +44,32 @@ unsigned long long launch_count();
     }                                     \
   } while (0)
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// The training step at batch 32 is a chain of ~350 short dependent kernels: between two of them the GPU idles for the launch
+// latency plus the next kernel's prologue (barrier init, TMEM allocation, descriptor prefetch, constant loads).  Kernels
+// launched through launch_pdl() may start while their predecessor in the stream is still draining; they call pdl_wait()
+// before they touch global memory (it returns once the predecessor grid has completed and its writes are visible) and
+// pdl_trigger() at their top so that THEIR successor can be scheduled early.  Works the same inside a CUDA-graph capture
+// (programmatic edges).  MTGSEG_PDL=0 launches everything with full serialisation (A/B).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ONLY for kernels that call pdl_wait() before their first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
                                                               const DwS p) {
   extern __shared__ __align__(128) uint4 dsm[];
   __shared__ uint64_t bar;
+  pdl_trigger();
   constexpr int NI = (TW - 1) * STRIDE + (KS - 1) * DIL + 1;
   uint4* sw = dsm;              // [KS*KS][CVc]
   uint4* sx = dsm + p.xoff;     // [R][Wp][CVc]
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
         ptx::fence_mbar_init();
       }
       __syncthreads();
+      pdl_wait();
       if (tid == 0) {
         ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>((KS * KS + p.R * p.Wp) * p.CVc) * 16u);
         ptx::tma_load_2d(sw, &tmw, &bar, v0 * 8, 0);
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
     }
     if (p.dbg == 1) return;
   } else {
+    pdl_wait();
     const int rows = (oy1 - oy0 - 1) * STRIDE + (KS - 1) * DIL + 1;
     const bf16* in_n = p.in + static_cast<size_t>(n) * p.H * p.W * p.C + v0 * 8;
     const int per_row = p.Wp * p.CVc;
@@ -365,11 +368,13 @@ __global__ void __launch_bounds__(256, 2) dwconv_half_kernel(const __grid_consta
   const int nv = min(p.CVc, p.CV - v0);
   const int HV = p.CVc * 2, nvh = nv * 2, PLh = 256 / HV;  // half-vectors per pixel of this group, pixel lanes
   const int oy0 = band * p.band, oy1 = min(p.Ho, oy0 + p.band);
+  pdl_trigger();
   if (tid == 0) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
   if (tid == 0) {
     ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>((KS * KS + p.R * p.Wp) * p.CVc) * 16u);
     ptx::tma_load_2d(dsm, &tmw, &bar, v0 * 8, 0);
@@ -590,7 +595,7 @@ int launch_smem2(const CUtensorMap& tmx, const CUtensorMap& tmw, const DwS& p, d
     MTG_CUDA(cudaFuncSetAttribute(dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2, ST><<<grid, 256, smem, st>>>(tmx, tmw, p);
+  MTG_CUDA(launch_pdl(dwconv_smem_kernel<KS, STRIDE, DIL, TW, TMA, F2, ST>, grid, dim3(256), smem, st, tmx, tmw, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -648,8 +653,8 @@ int launch_half(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaS
     MTG_CUDA(cudaFuncSetAttribute(dwconv_half_kernel<KS, DIL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  if (p.stat) dwconv_half_kernel<KS, DIL, true><<<grid, 256, smem, st>>>(tmx, tmw, p);
-  else dwconv_half_kernel<KS, DIL><<<grid, 256, smem, st>>>(tmx, tmw, p);
+  if (p.stat) MTG_CUDA(launch_pdl(dwconv_half_kernel<KS, DIL, true>, grid, dim3(256), smem, st, tmx, tmw, p));
+  else MTG_CUDA(launch_pdl(dwconv_half_kernel<KS, DIL, false>, grid, dim3(256), smem, st, tmx, tmw, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -1,4 +1,5 @@
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -13,6 +14,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MTGSEG_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

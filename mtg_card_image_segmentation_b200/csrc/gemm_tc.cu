@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kAScale ? 448 : 320, kAScale ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();  // the next kernel of the stream may be scheduled as soon as every CTA of this one is running
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
   const int BK = p.kbox;
@@ -152,6 +153,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; its output is read from here on
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t buf_stride = p.tmem_cols >> 1;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -691,7 +693,7 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     fprintf(stderr, "[conv_gemm<%d,%d>] M=%d N=%d K=%d BN=%d kbox=%d obox=%d num_kb=%d stages=%d b_res=%d res_slabs=%d res_bufs=%d epi=%d wbufs=%d tmem=%d need=%zu smem=%zu per_sm=%d grid=%d tiles=%lld\n",
             int(C3), int(AS), kp.M, kp.N, kp.K, kp.BN, kp.kbox, kp.obox, kp.num_kb, kp.stages, kp.b_res, kp.res_slabs, kp.res_bufs, kp.epi_mode, kp.wbufs, kp.tmem_cols, need, smem,
             per_sm, grid, total_tiles);
-  conv_gemm_kernel<C3, AS><<<grid, threads, smem, st>>>(tmA, tmB, tmO, tmR, kp);
+  MTG_CUDA(launch_pdl(conv_gemm_kernel<C3, AS>, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmO, tmR, kp));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

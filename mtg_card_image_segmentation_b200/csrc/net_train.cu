@@ -364,8 +364,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   RC(launch_upsample_bwd(T.d_o, LOGITS_F32, T.dh2, B, nc, Hh, Wh, Hl, Wl, static_cast<long long>(Hl) * Wl * nc, 1, nc, st));
   bf16* dcbr = T.g[0];
   bf16* dlow = T.g[4];  // kept until block 4's output gradient is formed
-  float* ds_head = T.pooled[0];
-  RC(launch_fill_f32(ds_head, 0.f, static_cast<size_t>(B) * ic, st));
+  float* ds_head = T.pooled[0];  // [B][head_bwd_segments(B)][ic] partial sums
   {
     HeadBwdArgs a;
     a.d_o = T.d_o; a.dh2 = T.dh2; a.cbr = T.cbr.y; a.s = T.hscale; a.low = T.blk[3].project.y;
@@ -379,7 +378,7 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
   float* dgap_high = T.pooled[2];  // [B][960]
   {
     SeBwdArgs a;
-    a.ds_partial = ds_head; a.chunks = 1; a.s = T.hscale; a.w1 = c.param(P.scale_w); a.w2 = nullptr;
+    a.ds_partial = ds_head; a.chunks = head_bwd_segments(B); a.s = T.hscale; a.w1 = c.param(P.scale_w); a.w2 = nullptr;
     a.dpre1 = dpre_s; a.dmean = dgap_high; a.B = B; a.C = 960; a.SQ = ic;
     RC(launch_se_bwd(a, st));
     RC(launch_outer_sum(dpre_s, T.hsum, 1, 1.f / static_cast<float>(Hh * Wh), c.grad(P.scale_w), nullptr, B, ic, 960, st));

@@ -179,7 +179,8 @@ struct HeadBwdArgs {
   float* dw_high = nullptr; float* dw_low = nullptr; float* db_high = nullptr; float* db_low = nullptr;  // accumulated (atomics)
   int B = 0, Hh = 0, Wh = 0, Hl = 0, Wl = 0, IC = 0, LC = 0, NC = 0;
 };
-int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);
+int head_bwd_segments(int B);  // pixel segments per image = ds partial slots per image
+int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);  // a.ds: [B][head_bwd_segments(B)][IC] partial sums, overwritten
 int launch_add_bf16(const bf16* a, const bf16* b, bf16* out, size_t n, cudaStream_t st);
 int launch_fill_f32(float* p, float v, size_t n, cudaStream_t st);
 // chunk_table: device array of {float* p; const float* g; float* m; float* v; int n;} (one CTA per entry)

@@ -2,6 +2,7 @@
 // scale branch), elementwise helpers and the fused multi-tensor AdamW.
 // Everything here moves little data (pooled vectors, 2-channel maps) or is a single streaming pass.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "ops.h"
 
@@ -245,6 +246,7 @@ struct HeadBwdP {
 constexpr int MAX_NC = 8;
 // grid (B, segments): a CTA owns 1/segments of the image's pixels (one CTA per image: 32 CTAs walking 300 + 1200 pixels serially, 171 us)
 __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
+  __shared__ float s_ds[256];
   const int n = blockIdx.x;
   const int nh = p.Hh * p.Wh, nl = p.Hl * p.Wl;
   const int seg = blockIdx.y, nseg = gridDim.y;
@@ -272,10 +274,19 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
       p.dcbr[row * p.IC + i] = __float2bfloat16(dt * sv);
       dsv = fmaf(dt, cv, dsv);
     }
-    atomicAdd(p.ds + static_cast<size_t>(n) * p.IC + i, dsv);  // ds is zeroed by the caller
+    s_ds[threadIdx.x] = dsv;  // threadIdx.x == grp * IC + i
 #pragma unroll
     for (int c = 0; c < MAX_NC; ++c)
       if (c < p.NC) atomicAdd(p.dw_high + c * p.IC + i, dwh[c]);
+  }
+  // ds partial of this (image, segment): fixed-order sum over the pixel groups, plain store.  (Atomics here made the whole
+  // backward chain irreproducible: ds feeds the activation gradients, and in bf16 one last-bit difference early in the chain
+  // decorrelates every later rounding -- two runs then differ by the rounding-noise floor, ~1 % of the gradient norm.)
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < p.IC) {
+    float t = 0.f;
+    for (int g = 0; g < g1; ++g) t += s_ds[g * p.IC + threadIdx.x];
+    p.ds[(static_cast<size_t>(n) * nseg + seg) * p.IC + threadIdx.x] = t;
   }
   // part 2: thread (k, grp) owns low channel k over every (blockDim/LC)-th low-res pixel
   const int g2 = max(1, static_cast<int>(blockDim.x) / p.LC);
@@ -409,11 +420,14 @@ int launch_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int
   return MTG_OK;
 }
 
+int head_bwd_segments(int B) { return B >= 128 ? 2 : 8; }
+
 int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.NC >= 1 && a.NC <= MAX_NC, MTG_ERR_UNSUPPORTED, "head_bwd: num_classes out of range");
   HeadBwdP p{a.d_o, a.dh2, a.cbr, a.s, a.low, a.w_high, a.w_low, a.dcbr, a.ds, a.dlow, a.dw_high, a.dw_low, a.db_high, a.db_low,
              a.Hh, a.Wh, a.Hl, a.Wl, a.IC, a.LC, a.NC};
-  head_bwd_kernel<<<dim3(a.B, a.B >= 128 ? 2 : 8), 256, 0, st>>>(p);
+  MTG_REQUIRE(a.IC <= 256, MTG_ERR_UNSUPPORTED, "head_bwd: inter_channels above 256");
+  head_bwd_kernel<<<dim3(a.B, head_bwd_segments(a.B)), 256, 0, st>>>(p);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -87,14 +87,14 @@ def test_head_tail_backward_vs_autograd(B, Hh, Wh, NC):
     _close("x2 bilinear transpose", up_t, d_h2, 1e-5)
     dcbr = torch.empty(B, Hh, Wh, IC, dtype=torch.bfloat16, device=dev)
     dlow = torch.empty(B, Hl, Wl, LC, dtype=torch.bfloat16, device=dev)
-    ds = torch.zeros(B, IC, device=dev); dwh = torch.zeros(NC, IC, device=dev); dwl = torch.zeros(NC, LC, device=dev)
+    ds = torch.full((B, lib.mtgseg_head_bwd_segments(B), IC), float("nan"), device=dev); dwh = torch.zeros(NC, IC, device=dev); dwl = torch.zeros(NC, LC, device=dev)
     dbh = torch.zeros(NC, device=dev); dbl = torch.zeros(NC, device=dev)
     N.check(lib.mtgseg_head_bwd(d_lowres.data_ptr(), d_h2.data_ptr(), cbr.data_ptr(), s.detach().data_ptr(), low.data_ptr(),
                                 w_high.data_ptr(), w_low.data_ptr(), dcbr.data_ptr(), ds.data_ptr(), dlow.data_ptr(), dwh.data_ptr(),
                                 dwl.data_ptr(), dbh.data_ptr(), dbl.data_ptr(), B, Hh, Wh, Hl, Wl, IC, LC, NC, N.stream_ptr()), "head_bwd")
     _close("head bwd dcbr (bf16)", dcbr, cbr_f.grad, 1e-2)
     _close("head bwd dlow (bf16)", dlow, low_f.grad, 1e-2)
-    _close("head bwd ds", ds, s.grad, 1e-4)
+    _close("head bwd ds (segment partials summed)", ds.sum(1), s.grad, 1e-4)
     _close("head bwd dw_high", dwh, w_high.grad, 1e-4)
     _close("head bwd dw_low", dwl, w_low.grad, 1e-4)
     _close("head bwd db_high", dbh, b_high.grad, 1e-4)

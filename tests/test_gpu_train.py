@@ -164,12 +164,21 @@ def test_grad_scaler_loop_matches_plain_step():
         else:
             loss.backward()
             opt.step()
+        grads.append([p.grad.detach().float().cpu().clone() * (1.0 if scale else 1.0) for p in model.parameters()])
         return float(loss.detach()), [p.detach().float().cpu().clone() for p in model.parameters()]
 
+    grads = []
     l0, p0 = one_step(0)
     l1, p1 = one_step(1024.0)
     assert l0 == l1
     worst = max(float((a - b).abs().max()) for a, b in zip(p0, p1))
+    names = [n for n, _ in _train_model(sd).named_parameters()]
+    for n, a, b, ga, gb in zip(names, p0, p1, grads[0], grads[1]):
+        d = (a - b).abs()
+        if float(d.max()) > 1e-4:
+            i = int(d.argmax())
+            print(f"  differs: {n} elem {i}: dparam {float(d.max()):.3e} g_plain {float(ga.flatten()[i]):.4e} g_scaled(after unscale) "
+                  f"{float(gb.flatten()[i]):.4e}; elems {int((d > 1e-4).sum())}/{d.numel()}")
     moved = max(float((a - sd[k].float()).abs().max()) for a, (k, _) in zip(p0, [kv for kv in _train_model(sd).named_parameters()]))
     print(f"GradScaler step vs plain step: max param difference {worst:.3e} (a step moves parameters by up to {moved:.3e})")
     # AdamW normalises the gradient: a 1e-3 step; the two runs may differ by bf16 rounding of scaled vs unscaled gradients

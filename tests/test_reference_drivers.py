@@ -111,7 +111,7 @@ def test_reference_train_validate_evaluate_on_the_drop_in():
 @pytest.mark.gpu
 def test_parity_on_weights_trained_by_the_reference():
     """SURVEY.md §8c fixture C, produced by the REFERENCE: its own unmodified ``create_model`` + ``train_epoch`` (torchvision /
-    cuDNN, fp16 autocast, GradScaler, torch AdamW) train the network on synthetic cards on this GPU; the resulting state_dict
+    cuDNN, torch AdamW; fp32, see below) train the network on synthetic cards on this GPU; the resulting state_dict
     goes into this package with ``load_state_dict(strict=True)``.  North-star tolerances on those weights at config.py
     resolution, against the reference model's own fp32 forward: tensor-core path logits <= 2e-2 of the logit range and rel-L2,
     fp32-exact path <= 1e-4, thresholded masks >= 99.9 % identical over ALL pixels (both paths).
@@ -124,6 +124,16 @@ def test_parity_on_weights_trained_by_the_reference():
     try:
         ref_train, Config = mods["train"], mods["config"].Config
         dev = torch.device("cuda")
+        # The fixture is trained in fp32 (Config.USE_AMP = False: a configuration switch of the reference, train/config.py:32, not an
+        # edit).  Measured (gpurun_out/r2_bisect.log, r2_t3.log): the reference's own fp16-autocast loop -- cuDNN / ATen only, no kernel
+        # of this repository involved -- diverges to NaN on these synthetic cards in some processes (from the first batch when the
+        # allocator's recycled blocks hold bf16 data of earlier tests, after a few epochs otherwise) and trains fine in others;
+        # a golden fixture must not depend on that.  The drop-in test above exercises the fp16 + GradScaler loop on THIS package.
+        Config.USE_AMP = False
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        z = torch.zeros(1 << 30, dtype=torch.float32, device=dev)  # recycled pages come back zeroed, not with stale bf16 patterns
+        del z
         torch.manual_seed(0)
         ref = mods["model"].create_model(num_classes=2, pretrained=False).to(dev)
         crit = mods["utils"].CombinedLoss(dice_weight=Config.DICE_WEIGHT, ce_weight=Config.BCE_WEIGHT)
