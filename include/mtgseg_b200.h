@@ -97,10 +97,18 @@ int mtgseg_forward_infer_f32(const mtgseg_net_desc* desc, const float* x, const 
  * mtgseg_backward: loss.backward() (train/train.py:101,105) for the forward that last used `workspace`.
  *   dlogits [batch,num_classes,in_h,in_w]; grads[i] = fp32 gradient buffer of state_dict entry i in the reference's
  *   layout (OIHW), NULL for buffers; the caller ZEROES them first (several are accumulated with atomics).
+ *   dlogits may be NULL after mtgseg_train_loss (below).
  * mtgseg_adamw_step: torch.optim.AdamW.step (train/train.py:167-171) over all tensors in one launch. chunk_table is a
  *   DEVICE array of n_chunks records {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int32 n;}
- *   (one CTA each; split big tensors into several records). inv_scale / found_inf: GradScaler hooks, may be NULL. */
+ *   (one CTA each; split big tensors into several records). inv_scale / found_inf: GradScaler hooks, may be NULL.
+ * mtgseg_train_loss (optional, replaces mtgseg_loss_fwd_bwd in a step that does not need the logits themselves): CombinedLoss
+ *   (train/utils.py:58-92) of the forward that last used `workspace`, computed from the head's LOW-RESOLUTION logits -- the final x8
+ *   bilinear upsample (tv:models/segmentation/lraspp.py:46) is linear, so the full-resolution logits are recomputed on the fly and
+ *   the gradient is pulled back to 40x30 inside the same kernel.  Call mtgseg_forward_train with logits == NULL before it and
+ *   mtgseg_backward with dlogits == NULL after it: no full-resolution logits / dlogits tensor exists in such a step. */
 size_t mtgseg_train_workspace_bytes(const mtgseg_net_desc* desc, int batch);
+int mtgseg_train_loss(const mtgseg_net_desc* desc, const int64_t* targets, float* loss3, float dice_weight, float ce_weight, float smooth,
+                      void* workspace, size_t workspace_bytes, int batch, void* stream);
 int mtgseg_forward_train(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, int n_params,
                          void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, int batch, void* stream);
 int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* packed, void* const* params, float* const* grads,
@@ -170,6 +178,13 @@ size_t mtgseg_loss_scratch_bytes(void);
 int mtgseg_loss_fwd_bwd(const void* logits, int logits_dtype, const int64_t* targets, void* dlogits, int dlogits_dtype,
                         float* scratch, float* loss3, int64_t batch, int64_t hw, int num_classes, float dice_weight,
                         float ce_weight, float smooth, void* stream);
+
+/* The kernel behind mtgseg_train_loss on caller-owned buffers (unit tests): lowres / d_lowres fp32 [batch,Hl,Wl,num_classes];
+ * logits = bilinear(lowres -> H x W, align_corners=False); loss3 as above; d_lowres = d loss3[0] / d lowres.
+ * scratch >= mtgseg_loss_lowres_scratch_floats(batch, Hl, Wl) floats.  Deterministic (gather form, fixed order). */
+size_t mtgseg_loss_lowres_scratch_floats(int batch, int Hl, int Wl);
+int mtgseg_loss_lowres(const float* lowres, const int64_t* targets, float* d_lowres, float* scratch, float* loss3, int batch, int Hl, int Wl,
+                       int H, int W, int num_classes, float dice_weight, float ce_weight, float smooth, void* stream);
 
 /* ---- per-operator entry points (unit tests, profiling) ------------------------------------------------ */
 /* nn.Conv2d 1x1 (+ folded BN, activation, residual, squeeze-excite input scale) on NHWC bf16:

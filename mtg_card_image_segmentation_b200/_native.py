@@ -45,6 +45,7 @@ SIGNATURES = {
     "mtgseg_workspace_bytes_f32": (_sz, [_ND, _i]),
     "mtgseg_forward_infer_f32": (_i, [_ND, _vp, C.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "mtgseg_train_workspace_bytes": (_sz, [_ND, _i]),
+    "mtgseg_train_loss": (_i, [_ND, _vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _sz, _i, _vp]),
     "mtgseg_forward_train": (_i, [_ND, _vp, _vp, C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp]),
     "mtgseg_backward": (_i, [_ND, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp]),
     "mtgseg_dp_unique_id": (_i, [_vp]),
@@ -84,6 +85,8 @@ SIGNATURES = {
     "mtgseg_metric_counts": (_i, [_vp, _i, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "mtgseg_loss_scratch_bytes": (_sz, []),
     "mtgseg_loss_fwd_bwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, C.c_int64, C.c_int64, _i, C.c_float, C.c_float, C.c_float, _vp]),
+    "mtgseg_loss_lowres_scratch_floats": (_sz, [_i, _i, _i]),
+    "mtgseg_loss_lowres": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float, _vp]),
     "mtgseg_conv1x1": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "mtgseg_conv3x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "mtgseg_dwconv_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i]),

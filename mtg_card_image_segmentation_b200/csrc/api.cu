@@ -122,12 +122,12 @@ int mtgseg_forward_train(const mtgseg_net_desc* desc, const float* x, const void
   NetPlan P;
   int rc = plan_for(desc, P);
   if (rc) return rc;
-  MTG_REQUIRE(x && packed && params && logits && workspace, MTG_ERR_ARG, "forward_train: null pointer");
+  MTG_REQUIRE(x && packed && params && workspace, MTG_ERR_ARG, "forward_train: null pointer");
   MTG_REQUIRE(n_params == P.n_params, MTG_ERR_ARG, "forward_train: expected %d state_dict entries, got %d", P.n_params, n_params);
   MTG_REQUIRE(batch > 0, MTG_ERR_ARG, "forward_train: batch must be positive");
   MTG_REQUIRE(static_cast<long long>(batch) * (desc->in_h / 16) * (desc->in_w / 16) > 1, MTG_ERR_UNSUPPORTED,
               "forward_train: BatchNorm needs more than one value per channel");
-  MTG_REQUIRE(logits_dtype >= LOGITS_F32 && logits_dtype <= LOGITS_F16, MTG_ERR_ARG, "forward_train: bad logits dtype");
+  MTG_REQUIRE(!logits || (logits_dtype >= LOGITS_F32 && logits_dtype <= LOGITS_F16), MTG_ERR_ARG, "forward_train: bad logits dtype");
   MTG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MTG_ERR_ARG, "forward_train: workspace must be 256-byte aligned");
   TrainIO io;
   io.x = x; io.packed = packed; io.params = params; io.logits = logits; io.logits_dtype = logits_dtype; io.batch = batch;
@@ -140,15 +140,32 @@ int mtgseg_backward(const mtgseg_net_desc* desc, const float* x, const void* pac
   NetPlan P;
   int rc = plan_for(desc, P);
   if (rc) return rc;
-  MTG_REQUIRE(x && packed && params && grads && dlogits && workspace, MTG_ERR_ARG, "backward: null pointer");
+  MTG_REQUIRE(x && packed && params && grads && workspace, MTG_ERR_ARG, "backward: null pointer");
   MTG_REQUIRE(n_params == P.n_params, MTG_ERR_ARG, "backward: expected %d state_dict entries, got %d", P.n_params, n_params);
-  MTG_REQUIRE(dlogits_dtype >= LOGITS_F32 && dlogits_dtype <= LOGITS_F16, MTG_ERR_ARG, "backward: bad dlogits dtype");
+  MTG_REQUIRE(!dlogits || (dlogits_dtype >= LOGITS_F32 && dlogits_dtype <= LOGITS_F16), MTG_ERR_ARG, "backward: bad dlogits dtype");
   TrainIO io;
   io.x = x; io.packed = packed; io.params = params; io.grads = grads; io.dlogits = dlogits; io.dlogits_dtype = dlogits_dtype;
   io.batch = batch;
   io.flat_grad = flat_grad; io.flat_floats = flat_floats; io.dp = dp_allreduce;
   MTG_REQUIRE(!dp_allreduce || (flat_grad && flat_floats > 0), MTG_ERR_ARG, "backward: dp_allreduce needs flat_grad / flat_floats");
   return run_train_backward(P, io, static_cast<uint8_t*>(workspace), workspace_bytes, S(stream));
+}
+
+size_t mtgseg_loss_lowres_scratch_floats(int batch, int Hl, int Wl) { return lowres_loss_scratch_floats(batch, Hl, Wl); }
+
+int mtgseg_loss_lowres(const float* lowres, const int64_t* targets, float* d_lowres, float* scratch, float* loss3, int batch, int Hl, int Wl,
+                       int H, int W, int num_classes, float dice_weight, float ce_weight, float smooth, void* stream) {
+  return launch_lowres_loss(lowres, targets, d_lowres, scratch, loss3, batch, Hl, Wl, H, W, num_classes, dice_weight, ce_weight, smooth,
+                            S(stream));
+}
+
+int mtgseg_train_loss(const mtgseg_net_desc* desc, const int64_t* targets, float* loss3, float dice_weight, float ce_weight, float smooth,
+                      void* workspace, size_t workspace_bytes, int batch, void* stream) {
+  NetPlan P;
+  int rc = plan_for(desc, P);
+  if (rc) return rc;
+  MTG_REQUIRE(targets && loss3 && workspace && batch > 0, MTG_ERR_ARG, "train_loss: bad arguments");
+  return run_train_loss(P, batch, targets, loss3, dice_weight, ce_weight, smooth, static_cast<uint8_t*>(workspace), workspace_bytes, S(stream));
 }
 
 int mtgseg_adamw_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,

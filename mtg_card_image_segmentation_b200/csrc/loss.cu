@@ -103,9 +103,141 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partials, int blo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same loss for the training step, computed from the LOW-RESOLUTION logits (40x30) the head produces: the x8 bilinear
+// upsample (tv:models/segmentation/lraspp.py:46) is linear, so the full-resolution logits are recomputed on the fly (same
+// arithmetic as upsample_out_kernel), the per-pixel softmax / CE / Dice terms are summed, and the gradient is pulled back
+// to the 40x30 grid by the transposed interpolation -- no full-resolution logits or dlogits tensor exists in the step.
+// Gather form: one thread per low-resolution pixel walks the fine pixels whose interpolation touches it (fixed order: this
+// gradient feeds the whole backward chain and must be reproducible); every fine pixel is visited by its (up to) four corner
+// owners, and counted for the loss sums by the owner of its top-left corner only.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index_l(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+
+struct LowLossP {
+  const float* lowres; const int64_t* targets; float* d_lowres; float* partials;
+  int Hl, Wl, H, W, NC; float g_ce, g_dice;
+};
+constexpr int LL_CP = 12;     // low-resolution pixels per CTA
+constexpr int LL_SLOTS = 20;  // fine-row slots per low-resolution pixel (a x8 window spans <= 18 fine rows)
+// grid (ceil(Hl*Wl / LL_CP), B), LL_CP * LL_SLOTS threads: thread (slot, cp) walks ONE fine row of the window of low-resolution
+// pixel cp; the slots' partial sums meet in shared memory and are added in slot order (deterministic).
+__global__ void __launch_bounds__(LL_CP * LL_SLOTS) lowres_loss_kernel(const LowLossP p) {
+  extern __shared__ float lo[];  // [Hl*Wl][NC] of this image
+  __shared__ float part[LL_SLOTS][LL_CP][MAX_NC + 2];
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int nlo = p.Hl * p.Wl * p.NC;
+  for (int i = threadIdx.x; i < nlo; i += blockDim.x) lo[i] = p.lowres[static_cast<size_t>(b) * nlo + i];
+  __syncthreads();
+  const int cp = threadIdx.x % LL_CP, slot = threadIdx.x / LL_CP;
+  const int q = blockIdx.x * LL_CP + cp;
+  float acc[MAX_NC];
+#pragma unroll
+  for (int c = 0; c < MAX_NC; ++c) acc[c] = 0.f;
+  float s_pt = 0.f, s_log = 0.f;
+  if (q < p.Hl * p.Wl) {
+    const int qy = q / p.Wl, qx = q - qy * p.Wl;
+    const float sy = static_cast<float>(p.Hl) / p.H, sx = static_cast<float>(p.Wl) / p.W;
+    // fine rows / columns whose source interval can touch (qy, qx): src in (q - 1, q + 1)
+    const int y_lo = max(0, static_cast<int>(floorf((qy - 1 + 0.5f) / sy - 0.5f)) - 1);
+    const int y_hi = min(p.H - 1, static_cast<int>(ceilf((qy + 1 + 0.5f) / sy - 0.5f)) + 1);
+    const int x_lo = max(0, static_cast<int>(floorf((qx - 1 + 0.5f) / sx - 0.5f)) - 1);
+    const int x_hi = min(p.W - 1, static_cast<int>(ceilf((qx + 1 + 0.5f) / sx - 0.5f)) + 1);
+    const int64_t* tb = p.targets + static_cast<size_t>(b) * p.H * p.W;
+    for (int y = y_lo + slot; y <= y_hi; y += LL_SLOTS) {  // one row per thread for x8 (more only for larger factors)
+      int y0, y1; float ly;
+      src_index_l(y, sy, p.Hl, y0, y1, ly);
+      const float wy = (y0 == qy ? 1.f - ly : 0.f) + (y1 == qy ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = x_lo; x <= x_hi; ++x) {
+        int x0, x1; float lx;
+        src_index_l(x, sx, p.Wl, x0, x1, lx);
+        const float wx = (x0 == qx ? 1.f - lx : 0.f) + (x1 == qx ? lx : 0.f);
+        if (wx == 0.f) continue;
+        // full-resolution logits of pixel (y, x): the arithmetic of upsample_out_kernel
+        float z[MAX_NC];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < MAX_NC; ++c)
+          if (c < p.NC) {
+            const float v00 = lo[(y0 * p.Wl + x0) * p.NC + c], v01 = lo[(y0 * p.Wl + x1) * p.NC + c];
+            const float v10 = lo[(y1 * p.Wl + x0) * p.NC + c], v11 = lo[(y1 * p.Wl + x1) * p.NC + c];
+            z[c] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+            m = fmaxf(m, z[c]);
+          }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_NC; ++c)
+          if (c < p.NC) { z[c] = expf(z[c] - m); sum += z[c]; }
+        const float inv = 1.f / sum;
+        const int t = static_cast<int>(tb[static_cast<size_t>(y) * p.W + x]);
+        float pt = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_NC; ++c)
+          if (c < p.NC) { z[c] *= inv; if (c == t) pt = z[c]; }
+        if (y0 == qy && x0 == qx) { s_pt += pt; s_log += logf(pt); }  // counted once, by its top-left corner's owner
+        const float w = wy * wx;
+#pragma unroll
+        for (int c = 0; c < MAX_NC; ++c)
+          if (c < p.NC) {
+            const float yv = (c == t) ? 1.f : 0.f;
+            acc[c] = fmaf(w, p.g_ce * (z[c] - yv) - p.g_dice * pt * (yv - z[c]), acc[c]);
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAX_NC; ++c) part[slot][cp][c] = acc[c];
+  part[slot][cp][MAX_NC] = s_pt;
+  part[slot][cp][MAX_NC + 1] = s_log;
+  __syncthreads();
+  if (slot == 0 && q < p.Hl * p.Wl) {
+    for (int c = 0; c < p.NC; ++c) {
+      float t = 0.f;
+      for (int k = 0; k < LL_SLOTS; ++k) t += part[k][cp][c];
+      p.d_lowres[(static_cast<size_t>(b) * p.Hl * p.Wl + q) * p.NC + c] = t;
+    }
+  }
+  if (threadIdx.x == 0) {
+    float a = 0.f, bb = 0.f;
+    for (int k = 0; k < LL_SLOTS; ++k)
+      for (int j = 0; j < LL_CP; ++j) { a += part[k][j][MAX_NC]; bb += part[k][j][MAX_NC + 1]; }
+    const int s = blockIdx.y * gridDim.x + blockIdx.x;
+    p.partials[2 * s] = a;
+    p.partials[2 * s + 1] = bb;
+  }
+}
+
 }  // namespace
 
 size_t loss_scratch_bytes() { return sizeof(float) * 2 * LOSS_BLOCKS; }
+size_t lowres_loss_scratch_floats(int B, int Hl, int Wl) { return static_cast<size_t>(2) * B * ceil_div(Hl * Wl, LL_CP); }
+
+int launch_lowres_loss(const float* lowres, const int64_t* targets, float* d_lowres, float* scratch, float* loss3, int B, int Hl, int Wl,
+                       int H, int W, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st) {
+  MTG_REQUIRE(lowres && targets && d_lowres && scratch && loss3, MTG_ERR_ARG, "lowres_loss: null pointer");
+  MTG_REQUIRE(nc >= 2 && nc <= MAX_NC, MTG_ERR_UNSUPPORTED, "lowres_loss: num_classes %d not in [2,%d]", nc, MAX_NC);
+  const double n = static_cast<double>(B) * H * W;
+  LowLossP p{lowres, targets, d_lowres, scratch, Hl, Wl, H, W, nc, static_cast<float>(ce_w / n),
+             static_cast<float>(dice_w * 2.0 / (2.0 * n + smooth))};
+  const dim3 grid(ceil_div(Hl * Wl, LL_CP), B);
+  const size_t smem = sizeof(float) * static_cast<size_t>(Hl) * Wl * nc;
+  MTG_REQUIRE(smem <= 40 * 1024, MTG_ERR_UNSUPPORTED, "lowres_loss: low-resolution map too large (%zu B)", smem);
+  MTG_CUDA(launch_pdl(lowres_loss_kernel, grid, dim3(LL_CP * LL_SLOTS), smem, st, p));
+  MTG_LAUNCH_CHECK();
+  loss_finalize_kernel<<<1, 256, 0, st>>>(scratch, static_cast<int>(grid.x * grid.y), n, dice_w, ce_w, smooth, loss3);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
 
 int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, int dlogits_dtype, float* scratch, float* loss3,
                 long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st) {

@@ -99,5 +99,7 @@ int dp_join(cudaStream_t main);
 size_t train_workspace_bytes(const NetPlan& P, int batch);
 int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st);
 int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st);
+int run_train_loss(const NetPlan& P, int batch, const int64_t* targets, float* loss3, float dice_w, float ce_w, float smooth, uint8_t* ws,
+                   size_t ws_bytes, cudaStream_t st);
 
 }  // namespace mtgseg

@@ -261,12 +261,25 @@ int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t w
     m.w_low = c.wf(P.low_w_off); m.b_low = c.wf(P.low_b_off); m.out = T.lowres;
     m.B = B; m.Hh = Hh; m.Wh = Wh; m.Hl = T.Hl; m.Wl = T.Wl; m.IC = ic; m.LC = 40; m.NC = nc;
     RC(launch_head_mix(m, st));
-    UpsampleOutArgs u;
-    u.lowres = T.lowres; u.logits = io.logits; u.logits_dtype = io.logits_dtype;
-    u.B = B; u.Hl = T.Hl; u.Wl = T.Wl; u.H = P.desc.in_h; u.W = P.desc.in_w; u.NC = nc;
-    RC(launch_upsample_out(u, st));
+    if (io.logits) {  // (a captured training step takes its loss from the low-resolution logits: run_train_loss)
+      UpsampleOutArgs u;
+      u.lowres = T.lowres; u.logits = io.logits; u.logits_dtype = io.logits_dtype;
+      u.B = B; u.Hl = T.Hl; u.Wl = T.Wl; u.H = P.desc.in_h; u.W = P.desc.in_w; u.NC = nc;
+      RC(launch_upsample_out(u, st));
+    }
   }
   return MTG_OK;
+}
+
+// CombinedLoss of the forward that last used `ws`, from its low-resolution logits; leaves dLoss/d(lowres) where the backward
+// pass expects the pulled-back gradient (mtgseg_backward with dlogits == NULL).
+int run_train_loss(const NetPlan& P, int batch, const int64_t* targets, float* loss3, float dice_w, float ce_w, float smooth, uint8_t* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  TrainBufs T;
+  layout(P, batch, ws, T);
+  MTG_REQUIRE(T.bytes <= ws_bytes, MTG_ERR_WORKSPACE, "train_loss: workspace too small: need %zu bytes, got %zu", T.bytes, ws_bytes);
+  return launch_lowres_loss(T.lowres, targets, T.d_o, T.pooled[4], loss3, batch, T.Hl, T.Wl, P.desc.in_h, P.desc.in_w, P.desc.num_classes,
+                            dice_w, ce_w, smooth, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -359,8 +372,9 @@ int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t 
 
   // ---- head tail ------------------------------------------------------------------------------------
   // dlogits [B][NC][H][W] -> d_o [B][Hl*Wl][NC] -> dh2 [B][Hh*Wh][NC]
-  RC(launch_upsample_bwd(io.dlogits, io.dlogits_dtype, T.d_o, B, nc, Hl, Wl, H, W, static_cast<long long>(nc) * H * W,
-                         static_cast<long long>(H) * W, 1, st));
+  if (io.dlogits)  // else: run_train_loss already left dLoss/d(lowres) in T.d_o
+    RC(launch_upsample_bwd(io.dlogits, io.dlogits_dtype, T.d_o, B, nc, Hl, Wl, H, W, static_cast<long long>(nc) * H * W,
+                           static_cast<long long>(H) * W, 1, st));
   RC(launch_upsample_bwd(T.d_o, LOGITS_F32, T.dh2, B, nc, Hh, Wh, Hl, Wl, static_cast<long long>(Hl) * Wl * nc, 1, nc, st));
   bf16* dcbr = T.g[0];
   bf16* dlow = T.g[4];  // kept until block 4's output gradient is formed

@@ -111,6 +111,12 @@ size_t loss_scratch_bytes();
 int launch_loss(const void* logits, int dtype, const int64_t* targets, void* dlogits, int dlogits_dtype, float* scratch, float* loss3,
                 long long batch, long long hw, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st);
 
+// the same loss from the low-resolution logits [B][Hl][Wl][NC] of the head (the x8 bilinear upsample recomputed on the fly):
+// loss3 and d_lowres = dLoss/d(lowres); scratch >= lowres_loss_scratch_floats() floats.  Deterministic.
+size_t lowres_loss_scratch_floats(int B, int Hl, int Wl);
+int launch_lowres_loss(const float* lowres, const int64_t* targets, float* d_lowres, float* scratch, float* loss3, int B, int Hl, int Wl,
+                       int H, int W, int nc, float dice_w, float ce_w, float smooth, cudaStream_t st);
+
 // ---- training-mode BatchNorm forward / backward (bn_train.cu) --------------------------------------
 int bn_chunks(int HW, int C);
 size_t bn_partial_floats(int B, int HW, int C);

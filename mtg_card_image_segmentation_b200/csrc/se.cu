@@ -12,6 +12,8 @@ namespace {
 
 // in [B][HW][C] bf16 -> out [B][C] fp32 sums.  grid (ceil(CV/8), B); block 256 = 8 vectors x 32 pixel lanes.
 __global__ void __launch_bounds__(256) gap_kernel(const bf16* __restrict__ in, float* __restrict__ out, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32][64 + 1];
   const int CV = C / 8;
   const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -55,6 +57,8 @@ struct FcP {
 // out[n][o] = act( sum_c w[o][c] * (in_scale * sum_k in[n][k][c]) + bias[o] )
 // grid (ceil(O/32), ceil(B/8)); each warp owns 4 outputs x 8 images, lanes stride over C in 8-wide vectors.
 __global__ void __launch_bounds__(256) fc_batched_kernel(const FcP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float xin[];  // [FC_IMGS][C]
   const int n0 = blockIdx.y * FC_IMGS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,6 +205,8 @@ __device__ __forceinline__ void se_fc(const float* x, int I, const bf16* __restr
 }
 
 __global__ void __launch_bounds__(SE_THREADS) se_fused_kernel(const SeP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float se_smem[];
   float* xin = se_smem;                   // [SE_IMGS][C]
   float* hid = se_smem + SE_IMGS * p.C;   // [SE_IMGS][SQ]
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(SE_THREADS) se_fused_kernel(const SeP p) {
 int launch_gap(const bf16* in, float* out, int B, int HW, int C, cudaStream_t st) {
   MTG_REQUIRE(in && out && C % 8 == 0, MTG_ERR_ARG, "gap: bad arguments");
   dim3 grid(ceil_div(C / 8, 8), B);
-  gap_kernel<<<grid, 256, 0, st>>>(in, out, HW, C);
+  MTG_CUDA(launch_pdl(gap_kernel, dim3(grid), dim3(256), 0, st, in, out, HW, C));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -258,18 +264,18 @@ int launch_se_mlp(const SeMlpArgs& a, cudaStream_t st) {
   const size_t fused_smem = static_cast<size_t>(SE_IMGS) * (a.C + a.SQ) * sizeof(float);
   if (!two_launch && fused_smem <= 48 * 1024) {
     SeP sp{a.sums, a.chunks, 1.0f / static_cast<float>(a.HW), a.B, a.C, a.SQ, a.w1, a.b1, a.act1, a.w2, a.b2, a.act2, a.out, a.w2 ? a.hidden : nullptr};
-    se_fused_kernel<<<ceil_div(a.B, SE_IMGS), SE_THREADS, fused_smem, st>>>(sp);
+    MTG_CUDA(launch_pdl(se_fused_kernel, dim3(ceil_div(a.B, SE_IMGS)), dim3(SE_THREADS), fused_smem, st, sp));
     MTG_LAUNCH_CHECK();
     return MTG_OK;
   }
   FcP l1{a.sums, a.chunks, 1.0f / static_cast<float>(a.HW), a.B, a.C, a.SQ, a.w1, a.b1, a.act1, a.w2 ? a.hidden : a.out};
   dim3 g1(ceil_div(a.SQ, FC_OUTS), ceil_div(a.B, FC_IMGS));
-  fc_batched_kernel<<<g1, 256, static_cast<size_t>(FC_IMGS) * a.C * sizeof(float), st>>>(l1);
+  MTG_CUDA(launch_pdl(fc_batched_kernel, dim3(g1), dim3(256), static_cast<size_t>(FC_IMGS) * a.C * sizeof(float), st, l1));
   MTG_LAUNCH_CHECK();
   if (a.w2) {
     FcP l2{a.hidden, 1, 1.0f, a.B, a.SQ, a.C, a.w2, a.b2, a.act2, a.out};
     dim3 g2(ceil_div(a.C, FC_OUTS), ceil_div(a.B, FC_IMGS));
-    fc_batched_kernel<<<g2, 256, static_cast<size_t>(FC_IMGS) * a.SQ * sizeof(float), st>>>(l2);
+    MTG_CUDA(launch_pdl(fc_batched_kernel, dim3(g2), dim3(256), static_cast<size_t>(FC_IMGS) * a.SQ * sizeof(float), st, l2));
     MTG_LAUNCH_CHECK();
   }
   return MTG_OK;

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                                                    float3 nadd, const float* __restrict__ w,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int act) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 sw[27 * 4];
   __shared__ float ssc[16], ssh[16];
   for (int i = threadIdx.x; i < 27 * 4; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
@@ -130,8 +132,8 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
   // v/255 normalised: (v/255 - mean)/std = v * 1/(255 std) - mean/std
   const float3 nmul = make_float3(1.f / (255.f * a.std[0]), 1.f / (255.f * a.std[1]), 1.f / (255.f * a.std[2]));
   const float3 nadd = make_float3(-a.mean[0] / a.std[0], -a.mean[1] / a.std[1], -a.mean[2] / a.std[2]);
-  if (a.x_u8) stem_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(nullptr, a.x_u8, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act);
-  else stem_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(a.x, nullptr, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act);
+  if (a.x_u8) MTG_CUDA(launch_pdl(stem_kernel<true>, dim3(static_cast<int>(blocks)), dim3(256), 0, st, nullptr, a.x_u8, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
+  else MTG_CUDA(launch_pdl(stem_kernel<false>, dim3(static_cast<int>(blocks)), dim3(256), 0, st, a.x, nullptr, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

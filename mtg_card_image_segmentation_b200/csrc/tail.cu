@@ -36,6 +36,8 @@ struct MixP {
 
 template <int CMAX>
 __global__ void __launch_bounds__(256) head_mix_kernel(const MixP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* wsx = sm;                        // [NC][IC]  w_high * s[b]
   float* h2 = wsx + p.NC * p.IC;          // [Hh*Wh][NC]
@@ -106,6 +108,8 @@ struct UpP {
 // CMAX: compile-time class capacity (2 for the card/background network: no dead predicated code for 6 absent classes)
 template <int CMAX>
 __global__ void __launch_bounds__(256) upsample_out_kernel(const UpP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float lo[];  // [Hl*Wl][NC]
   __shared__ unsigned long long scount[4];
   const int b = blockIdx.y;
@@ -224,8 +228,8 @@ int launch_head_mix(const HeadMixArgs& a, cudaStream_t st) {
     MTG_CUDA(cudaFuncSetAttribute(head_mix_kernel<MAX_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  if (a.NC <= 2) head_mix_kernel<2><<<a.B, 256, smem, st>>>(p);
-  else head_mix_kernel<MAX_NC><<<a.B, 256, smem, st>>>(p);
+  if (a.NC <= 2) MTG_CUDA(launch_pdl(head_mix_kernel<2>, dim3(a.B), dim3(256), smem, st, p));
+  else MTG_CUDA(launch_pdl(head_mix_kernel<MAX_NC>, dim3(a.B), dim3(256), smem, st, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -247,8 +251,8 @@ int launch_upsample_out(const UpsampleOutArgs& a, cudaStream_t st) {
   int row_blocks = ceil_div(a.H, 40);
   p.rows_per_cta = ceil_div(a.H, row_blocks);
   dim3 grid(row_blocks, a.B);
-  if (a.NC <= 2) upsample_out_kernel<2><<<grid, 256, smem, st>>>(p);
-  else upsample_out_kernel<MAX_NC><<<grid, 256, smem, st>>>(p);
+  if (a.NC <= 2) MTG_CUDA(launch_pdl(upsample_out_kernel<2>, dim3(grid), dim3(256), smem, st, p));
+  else MTG_CUDA(launch_pdl(upsample_out_kernel<MAX_NC>, dim3(grid), dim3(256), smem, st, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

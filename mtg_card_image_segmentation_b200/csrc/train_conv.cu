@@ -108,6 +108,8 @@ struct DwBwdP {
 // dx[n,iy,ix,c] = sum_taps w[tap][c] * dz[n,(iy+pad-ky*d)/s,(ix+pad-kx*d)/s,c]   (grid: chunks, groups, B)
 template <int KS>
 __global__ void __launch_bounds__(256) dw_dgrad_kernel(const DwBwdP p) {
+  pdl_trigger();
+  pdl_wait();
   const int vl = threadIdx.x % p.CVc, pl = threadIdx.x / p.CVc;
   const int v = blockIdx.y * p.CVc + vl;
   if (pl >= p.PL || v >= p.CV) return;
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const DwBwdP p) {
 // The ox loop is unrolled by R so that all slot indices are compile-time.  grid (ctas*KS, groups).
 template <int KS, int S, int DIL>
 __global__ void __launch_bounds__(256) dw_wgrad_rows_kernel(const DwBwdP p, int tasks_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int WIN = (KS - 1) * DIL + 1, R = WIN + S;
   __shared__ float red[256 * 8];
   const int vl = threadIdx.x % p.CVc, pl = threadIdx.x / p.CVc;
@@ -296,6 +300,8 @@ __global__ void __launch_bounds__(256) dw_wgrad_rows_kernel(const DwBwdP p, int 
 __global__ void __launch_bounds__(448) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz,
                                                          float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
                                                          int pix_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sp[64][28];
   __shared__ float sg[64][16];
   // 32-bit pixel indices (the launcher checks B*Ho*Wo < 2^31): the staging loop decomposes one index per gathered element,
@@ -376,8 +382,8 @@ int launch_dw_dgrad(const DwBwdArgs& a, cudaStream_t st) {
   DwBwdP p{};
   fill_dw(a, p, 0);
   dim3 grid(p.chunks, ceil_div(p.CV, p.CVc), a.B);
-  if (a.k == 3) dw_dgrad_kernel<3><<<grid, 256, 0, st>>>(p);
-  else dw_dgrad_kernel<5><<<grid, 256, 0, st>>>(p);
+  if (a.k == 3) MTG_CUDA(launch_pdl(dw_dgrad_kernel<3>, dim3(grid), dim3(256), 0, st, p));
+  else MTG_CUDA(launch_pdl(dw_dgrad_kernel<5>, dim3(grid), dim3(256), 0, st, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -405,11 +411,11 @@ int launch_dw_wgrad(const DwBwdArgs& a, cudaStream_t st) {
     ctas = ceil_div(total, tpc);
     const dim3 rgrid(ctas * a.k, groups);
     switch (combo) {
-      case 311: dw_wgrad_rows_kernel<3, 1, 1><<<rgrid, 256, 0, st>>>(p, tpc); break;
-      case 321: dw_wgrad_rows_kernel<3, 2, 1><<<rgrid, 256, 0, st>>>(p, tpc); break;
-      case 511: dw_wgrad_rows_kernel<5, 1, 1><<<rgrid, 256, 0, st>>>(p, tpc); break;
-      case 521: dw_wgrad_rows_kernel<5, 2, 1><<<rgrid, 256, 0, st>>>(p, tpc); break;
-      default: dw_wgrad_rows_kernel<5, 1, 2><<<rgrid, 256, 0, st>>>(p, tpc); break;
+      case 311: MTG_CUDA(launch_pdl(dw_wgrad_rows_kernel<3, 1, 1>, dim3(rgrid), dim3(256), 0, st, p, tpc)); break;
+      case 321: MTG_CUDA(launch_pdl(dw_wgrad_rows_kernel<3, 2, 1>, dim3(rgrid), dim3(256), 0, st, p, tpc)); break;
+      case 511: MTG_CUDA(launch_pdl(dw_wgrad_rows_kernel<5, 1, 1>, dim3(rgrid), dim3(256), 0, st, p, tpc)); break;
+      case 521: MTG_CUDA(launch_pdl(dw_wgrad_rows_kernel<5, 2, 1>, dim3(rgrid), dim3(256), 0, st, p, tpc)); break;
+      default: MTG_CUDA(launch_pdl(dw_wgrad_rows_kernel<5, 1, 2>, dim3(rgrid), dim3(256), 0, st, p, tpc)); break;
     }
     MTG_LAUNCH_CHECK();
     return MTG_OK;
@@ -428,7 +434,7 @@ int launch_stem_wgrad(const float* x, const bf16* dz, float* dw, int B, int H, i
   long long ctas = 148 * 4;
   long long per = ((total + ctas - 1) / ctas + 63) / 64 * 64;
   ctas = (total + per - 1) / per;
-  stem_wgrad_kernel<<<static_cast<unsigned>(ctas), 448, 0, st>>>(x, dz, dw, B, H, W, Ho, Wo, static_cast<int>(per));
+  MTG_CUDA(launch_pdl(stem_wgrad_kernel, dim3(static_cast<unsigned>(ctas)), dim3(448), 0, st, x, dz, dw, B, H, W, Ho, Wo, static_cast<int>(per)));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

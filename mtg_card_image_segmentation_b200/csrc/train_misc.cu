@@ -17,6 +17,8 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dot_pool_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, float* __restrict__ out,
                                                        int HW, int C, int CV, int CVc, int PL, int rows_per_chunk, int chunks) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[256 * 8];
   const int vl = threadIdx.x % CVc, pl = threadIdx.x / CVc;
   const int v = blockIdx.y * CVc + vl;
@@ -91,6 +93,8 @@ __device__ __forceinline__ float tile_matvec(const float* __restrict__ w, int ld
 
 // grid (ceil(SQ / 64), B): two-layer form only
 __global__ void __launch_bounds__(256) se_bwd_hidden_kernel(const SeBwdP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* dp2 = sm;            // [C]
   float* scratch = sm + p.C;  // [256]
@@ -113,6 +117,8 @@ __global__ void __launch_bounds__(256) se_bwd_hidden_kernel(const SeBwdP p) {
 
 // grid (ceil(C / 64), B)
 __global__ void __launch_bounds__(256) se_bwd_mean_kernel(const SeBwdP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* dp1 = sm;             // [SQ]
   float* scratch = sm + p.SQ;  // [256]
@@ -141,6 +147,8 @@ __global__ void __launch_bounds__(256) se_bwd_mean_kernel(const SeBwdP p) {
 // CTA tile: 16 rows (i) x 64 columns (j); u and the chunk-reduced v of up to 64 images are staged in shared memory.
 __global__ void __launch_bounds__(256) outer_sum_kernel(const float* __restrict__ u, const float* __restrict__ v, int v_chunks, float vscale,
                                                         float* __restrict__ dw, float* __restrict__ dbias, int B, int I, int J) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float us[64][16];
   __shared__ float vs[64][64];
   const int j0 = blockIdx.x * 64, i0 = blockIdx.y * 16;
@@ -199,6 +207,8 @@ template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { retu
 template <typename T>
 __global__ void __launch_bounds__(128) upsample_bwd_kernel(const T* __restrict__ g, float* __restrict__ out, int B, int NC, int Hc, int Wc,
                                                            int Hf, int Wf, long long sn, long long sc, long long sp) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * Hc * Wc * NC) return;
   const int c = idx % NC;
@@ -246,6 +256,8 @@ struct HeadBwdP {
 constexpr int MAX_NC = 8;
 // grid (B, segments): a CTA owns 1/segments of the image's pixels (one CTA per image: 32 CTAs walking 300 + 1200 pixels serially, 171 us)
 __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_ds[256];
   const int n = blockIdx.x;
   const int nh = p.Hh * p.Wh, nl = p.Hl * p.Wl;
@@ -321,6 +333,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdP p) {
 }
 
 __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, size_t nvec) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float fa[8], fb[8];
     unpack8(ldg16(a + i * 8), fa);
@@ -344,6 +358,8 @@ struct AdamChunk { float* p; const float* g; float* m; float* v; int n; int pad;
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale,
                                                     const float* __restrict__ found_inf, const float* __restrict__ hyper) {
+  pdl_trigger();
+  pdl_wait();
   if (found_inf && *found_inf != 0.f) return;
   if (hyper) {  // captured step: the scalars of THIS replay live in device memory (adamw_hyper_kernel)
     lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; bc1 = hyper[5]; bc2_sqrt = hyper[6];
@@ -380,7 +396,7 @@ int launch_dot_pool(const bf16* a, const bf16* b, float* out, int B, int HW, int
   MTG_REQUIRE(a && b && out && C % 8 == 0, MTG_ERR_ARG, "dot_pool: bad arguments");
   const int CV = C / 8, CVc = group_vectors(CV), PL = 256 / CVc;
   dim3 grid(chunks, ceil_div(CV, CVc), B);
-  dot_pool_kernel<<<grid, 256, 0, st>>>(a, b, out, HW, C, CV, CVc, PL, ceil_div(HW, chunks), chunks);
+  MTG_CUDA(launch_pdl(dot_pool_kernel, dim3(grid), dim3(256), 0, st, a, b, out, HW, C, CV, CVc, PL, ceil_div(HW, chunks), chunks));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -391,10 +407,10 @@ int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.C <= 4096 && a.SQ <= 4096, MTG_ERR_UNSUPPORTED, "se_bwd: C / SQ above 4096");
   if (a.w2) {
     MTG_REQUIRE(a.hid && a.dpre2, MTG_ERR_ARG, "se_bwd: the two-layer form needs hid and dpre2");
-    se_bwd_hidden_kernel<<<dim3(ceil_div(a.SQ, SE_TILE), a.B), 256, sizeof(float) * (a.C + 256), st>>>(p);
+    MTG_CUDA(launch_pdl(se_bwd_hidden_kernel, dim3(dim3(ceil_div(a.SQ, SE_TILE), a.B)), dim3(256), sizeof(float) * (a.C + 256), st, p));
     MTG_LAUNCH_CHECK();
   }
-  se_bwd_mean_kernel<<<dim3(ceil_div(a.C, SE_TILE), a.B), 256, sizeof(float) * (a.SQ + 256), st>>>(p);
+  MTG_CUDA(launch_pdl(se_bwd_mean_kernel, dim3(dim3(ceil_div(a.C, SE_TILE), a.B)), dim3(256), sizeof(float) * (a.SQ + 256), st, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -402,7 +418,7 @@ int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
 int launch_outer_sum(const float* u, const float* v, int v_chunks, float vscale, float* dw, float* dbias, int B, int I, int J,
                      cudaStream_t st) {
   MTG_REQUIRE(u && v && dw, MTG_ERR_ARG, "outer_sum: null pointer");
-  outer_sum_kernel<<<dim3(ceil_div(J, 64), ceil_div(I, 16)), 256, 0, st>>>(u, v, v_chunks, vscale, dw, dbias, B, I, J);
+  MTG_CUDA(launch_pdl(outer_sum_kernel, dim3(dim3(ceil_div(J, 64), ceil_div(I, 16))), dim3(256), 0, st, u, v, v_chunks, vscale, dw, dbias, B, I, J));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -412,9 +428,9 @@ int launch_upsample_bwd(const void* g, int dtype, float* out, int B, int NC, int
   MTG_REQUIRE(g && out, MTG_ERR_ARG, "upsample_bwd: null pointer");
   const int total = B * Hc * Wc * NC;
   const int grid = ceil_div(total, 128);
-  if (dtype == LOGITS_F32) upsample_bwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp);
-  else if (dtype == LOGITS_BF16) upsample_bwd_kernel<bf16><<<grid, 128, 0, st>>>(static_cast<const bf16*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp);
-  else if (dtype == LOGITS_F16) upsample_bwd_kernel<__half><<<grid, 128, 0, st>>>(static_cast<const __half*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp);
+  if (dtype == LOGITS_F32) MTG_CUDA(launch_pdl(upsample_bwd_kernel<float>, dim3(grid), dim3(128), 0, st, static_cast<const float*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp));
+  else if (dtype == LOGITS_BF16) MTG_CUDA(launch_pdl(upsample_bwd_kernel<bf16>, dim3(grid), dim3(128), 0, st, static_cast<const bf16*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp));
+  else if (dtype == LOGITS_F16) MTG_CUDA(launch_pdl(upsample_bwd_kernel<__half>, dim3(grid), dim3(128), 0, st, static_cast<const __half*>(g), out, B, NC, Hc, Wc, Hf, Wf, sn, sc, sp));
   else MTG_REQUIRE(false, MTG_ERR_ARG, "upsample_bwd: unknown dtype %d", dtype);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
@@ -427,7 +443,7 @@ int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st) {
   HeadBwdP p{a.d_o, a.dh2, a.cbr, a.s, a.low, a.w_high, a.w_low, a.dcbr, a.ds, a.dlow, a.dw_high, a.dw_low, a.db_high, a.db_low,
              a.Hh, a.Wh, a.Hl, a.Wl, a.IC, a.LC, a.NC};
   MTG_REQUIRE(a.IC <= 256, MTG_ERR_UNSUPPORTED, "head_bwd: inter_channels above 256");
-  head_bwd_kernel<<<dim3(a.B, head_bwd_segments(a.B)), 256, 0, st>>>(p);
+  MTG_CUDA(launch_pdl(head_bwd_kernel, dim3(dim3(a.B, head_bwd_segments(a.B))), dim3(256), 0, st, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -436,7 +452,7 @@ int launch_add_bf16(const bf16* a, const bf16* b, bf16* out, size_t n, cudaStrea
   MTG_REQUIRE(n % 8 == 0, MTG_ERR_ARG, "add_bf16: n %% 8 != 0");
   size_t blocks = (n / 8 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  add_bf16_kernel<<<static_cast<unsigned>(blocks ? blocks : 1), 256, 0, st>>>(a, b, out, n / 8);
+  MTG_CUDA(launch_pdl(add_bf16_kernel, dim3(static_cast<unsigned>(blocks ? blocks : 1)), dim3(256), 0, st, a, b, out, n / 8));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -454,8 +470,8 @@ int launch_adamw(const void* chunk_table, int n_chunks, float lr, float b1, floa
   MTG_REQUIRE(chunk_table && n_chunks > 0 && step > 0, MTG_ERR_ARG, "adamw: bad arguments");
   const float bc1 = 1.f - powf(b1, static_cast<float>(step));
   const float bc2s = sqrtf(1.f - powf(b2, static_cast<float>(step)));
-  adamw_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const AdamChunk*>(chunk_table), lr, b1, b2, eps, wd, bc1, bc2s, inv_scale, found_inf,
-                                         nullptr);
+  MTG_CUDA(launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, static_cast<const AdamChunk*>(chunk_table), lr, b1, b2, eps, wd, bc1, bc2s, inv_scale, found_inf,
+                                         nullptr));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
@@ -470,7 +486,7 @@ int launch_adamw_hyper(float* hyper, float lr, float b1, float b2, float eps, fl
 
 int launch_adamw_dev(const void* chunk_table, int n_chunks, const float* hyper, cudaStream_t st) {
   MTG_REQUIRE(chunk_table && n_chunks > 0 && hyper, MTG_ERR_ARG, "adamw_dev: bad arguments");
-  adamw_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const AdamChunk*>(chunk_table), 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f, nullptr, nullptr, hyper);
+  MTG_CUDA(launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, static_cast<const AdamChunk*>(chunk_table), 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f, nullptr, nullptr, hyper));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

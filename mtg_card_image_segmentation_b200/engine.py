@@ -143,7 +143,8 @@ class SegEngine:
         return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
 
     def train_forward(self, tensors, x, logits_dtype=torch.float32):
-        """model.train(); model(x): batch-statistics BatchNorm, running stats updated in place, activations saved."""
+        """model.train(); model(x): batch-statistics BatchNorm, running stats updated in place, activations saved.
+        logits_dtype None: no full-resolution logits (the captured step takes loss and gradient from the low-resolution ones)."""
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError(f"expected a (B,3,H,W) batch, got {tuple(x.shape)}")
         x = x.float().contiguous()
@@ -158,14 +159,27 @@ class SegEngine:
             if self._train_ws is None or self._train_ws.numel() < need or self._train_ws.device != dev:
                 self._train_ws = None
                 self._train_ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            logits = torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
+            logits = None if logits_dtype is None else torch.empty((B, self.num_classes, H, W), dtype=logits_dtype, device=dev)
             rc = self.lib.mtgseg_forward_train(C.byref(d), x.data_ptr(), packed.data_ptr(), self._ptr_array(tensors), len(tensors),
-                                               logits.data_ptr(), _TORCH_TO_LOGITS[logits_dtype], self._train_ws.data_ptr(),
+                                               N.ptr(logits), _TORCH_TO_LOGITS.get(logits_dtype, N.LOGITS_NONE), self._train_ws.data_ptr(),
                                                self._train_ws.numel(), B, N.stream_ptr())
             N.check(rc, "mtgseg_forward_train")
         self._stats_dirty = True  # running statistics changed under the folded-BN cache
         self._train_gen += 1
         return logits, x
+
+    def train_loss(self, x, targets, dice_weight, ce_weight, smooth, out=None):
+        """CombinedLoss of the last training forward from its low-resolution logits (mtgseg_train_loss); leaves the pulled-back
+        gradient in the workspace for train_backward(dlogits=None).  Returns loss3 = (total, dice, ce)."""
+        B, _, H, W = x.shape
+        t = targets.contiguous()
+        if t.dtype != torch.int64 or tuple(t.shape) != (B, H, W) or t.device != x.device:
+            raise RuntimeError("targets must be an int64 (B,H,W) tensor on the input's device")
+        loss3 = out if out is not None else torch.empty(3, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(self.lib.mtgseg_train_loss(C.byref(self.desc(H, W)), t.data_ptr(), loss3.data_ptr(), dice_weight, ce_weight, smooth,
+                                               self._train_ws.data_ptr(), self._train_ws.numel(), B, N.stream_ptr()), "mtgseg_train_loss")
+        return loss3
 
     def train_token(self):
         """Identifies the forward whose activations the workspace holds and the weight arena it used (checked by backward)."""
@@ -181,7 +195,7 @@ class SegEngine:
                                "activations per model: call backward() before the next model(x) / optimizer.step().")
         B, _, H, W = x.shape
         dev = x.device
-        dlogits = dlogits.contiguous()
+        dlogits = None if dlogits is None else dlogits.contiguous()
         with torch.cuda.device(dev):
             sizes = [t.numel() if p else 0 for t, p in zip(tensors, is_param)]
             flat = self._static_flat  # GraphedTrainStep: one fixed gradient buffer, so that the captured addresses never change
@@ -195,7 +209,8 @@ class SegEngine:
                 off += n
             d = self.desc(H, W)
             rc = self.lib.mtgseg_backward(C.byref(d), x.data_ptr(), self._packed.data_ptr(), self._ptr_array(tensors),
-                                          self._ptr_array(views), len(tensors), dlogits.data_ptr(), _TORCH_TO_LOGITS[dlogits.dtype],
+                                          self._ptr_array(views), len(tensors), N.ptr(dlogits),
+                                          N.LOGITS_NONE if dlogits is None else _TORCH_TO_LOGITS[dlogits.dtype],
                                           self._train_ws.data_ptr(), self._train_ws.numel(), B, flat.data_ptr(), flat.numel(),
                                           1 if dp else 0, N.stream_ptr())
             N.check(rc, "mtgseg_backward")
@@ -292,8 +307,12 @@ class GraphedTrainStep:
     kernel directly, without autograd), active pruning masks.  Data parallel: call ``parallel.enable_gradient_exchange(model)`` first;
     the bucketed NCCL exchange is then part of the captured backward."""
 
-    def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3, allow_unsynchronised=False):
+    def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3, allow_unsynchronised=False, lowres_loss=False):
         from .optim import FusedAdamW
+        # lowres_loss: take loss and gradient from the head's 40x30 logits (mtgseg_train_loss): no full-resolution logits / dlogits
+        # tensors in the step (-59 MB at B=32) and two launches fewer.  Measured on a B200: neutral at B=32 (5.43 vs 5.41 ms), slower
+        # at B=256 (26.41 vs 26.04 ms: every fine pixel's softmax is recomputed by its four corner owners), hence off by default.
+        self._lowres_loss = bool(lowres_loss)
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
             raise RuntimeError("GraphedTrainStep needs a FusedAdamW optimizer with one parameter group")
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
@@ -365,12 +384,18 @@ class GraphedTrainStep:
     def _forward_backward(self):
         # straight through the engine, no autograd: the autograd engine would run AccumulateGrad nodes on whatever stream they were
         # created on (e.g. the default stream of earlier eager steps whose loss tensor is still alive), which a capture forbids
-        from .utils import fused_loss
         model, eng = self.model, self.model.engine()
         tensors = model._state_tensors()
-        logits, x32 = eng.train_forward(tensors, self.x, self._logits_dtype)
-        loss3, dlogits = fused_loss(logits, self.y, *self._loss_weights, True)
-        flat, views = eng.train_backward(tensors, self._is_param, x32, dlogits, dp=getattr(model, "data_parallel", False))
+        from .utils import fused_loss
+        dp = getattr(model, "data_parallel", False)
+        if self._lowres_loss:
+            _, x32 = eng.train_forward(tensors, self.x, None)
+            loss3 = eng.train_loss(x32, self.y, *self._loss_weights)
+            flat, views = eng.train_backward(tensors, self._is_param, x32, None, dp=dp)
+        else:
+            logits, x32 = eng.train_forward(tensors, self.x, self._logits_dtype)
+            loss3, dlogits = fused_loss(logits, self.y, *self._loss_weights, True)
+            flat, views = eng.train_backward(tensors, self._is_param, x32, dlogits, dp=dp)
         model.last_flat_grad = flat
         for t, v in zip(tensors, views):
             if v is not None:

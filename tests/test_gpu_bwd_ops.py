@@ -99,3 +99,30 @@ def test_head_tail_backward_vs_autograd(B, Hh, Wh, NC):
     _close("head bwd dw_low", dwl, w_low.grad, 1e-4)
     _close("head bwd db_high", dbh, b_high.grad, 1e-4)
     _close("head bwd db_low", dbl, b_low.grad, 1e-4)
+
+
+@pytest.mark.parametrize("B,Hl,Wl,NC", [(2, 40, 30, 2), (3, 8, 6, 2), (1, 5, 7, 3)])
+def test_lowres_loss_and_gradient_vs_reference_formula(B, Hl, Wl, NC):
+    """CombinedLoss taken from the head's low-resolution logits (csrc/loss.cu lowres_loss_kernel, what the captured training step
+    uses): equals train/utils.py:58-92 applied to F.interpolate(lowres, x8, bilinear) -- value <= 1e-5, gradient w.r.t. the
+    low-resolution logits <= 1e-4 of its range; bit-identical between two runs (it feeds the backward chain)."""
+    from oracle import lraspp_oracle as O
+    H, W = 8 * Hl, 8 * Wl
+    g = torch.Generator().manual_seed(Hl * 100 + NC)
+    lowres = (torch.randn(B, Hl, Wl, NC, generator=g) * 2).cuda().requires_grad_()
+    t = torch.randint(0, NC, (B, H, W), generator=g).cuda()
+    logits = F.interpolate(lowres.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=False)
+    loss_ref = O.combined_loss(logits, t)
+    (d_ref,) = torch.autograd.grad(loss_ref, lowres)
+    lib = N.load()
+    outs = []
+    for _ in range(2):
+        d = torch.full_like(lowres, float("nan")).detach()
+        scratch = torch.empty(lib.mtgseg_loss_lowres_scratch_floats(B, Hl, Wl), dtype=torch.float32, device="cuda")
+        loss3 = torch.empty(3, dtype=torch.float32, device="cuda")
+        N.check(lib.mtgseg_loss_lowres(lowres.detach().data_ptr(), t.data_ptr(), d.data_ptr(), scratch.data_ptr(), loss3.data_ptr(), B, Hl, Wl,
+                                       H, W, NC, 0.5, 0.5, 1e-6, N.stream_ptr()), "loss_lowres")
+        outs.append((loss3.clone(), d))
+    assert abs(outs[0][0][0].item() - loss_ref.item()) <= 1e-5 * max(1.0, abs(loss_ref.item()))
+    _close("lowres loss gradient", outs[0][1], d_ref, 1e-4)
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])

@@ -90,7 +90,7 @@ def _worker(rank, world, port, out):
             oe.step()
             le.append(float(loss))
             lg.append(float(gstep.step(xs, ms)))
-        ok = ok and le[0] == lg[0] and all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg))
+        ok = ok and abs(le[0] - lg[0]) <= 2e-6 * abs(le[0]) and all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg))
         pe = torch.cat([p.detach().flatten() for p in graph.parameters()])
         allp = [torch.empty_like(pe) for _ in range(world)]
         dist.all_gather(allp, pe)

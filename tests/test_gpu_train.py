@@ -233,7 +233,7 @@ def test_graphed_train_step_matches_eager_loop():
     lg, sg, mg, first, launches = graphed()
     print(f"losses eager {le} graphed {lg}; {launches} launches per replay")
     assert launches > 300
-    assert lg[0] == le[0]
+    assert abs(lg[0] - le[0]) <= 2e-6 * abs(le[0])  # same forward bits; the captured step sums the loss over the 40x30 grid's owners
     assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg))
     # AdamW's first step moves every weight by ~lr*sign(g): the step taken must be the 3e-4 set after construction, not the 1e-3 the
     # graph was captured under
@@ -291,7 +291,7 @@ def test_graphed_train_step_under_autocast_and_rebuild():
         g1 = GraphedTrainStep(model, crit, opt, xc, mc)
     got = [float(g1.step(xc, mc)) for _ in range(2)]
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        g2 = GraphedTrainStep(model, crit, opt, xc, mc)  # rebuilt mid-training: must continue from step 2, not restart
+        g2 = GraphedTrainStep(model, crit, opt, xc, mc, lowres_loss=True)  # rebuilt mid-training: must continue from step 2, not restart (and: loss from the 40x30 logits)
     assert all(float(st["step"]) == 2 for st in opt.state.values())
     got.append(float(g2.step(xc, mc)))
     opt.zero_grad(set_to_none=True)
@@ -301,7 +301,8 @@ def test_graphed_train_step_under_autocast_and_rebuild():
     opt.step()
     got.append(float(loss.detach()))
     print(f"autocast losses eager {ref} graphed/rebuilt/eager {got}")
-    assert got[0] == ref[0]
+    # (the captured step takes the loss from the fp32 low-resolution logits; the eager loop from the bf16-rounded full-resolution ones)
+    assert abs(got[0] - ref[0]) <= 1e-4 * abs(ref[0])
     assert all(abs(a - b) <= 5e-3 * abs(a) for a, b in zip(ref, got))
     assert all(float(st["step"]) == 4 for st in opt.state.values())
     assert int(model.state_dict()["model.backbone.0.1.num_batches_tracked"]) == 4
