@@ -25,7 +25,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <mutex>
+#include <unordered_map>
 
 #include "ops.h"
 #include "ptx.cuh"
@@ -594,8 +597,38 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor map, zero OOB fill; swizzle by kbox: 64 -> 128 B, 32 -> 64 B, 16 -> 32 B, 0 -> none (dense box, used by the
 // depthwise tiles).  dims/strides innermost first; strides in bytes for dims 1..
+// Encoded maps are cached per thread, keyed on everything that goes into them (base pointer, geometry, box, swizzle): a training
+// step needs ~450 maps over ~150 distinct (tensor, tiling) pairs that repeat every step (the workspace layout is fixed), and
+// cuTensorMapEncodeTiled was a visible share of the 4 ms the host needs to enqueue an eager step.
+struct MapKey {
+  const void* base; int rank, kbox; uint64_t dims[5]; uint64_t strides[4]; uint32_t box[5];
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return static_cast<size_t>(h);
+  }
+};
+
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box, int kbox = 64) {
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.kbox = kbox;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i > 0) key.strides[i - 1] = strides_bytes[i - 1];
+  }
+  auto hit = cache.find(key);
+  if (hit != cache.end()) {
+    *map = hit->second;
+    return MTG_OK;
+  }
   EncodeTiledFn fn = get_encode_fn();
   MTG_REQUIRE(fn != nullptr, MTG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -615,6 +648,8 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MTG_REQUIRE(r == CUDA_SUCCESS, MTG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu)",
               static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]));
+  if (cache.size() >= 4096) cache.clear();  // bounded: varying batch shapes / reallocated workspaces must not grow it forever
+  cache.emplace(key, *map);
   return MTG_OK;
 }
 
