@@ -133,7 +133,7 @@ struct BnApplyP {
   const bf16* z; int act; const bf16* residual; bf16* y; float* gap;
   // finalize (folded in): batch statistics -> scale / shift for this CTA's channels; the CTA (chunk 0, image 0) of every channel
   // group also saves them and updates the running statistics
-  const double* stat; double count;
+  const double* stat; double count, inv_count;
   const float* gamma; const float* beta; float eps, momentum;
   float* running_mean; float* running_var; long long* num_batches_tracked;
   float* scale; float* shift; float* save_mean; float* save_rstd;
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const G
   __shared__ float s_sc[128], s_sh[128];
   pdl_trigger();
   const Lane l = lane_of(g);
-  const int n = blockIdx.z, chunk = blockIdx.x;
-  const bool writer = chunk == 0 && n == 0;
+  const int chunk = blockIdx.x;
+  const bool writer = chunk == 0 && blockIdx.z == 0;
   pdl_wait();
   if (writer && blockIdx.y == 0 && threadIdx.x == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
   // scale / shift of this CTA's channels: ONE thread per channel does the fp64 arithmetic (the fp64 issue rate is 1/64 of
@@ -155,10 +155,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const G
     for (int cl = threadIdx.x; cl < cw; cl += blockDim.x) {
       const int c = blockIdx.y * cw + cl;
       if (c < g.C) {
-        const double mean = p.stat[c] / p.count;
-        double var = p.stat[g.C + c] / p.count - mean * mean;
+        // fp64 only where cancellation needs it (E[z^2] - mean^2): three multiplies and one FMA; the reciprocal square root is the
+        // correctly rounded fp32 one (fp64 division / sqrt issue at 1/64 rate: with one prologue per CTA they cost ~15 % of the
+        // pass at B = 256)
+        const double mean = p.stat[c] * p.inv_count;
+        double var = fma(-mean, mean, p.stat[g.C + c] * p.inv_count);
         if (var < 0.0) var = 0.0;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+        const float rstd = 1.0f / sqrtf(static_cast<float>(var) + p.eps);
         const float sc = __ldg(p.gamma + c) * rstd;
         const float sh = __ldg(p.beta + c) - static_cast<float>(mean) * sc;
         s_sc[cl] = sc;
@@ -178,55 +181,58 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const G
     }
     __syncthreads();
   }
-  float gsum[1][8];
+  float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gsum[0][j] = 0.f;
-  if (l.active) {
-    float sc[8], sh[8];
+  for (int j = 0; j < 8; ++j) { sc[j] = l.active ? s_sc[l.vl * 8 + j] : 0.f; sh[j] = l.active ? s_sh[l.vl * 8 + j] : 0.f; }
+  const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
+  // a CTA walks g.ipc images (large batches: fewer, longer CTAs amortise the prologue above)
+  for (int n = blockIdx.z * g.ipc; n < min(g.B, (static_cast<int>(blockIdx.z) + 1) * g.ipc); ++n) {
+    float gsum[1][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = s_sc[l.vl * 8 + j]; sh[j] = s_sh[l.vl * 8 + j]; }
-    const int r0 = chunk * g.rows_per_chunk, r1 = min(g.HW, r0 + g.rows_per_chunk);
-    const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
-    // kRowsInFlight independent 16-byte loads per thread before the first use: the loop is latency bound otherwise (the store
-    // in the body keeps the compiler from hoisting the next row's load)
-    for (int r = r0 + l.pl; r < r1; r += kRowsInFlight * g.PL) {
-      uint4 zq[kRowsInFlight], rq[kRowsInFlight];
+    for (int j = 0; j < 8; ++j) gsum[0][j] = 0.f;
+    if (l.active) {
+      const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
+      // kRowsInFlight independent 16-byte loads per thread before the first use: the loop is latency bound otherwise (the store
+      // in the body keeps the compiler from hoisting the next row's load)
+      for (int r = r0 + l.pl; r < r1; r += kRowsInFlight * g.PL) {
+        uint4 zq[kRowsInFlight], rq[kRowsInFlight];
 #pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u) {
-        const int rr = r + u * g.PL;
-        const size_t off = img + static_cast<size_t>(rr < r1 ? rr : r) * g.C;
-        zq[u] = ldg16(p.z + off);
-        if (p.residual) rq[u] = ldg16(p.residual + off);
-      }
-#pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u) {
-        const int rr = r + u * g.PL;
-        if (rr >= r1) break;
-        const size_t off = img + static_cast<size_t>(rr) * g.C;
-        float f[8];
-        unpack8(zq[u], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], sc[j], sh[j]), p.act);
-        if (p.residual) {
-          float rf[8];
-          unpack8(rq[u], rf);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] += rf[j];
+        for (int u = 0; u < kRowsInFlight; ++u) {
+          const int rr = r + u * g.PL;
+          const size_t off = img + static_cast<size_t>(rr < r1 ? rr : r) * g.C;
+          zq[u] = ldg16(p.z + off);
+          if (p.residual) rq[u] = ldg16(p.residual + off);
         }
-        const uint4 q = pack8(f);
-        *reinterpret_cast<uint4*>(p.y + off) = q;
-        if (p.gap) {
-          float rf[8];
-          unpack8(q, rf);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) gsum[0][j] += rf[j];
+        for (int u = 0; u < kRowsInFlight; ++u) {
+          const int rr = r + u * g.PL;
+          if (rr >= r1) break;
+          const size_t off = img + static_cast<size_t>(rr) * g.C;
+          float f[8];
+          unpack8(zq[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], sc[j], sh[j]), p.act);
+          if (p.residual) {
+            float rf[8];
+            unpack8(rq[u], rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += rf[j];
+          }
+          const uint4 q = pack8(f);
+          *reinterpret_cast<uint4*>(p.y + off) = q;
+          if (p.gap) {
+            float rf[8];
+            unpack8(q, rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gsum[0][j] += rf[j];
+          }
         }
       }
     }
-  }
-  if (p.gap) {
-    float* const dst[1] = {p.gap};
-    block_reduce_store<1>(g, l, gsum, red, dst, (static_cast<size_t>(n) * g.chunks + chunk) * g.C);
+    if (p.gap) {
+      float* const dst[1] = {p.gap};
+      block_reduce_store<1>(g, l, gsum, red, dst, (static_cast<size_t>(n) * g.chunks + chunk) * g.C);
+    }
   }
 }
 
@@ -239,7 +245,7 @@ struct BnBwdP {
   const float* mean; const float* rstd;     // saved batch statistics
   int act;
   const float* se_s; const float* se_dmean; float inv_hw;  // optional: dy' = dy*se_s[n,c] + se_dmean[n,c]*inv_hw
-  double* bstat; double count;              // [2][C]: sum dyh, sum dyh*xhat (reduce adds, apply reads)
+  double* bstat; double inv_count;          // [2][C]: sum dyh, sum dyh*xhat (reduce adds, apply reads); 1 / (B*HW)
   float* dgamma; float* dbeta;              // (apply, designated CTA) = the two sums
   bf16* dz;                                 // (apply)
 };
@@ -273,8 +279,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdP p, const Geo g
       const int c = blockIdx.y * cw + cl;
       if (c < g.C) {
         const double s = p.bstat[c], sx = p.bstat[g.C + c];
-        s_c1[cl] = static_cast<float>(s / p.count);
-        s_c2[cl] = static_cast<float>(sx / p.count);
+        s_c1[cl] = static_cast<float>(s * p.inv_count);
+        s_c2[cl] = static_cast<float>(sx * p.inv_count);
         if (writer) { p.dbeta[c] = static_cast<float>(s); p.dgamma[c] = static_cast<float>(sx); }
       }
     }
@@ -341,6 +347,11 @@ Geo make_geo(int C, int HW, int want_chunks, int B) {
   g.B = B; g.ipc = 1;
   return g;
 }
+// the elementwise passes: at most ~2048 CTAs per channel group (each CTA pays a statistics prologue)
+Geo elementwise_geo(Geo g) {
+  g.ipc = ceil_div(g.B * g.chunks, 2048);
+  return g;
+}
 // the reducing passes: at most ~512 CTAs (= fp64 atomics) per channel
 Geo reducing_geo(Geo g) {
   g.ipc = ceil_div(g.B * g.chunks, 512);
@@ -376,8 +387,10 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
     ga = make_geo(a.C, a.HW, a.gap_chunks, a.B);
     grid = dim3(ga.chunks, ceil_div(ga.CV, ga.CVc), a.B);
   }
-  BnApplyP ap{a.z, a.act, a.residual, a.y, a.gap, a.stat, static_cast<double>(a.B) * a.HW, a.gamma, a.beta, a.eps, a.momentum,
+  BnApplyP ap{a.z, a.act, a.residual, a.y, a.gap, a.stat, static_cast<double>(a.B) * a.HW, 1.0 / (static_cast<double>(a.B) * a.HW), a.gamma, a.beta, a.eps, a.momentum,
               a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd};
+  ga = elementwise_geo(ga);
+  grid.z = ceil_div(a.B, ga.ipc);
   MTG_CUDA(launch_pdl(bn_apply_kernel, grid, dim3(256), 0, st, ap, ga));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
@@ -390,11 +403,13 @@ int launch_bn_train_bwd(const BnTrainBwdArgs& a, cudaStream_t st) {
   dim3 grid(g.chunks, ceil_div(g.CV, g.CVc), a.B);
   const dim3 rgrid(g.chunks, grid.y, ceil_div(a.B, gr.ipc));
   BnBwdP p{a.z, a.dy, a.scale, a.shift, a.save_mean, a.save_rstd, a.act, a.se_s, a.se_dmean, 1.f / static_cast<float>(a.HW),
-           a.bstat, static_cast<double>(a.B) * a.HW, a.dgamma, a.dbeta, a.dz};
+           a.bstat, 1.0 / (static_cast<double>(a.B) * a.HW), a.dgamma, a.dbeta, a.dz};
   if (!a.bstat_zeroed) MTG_CUDA(cudaMemsetAsync(a.bstat, 0, sizeof(double) * 2 * a.C, st));
   MTG_CUDA(launch_pdl(bn_bwd_kernel<false>, rgrid, dim3(256), 0, st, p, gr));
   MTG_LAUNCH_CHECK();
-  MTG_CUDA(launch_pdl(bn_bwd_kernel<true>, grid, dim3(256), 0, st, p, g));
+  const Geo ge = elementwise_geo(g);
+  grid.z = ceil_div(a.B, ge.ipc);
+  MTG_CUDA(launch_pdl(bn_bwd_kernel<true>, grid, dim3(256), 0, st, p, ge));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
