@@ -381,14 +381,14 @@ def run_ours(args):
                                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
                         "whole_step_algorithmic_GB/s": sum(v["bytes"] for v in agg.values()) / (total_ms * 1e-3) / 1e9}
             # dram read+write per launch of the dominant family, from the committed `ncu --set full` capture of one forward
-            # (profiles/r1_traffic.json, written by tools/forward_full_summary.py); null when no capture is committed or
+            # (profiles/r2_traffic.json, written by tools/forward_full_summary.py); null when no capture is committed or
             # it was taken at another batch size.
-            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
             if os.path.exists(tpath) and B == 256:
                 tf = json.load(open(tpath))["families"].get(dom)
                 if tf and tf["launches"] == a["launches"]:
                     roofline["traffic"] = tf["traffic_bytes_per_launch"]
-                    roofline["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, B=256, caches flushed per kernel)"
+                    roofline["traffic_source"] = "profiles/r2_traffic.json (ncu --set full, B=256, caches flushed per kernel)"
             if args.layers_out:
                 os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
                 with open(args.layers_out, "w") as f:

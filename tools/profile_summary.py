@@ -70,5 +70,45 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def fullcsv(src, dst):
+    """Same table from a CSV that was exported on the GPU box (`ncu -i X.ncu-rep --page raw --csv > X.csv`; the report itself is too
+    large to bring back), one compact row per launch."""
+    rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
+    hdr, units = rows[0], rows[1]
+    col = {n: i for i, n in enumerate(hdr)}
+    sel = [("gpu__time_duration.sum", "us", 1e-3), ("dram__bytes_read.sum", "rd MB", None), ("dram__bytes_write.sum", "wr MB", None),
+           ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram thr %", 1), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm thr %", 1),
+           ("l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex %", 1), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 thr %", 1),
+           ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps act %", 1), ("launch__registers_per_thread", "regs", 1),
+           ("launch__occupancy_limit_registers", "occ regs", 1), ("launch__occupancy_limit_shared_mem", "occ smem", 1)]
+
+    def num(r, k):
+        try:
+            return float(r[col[k]].replace(",", ""))
+        except (KeyError, ValueError):
+            return float("nan")
+
+    def mb(r, k):  # ncu scales byte columns per column (unit row): normalise to MB
+        u = units[col[k]].lower() if k in col else ""
+        f = {"byte": 1e-6, "kbyte": 1e-3, "mbyte": 1.0, "gbyte": 1e3}.get(u, 1e-6)
+        return num(r, k) * f
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full (CSV export): {src}\n\n`--clock-control none`; caches are flushed before every kernel, launches are serialised.\n\n")
+        f.write("| kernel | grid | " + " | ".join(n for _, n, _ in sel) + " | GB/s (rd+wr) |\n|---|---|" + "---:|" * (len(sel) + 1) + "\n")
+        for r in rows[2:]:
+            us = num(r, "gpu__time_duration.sum") * ({"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(units[col["gpu__time_duration.sum"]].lower(), 1e-3))
+            vals = []
+            for k, _, sc in sel:
+                if k == "gpu__time_duration.sum":
+                    vals.append(f"{us:.1f}")
+                elif sc is None:
+                    vals.append(f"{mb(r, k):.1f}")
+                else:
+                    vals.append(f"{num(r, k):.1f}")
+            gbs = (mb(r, "dram__bytes_read.sum") + mb(r, "dram__bytes_write.sum")) / us * 1e3 if us > 0 else float("nan")  # MB/us = TB/s
+            f.write(f"| `{short(r[col['Kernel Name']])[:60]}` | {r[col['Grid Size']] if 'Grid Size' in col else ''} | " + " | ".join(vals) + f" | {gbs:.0f} |\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "fullcsv": fullcsv}[sys.argv[1]](sys.argv[2], sys.argv[3])
