@@ -266,12 +266,19 @@ def run_ours(args):
         g = GraphedInference(model, x, logits_dtype=torch.bfloat16, splits=args.splits) if not args.no_graph else None
         step = (lambda: g.replay()) if g else (lambda: model.engine().infer(model._state_tensors(), x, torch.bfloat16))
         launches_per_step = g.launches_per_replay if g else None
-        for _ in range(max(3, args.warmup)):
-            step()
-        barrier()
-        l0 = lib.mtgseg_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the sampler starts before the warm-up: with 8 GPUs in the box nvidia-smi needs longer than the whole timed region (180 ms)
+        # to deliver its first line; only samples taken under load enter the summary
         with ClockSampler(local) as clk:
+            for _ in range(max(3, args.warmup)):
+                step()
+            barrier()
+            t_wait = time.perf_counter()
+            while not clk.lines and time.perf_counter() - t_wait < 3.0:  # until the first sample has arrived (untimed; keeps the GPU busy)
+                step()
+                torch.cuda.synchronize()
+            barrier()
+            l0 = lib.mtgseg_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.steps):
                 step()
@@ -319,7 +326,9 @@ def run_ours(args):
                             comp_s.wait_event(read_back[k])  # the static mask of instance k has been copied out
                             mask = graphs[k].replay()["mask"]
                         else:
-                            mask = model.predict(xbuf[k])["mask"]  # public API: uint8 argmax mask (train/evaluate.py:66-78)
+                            # public API: uint8 argmax mask (train/evaluate.py:66-78); configs[1] is the bf16 tensor-core path (the
+                            # default "auto" rule would send a float32 batch outside autocast through the fp32-exact path)
+                            mask = model.predict(xbuf[k], precision="bf16")["mask"]
                         done[k].record(comp_s)
                         computed[k].record(comp_s)
                     with torch.cuda.stream(back_s):
