@@ -20,6 +20,11 @@ namespace mtgseg {
 int make_tma_map_bf16(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
                       const unsigned long long* strides_bytes, const unsigned* box, int kbox);  // gemm_tc.cu
 
+// column-strip kernel (dwcol.cu)
+struct DwColPlan { bool ok; int P, occ, pad, Ho, Wo, band, bands, R, Wp, groups; size_t stage_bytes; };
+DwColPlan dw_col_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap);
+int launch_dwconv_col(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st);
+
 namespace {
 
 struct DwP {
@@ -575,7 +580,26 @@ DwPlan dw_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
   return q;
 }
 
+// Column-strip kernel (dwcol.cu) or the staged 8-channel kernels above?  Measured per layer at B=256 on one box (tools/dw_probe.py,
+// column / staged, us): b1 80/129, b4 82/116, b5 72/111, b7 46/53, b8 26/34, b11 53/65, b12 67/89, b13 97/152, b14 144/196; but
+// b2 204/138 and b3 154/109: 3x3 layers on large maps whose channel groups are narrower than a pixel (32 / 48-byte TMA box
+// rows out of 128 / 144-byte pixels) stay on the staged kernel, which reads whole contiguous rows.
+// MTGSEG_DW_VARIANT=8 forces the column-strip kernel wherever its tiling fits; 7 / 4 / 5 / 3 / 2 / 1 never use it.
+static bool use_col(int H, int W, int C, int k, int stride, int dil, bool need_gap, DwColPlan* plan) {
+  const int v = dw_variant();
+  if (v != 0 && v != 8) return false;
+  const DwColPlan q = dw_col_plan(H, W, C, k, stride, dil, need_gap);
+  if (!q.ok) return false;
+  if (v == 0 && k == 3 && q.groups > 1 && H * W >= 4096) return false;
+  if (plan) *plan = q;
+  return true;
+}
+
 int dwconv_chunks(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
+  {
+    DwColPlan q;
+    if (use_col(H, W, C, k, stride, dil, need_gap, &q)) return q.bands;
+  }
   if (dw_variant() == 2) {  // legacy direct-from-L1 kernel
     const int pad = (k - 1) / 2 * dil;
     const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
@@ -662,6 +686,10 @@ int launch_half(const DwConvArgs& a, const DwS& p, dim3 grid, size_t smem, cudaS
 int launch_dwconv(const DwConvArgs& a, cudaStream_t st) {
   MTG_REQUIRE(a.in && a.w && a.out && a.scale && a.shift, MTG_ERR_ARG, "dwconv: null pointer");
   MTG_REQUIRE(a.C % 8 == 0 && a.C >= 8 && a.C <= 2048, MTG_ERR_UNSUPPORTED, "dwconv: C=%d must be a multiple of 8 in [8,2048]", a.C);
+  {
+    DwColPlan q;
+    if (use_col(a.H, a.W, a.C, a.k, a.stride, a.dil, a.gap_partial != nullptr, &q)) return launch_dwconv_col(a, q, st);
+  }
   if (dw_variant() != 2) {
     const DwPlan q = dw_plan(a.H, a.W, a.C, a.k, a.stride, a.dil, a.gap_partial != nullptr);
     MTG_REQUIRE(q.ok, MTG_ERR_UNSUPPORTED, "dwconv: feature map %dx%d (C=%d, k=%d) does not fit the shared-memory tiling", a.H, a.W, a.C, a.k);

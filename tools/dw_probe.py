@@ -18,6 +18,10 @@ LAYERS = [("b1", 160, 120, 16, 3, 1, 1, 1, 0), ("b2", 160, 120, 64, 3, 2, 1, 1, 
           ("b7", 40, 30, 240, 3, 2, 1, 2, 0), ("b8", 20, 15, 200, 3, 1, 1, 2, 0), ("b9", 20, 15, 184, 3, 1, 1, 2, 0),
           ("b10", 20, 15, 184, 3, 1, 1, 2, 0), ("b11", 20, 15, 480, 3, 1, 1, 2, 1), ("b12", 20, 15, 672, 3, 1, 1, 2, 1),
           ("b13", 20, 15, 672, 5, 1, 2, 2, 1), ("b14", 20, 15, 960, 5, 1, 2, 2, 1), ("b15", 20, 15, 960, 5, 1, 2, 2, 1)]
+ONLY = [x for x in os.environ.get("DW_LAYERS", "").split(",") if x]
+if ONLY:
+    LAYERS = [l for l in LAYERS if l[0] in ONLY]
+REPS = int(os.environ.get("DW_REPS", REPS))
 dev = "cuda"
 variant = os.environ.get("MTGSEG_DW_VARIANT", "0")
 res = {"variant": variant, "batch": B, "layers": {}}
@@ -29,6 +33,10 @@ for (name, H, W, C, k, s, d, act, gap) in LAYERS:
     w = (torch.randn(k * k, C, device=dev, generator=g) * 0.2).bfloat16()
     sc = torch.rand(C, device=dev, generator=g) + 0.5
     sh = torch.randn(C, device=dev, generator=g) * 0.1
+    if os.environ.get("DW_NCU"):  # one launch per layer for a profiler capture
+        D.dwconv(xs[0], w, sc, sh, act, k, s, d, bool(gap)); torch.cuda.synchronize()
+        del xs; torch.cuda.empty_cache()
+        continue
     for i in range(nbuf):
         out, gp = D.dwconv(xs[i], w, sc, sh, act, k, s, d, bool(gap))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
