@@ -745,7 +745,14 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
 
   GemmKParams kp{};
   kp.M = g.M; kp.N = g.N; kp.K = g.K;
-  if (g.N <= 256) {
+  // MTGSEG_GEMM_BN128 (A/B): with a cheap A operand (K <= 256) cap the N tile at 128 columns: 2 x 128 TMEM columns per CTA
+  // instead of 512, so two CTAs (16 epilogue warps) share an SM; costs a re-read of the A tile from L2 per extra N tile
+  static const int bn128 = getenv("MTGSEG_GEMM_BN128") ? atoi(getenv("MTGSEG_GEMM_BN128")) : 0;
+  const int pad128 = ceil_div(g.N, 128) * 128 - g.N;
+  if (bn128 && !g.conv3x3 && g.N > 128 && g.K <= 256 && pad128 * 100 <= bn128 * g.N) {
+    kp.BN = 128;
+    kp.n_tiles = ceil_div(g.N, 128);
+  } else if (g.N <= 256) {
     kp.n_tiles = 1;
     kp.BN = static_cast<int>(align_up(g.N, 16));
   } else {
