@@ -53,11 +53,9 @@ __device__ __forceinline__ void fhfma2(float& a0, float& a1, uint32_t x, uint32_
 }
 
 constexpr int kMaxStages = 4;
-__host__ __device__ constexpr int col_strip(int stride) { return stride == 1 ? 10 : 5; }
 
-template <int KS, int S, int D, int P, int OCC>
-__global__ void __launch_bounds__(256, OCC) dw_col_kernel(const __grid_constant__ CUtensorMap tmx, const DwC p) {
-  constexpr int TH = col_strip(S);
+template <int KS, int S, int D, int P, int TH>
+__global__ void __launch_bounds__(256, 2) dw_col_kernel(const __grid_constant__ CUtensorMap tmx, const DwC p) {
   constexpr int RI = (TH - 1) * S + (KS - 1) * D + 1;  // staged rows one strip reads
   constexpr int XL = 256 / P;                          // column lanes
   extern __shared__ __align__(128) uint32_t dyn[];
@@ -205,16 +203,15 @@ __global__ void __launch_bounds__(256, OCC) dw_col_kernel(const __grid_constant_
 
 constexpr size_t kDynBudget = 106 * 1024;  // dynamic shared memory per CTA at two CTAs per SM
 constexpr int kPairSet[] = {8, 12, 16, 20, 24, 32};
-// per-stage shared-memory budget for OCC co-resident CTAs (two stages + 2.2 KB static + 1 KB reserved each, 227 KB per SM)
-// MTGSEG_DWCOL_STAGE_KB (A/B): stage size the planner may fill at two CTAs per SM (default 52; smaller = more stages in flight)
-size_t stage_budget(int occ) {
+// MTGSEG_DWCOL_STAGE_KB (A/B): stage size the planner may fill (default 52: two stages, two CTAs per SM; smaller = more stages)
+size_t stage_budget() {
   static int kb = -1;
   if (kb < 0) {
     const char* e = getenv("MTGSEG_DWCOL_STAGE_KB");
     kb = e ? atoi(e) : 52;
     if (kb < 8 || kb > 52) kb = 52;
   }
-  return occ == 3 ? 35 * 1024 : static_cast<size_t>(kb) * 1024;
+  return static_cast<size_t>(kb) * 1024;
 }
 
 int col_sms() {
@@ -228,70 +225,62 @@ int col_sms() {
   return n;
 }
 
-// MTGSEG_DWCOL_OCC (A/B): 2 or 3 pins the co-resident CTA count the planner may choose; default: both are candidates
-int col_occ_pin() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MTGSEG_DWCOL_OCC");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
 }
-
 // MTGSEG_DWCOL_STAGES (A/B): caps the shared-memory stages per CTA (default: as many as fit, 2..4)
-int col_stage_pin() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MTGSEG_DWCOL_STAGES");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
+int col_stage_pin() { static int v = env_int("MTGSEG_DWCOL_STAGES"); return v; }
+// MTGSEG_DWCOL_TH (A/B): pins the strip height of the stride-1 kernels to 10 or 20 (default: the planner's choice)
+int col_th_pin() { static int v = env_int("MTGSEG_DWCOL_TH"); return v; }
 
 }  // namespace
 
-struct DwColPlan { bool ok; int P, occ, pad, Ho, Wo, band, bands, R, Wp, groups; size_t stage_bytes; };
+struct DwColPlan { bool ok; int P, TH, pad, Ho, Wo, band, bands, R, Wp, groups; size_t stage_bytes; };
 
-// Channel pairs per CTA group, rows per band and CTAs per SM: the candidate with the best product of lane use, column balance,
-// (at half weight: halo rows cost L2 bandwidth, not issue slots) useful staged rows and resident warps (the kernel is issue
-// bound: 24 warps per SM hide more of the fixed-latency stalls than 16), under the stage budget of its occupancy.
+// Channel pairs per CTA group, strip height and rows per band: the candidate with the best product of lane use, column balance,
+// (at half weight: halo rows cost L2 bandwidth, not issue slots) useful staged rows and strip efficiency (a strip re-reads
+// (k-1)*dil halo rows from shared memory and pays its fixed costs once), under the stage budget.
 DwColPlan dw_col_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap) {
   DwColPlan best{};
   best.ok = false;
   if (C % 8 != 0 || C < 8) return best;
-  const int TH = col_strip(stride);
   const int pad = (k - 1) / 2 * dil;
   const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
   if (Ho < 1 || Wo < 1) return best;
   const int Wp = (Wo - 1) * stride + (k - 1) * dil + 1;
   if (Wp > 256) return best;  // TMA box limit
   const int pairs = C / 2;
+  const size_t budget = stage_budget();
   double best_score = -1.0;
-  for (int occ = 2; occ <= 3; ++occ) {
-    if (col_occ_pin() && occ != col_occ_pin()) continue;
-    const size_t budget = stage_budget(occ);
+  for (int TH : {10, 20}) {
+    if (stride == 2 && TH == 20) continue;
+    const int th = stride == 2 ? 5 : TH;
+    if (stride == 1 && col_th_pin() && th != col_th_pin()) continue;
     for (int P : kPairSet) {
       const int groups = ceil_div(pairs, P);
       auto rows = [&](int band) { return (band - 1) * stride + (k - 1) * dil + 1; };
       auto bytes = [&](int band) { return static_cast<size_t>(rows(band)) * Wp * P * 4; };
-      if (bytes(TH) > budget || rows(TH) > 256) continue;
-      const int ho_up = ceil_div(Ho, TH) * TH;
-      int band = TH;
-      while (band + TH <= ho_up && bytes(band + TH) <= budget && rows(band + TH) <= 256) band += TH;
+      if (bytes(th) > budget || rows(th) > 256) continue;
+      const int ho_up = ceil_div(Ho, th) * th;
+      int band = th;
+      while (band + th <= ho_up && bytes(band + th) <= budget && rows(band + th) <= 256) band += th;
       int bands = ceil_div(Ho, band);
-      band = ceil_div(ceil_div(Ho, bands), TH) * TH;  // even bands, whole strips
+      band = ceil_div(ceil_div(Ho, bands), th) * th;  // even bands, whole strips
       bands = ceil_div(Ho, band);
       if (need_gap && bands > 16) continue;
       const int XL = 256 / P;
-      const int Q = band / TH * Wo;
+      const int Q = band / th * Wo;
       const double lane = static_cast<double>(pairs) / (groups * P) * (XL * P) / 256.0;
       const double col = static_cast<double>(Q) / (ceil_div(Q, XL) * XL);
       const double halo = static_cast<double>(band * stride) / rows(band);
       const double box = P >= 16 ? 1.0 : (P == 12 ? 0.97 : 0.94);  // narrow TMA box rows (48 / 32 bytes) cost request rate
-      const double score = lane * col * (0.5 + 0.5 * halo) * box * (occ == 3 ? 1.12 : 1.0);
+      const double rows_used = static_cast<double>(Ho) / (bands * band);  // strips hanging over the last row compute unused outputs
+      const double strip = static_cast<double>(th * stride) / ((th - 1) * stride + (k - 1) * dil + 1 + 2);  // + ~2 rows of fixed cost
+      const double score = lane * col * (0.5 + 0.5 * halo) * box * rows_used * (0.6 + 0.4 * strip);
       if (score > best_score) {
         best_score = score;
-        best = DwColPlan{true, P, occ, pad, Ho, Wo, band, bands, rows(band), Wp, groups, align_up(bytes(band), 128)};
+        best = DwColPlan{true, P, th, pad, Ho, Wo, band, bands, rows(band), Wp, groups, align_up(bytes(band), 128)};
       }
     }
   }
@@ -300,7 +289,7 @@ DwColPlan dw_col_plan(int H, int W, int C, int k, int stride, int dil, bool need
 
 namespace {
 
-template <int KS, int S, int D, int P, int OCC>
+template <int KS, int S, int D, int P, int TH>
 int launch_col2(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st) {
   CUtensorMap tmx{};
   // input [B][H][W][C] bf16 as a 4-D tensor, box = (group channels, padded row, band rows + halo, 1 image); out-of-bounds
@@ -317,39 +306,37 @@ int launch_col2(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st) {
   p.act = a.act; p.C = a.C; p.Ho = q.Ho; p.Wo = q.Wo; p.pad = q.pad; p.band = q.band; p.bands = q.bands; p.R = q.R; p.Wp = q.Wp;
   p.tiles = a.B * q.bands;
   p.stage_words = static_cast<int>(q.stage_bytes / 4);
-  const int slots = OCC * col_sms();
+  const int slots = 2 * col_sms();
   int gx = slots / q.groups;
   if (gx < 1) gx = 1;
   if (gx > p.tiles) gx = p.tiles;
   gx = ceil_div(p.tiles, ceil_div(p.tiles, gx));  // same tiles per CTA, fewer CTAs
   const dim3 grid(gx, q.groups);
-  // as many stages as fit (2..4): the memory-bound layers need more than one tile in flight per CTA to cover the TMA latency
-  const size_t dyn = OCC == 3 ? 70 * 1024 : kDynBudget;
-  int stages = static_cast<int>(dyn / q.stage_bytes);
+  // as many stages as fit (2..4) (measured: more than two change nothing, the kernel is issue bound, not latency bound)
+  int stages = static_cast<int>(kDynBudget / q.stage_bytes);
   stages = stages < 2 ? 2 : (stages > kMaxStages ? kMaxStages : stages);
   if (col_stage_pin() >= 2 && col_stage_pin() <= stages) stages = col_stage_pin();
   p.stages = stages;
   const size_t smem = stages * q.stage_bytes;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    MTG_CUDA(cudaFuncSetAttribute(dw_col_kernel<KS, S, D, P, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(OCC == 3 ? 70 * 1024 : kDynBudget)));
+    MTG_CUDA(cudaFuncSetAttribute(dw_col_kernel<KS, S, D, P, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDynBudget)));
     configured = true;
   }
-  MTG_CUDA(launch_pdl(dw_col_kernel<KS, S, D, P, OCC>, grid, dim3(256), smem, st, tmx, p));
+  MTG_CUDA(launch_pdl(dw_col_kernel<KS, S, D, P, TH>, grid, dim3(256), smem, st, tmx, p));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
 
-template <int KS, int S, int D, int OCC>
+template <int KS, int S, int D, int TH>
 int launch_col1(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st) {
   switch (q.P) {
-    case 8: return launch_col2<KS, S, D, 8, OCC>(a, q, st);
-    case 12: return launch_col2<KS, S, D, 12, OCC>(a, q, st);
-    case 16: return launch_col2<KS, S, D, 16, OCC>(a, q, st);
-    case 20: return launch_col2<KS, S, D, 20, OCC>(a, q, st);
-    case 24: return launch_col2<KS, S, D, 24, OCC>(a, q, st);
-    case 32: return launch_col2<KS, S, D, 32, OCC>(a, q, st);
+    case 8: return launch_col2<KS, S, D, 8, TH>(a, q, st);
+    case 12: return launch_col2<KS, S, D, 12, TH>(a, q, st);
+    case 16: return launch_col2<KS, S, D, 16, TH>(a, q, st);
+    case 20: return launch_col2<KS, S, D, 20, TH>(a, q, st);
+    case 24: return launch_col2<KS, S, D, 24, TH>(a, q, st);
+    case 32: return launch_col2<KS, S, D, 32, TH>(a, q, st);
     default: break;
   }
   MTG_REQUIRE(false, MTG_ERR_UNSUPPORTED, "dwconv: no column-strip instantiation for %d channel pairs per group", q.P);
@@ -357,7 +344,8 @@ int launch_col1(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st) {
 
 template <int KS, int S, int D>
 int launch_col0(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st) {
-  return q.occ == 3 ? launch_col1<KS, S, D, 3>(a, q, st) : launch_col1<KS, S, D, 2>(a, q, st);
+  if constexpr (S == 2) return launch_col1<KS, S, D, 5>(a, q, st);
+  else return q.TH == 20 ? launch_col1<KS, S, D, 20>(a, q, st) : launch_col1<KS, S, D, 10>(a, q, st);
 }
 
 }  // namespace

@@ -21,7 +21,7 @@ int make_tma_map_bf16(CUtensorMap* map, const void* base, int rank, const unsign
                       const unsigned long long* strides_bytes, const unsigned* box, int kbox);  // gemm_tc.cu
 
 // column-strip kernel (dwcol.cu)
-struct DwColPlan { bool ok; int P, occ, pad, Ho, Wo, band, bands, R, Wp, groups; size_t stage_bytes; };
+struct DwColPlan { bool ok; int P, TH, pad, Ho, Wo, band, bands, R, Wp, groups; size_t stage_bytes; };
 DwColPlan dw_col_plan(int H, int W, int C, int k, int stride, int dil, bool need_gap);
 int launch_dwconv_col(const DwConvArgs& a, const DwColPlan& q, cudaStream_t st);
 

@@ -87,13 +87,27 @@ __device__ __forceinline__ void fma8_f2(float (&acc)[8], const float (&x)[8], co
   }
 }
 
+// z[0..7] *= t[0..7] as four packed fp32x2 multiplies (FMUL2)
+__device__ __forceinline__ void mul8_f2(float (&z)[8], const float (&t)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    uint64_t a, b;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(z[j]), "f"(z[j + 1]));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(t[j]), "f"(t[j + 1]));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z[j]), "=f"(z[j + 1]) : "l"(a));
+  }
+}
+
 template <bool kConv3x3, bool kAScale>
 __global__ void __launch_bounds__(kAScale ? 448 : 320, kAScale ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();  // the next kernel of the stream may be scheduled as soon as every CTA of this one is running
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by pointer arithmetic on the __shared__ base (not through uintptr_t): the compiler keeps the shared address space, so
+  // the epilogue's scale / shift loads and staging stores are LDS / STS instead of generic LD.E / ST.E with 64-bit address math
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = p.stages;
   const int BK = p.kbox;
   const int A_STAGE_BYTES = BM * BK * 2;
@@ -103,7 +117,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sBres = smem;
   uint8_t* sA = smem + b_res_bytes;
   uint8_t* sB = sA + S * A_STAGE_BYTES;
-  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + (p.b_res ? 0 : S * b_stage_bytes)) + 1023) & ~uintptr_t(1023));  // OUT_BUFS slabs
+  uint8_t* sOut = smem + ((b_res_bytes + S * A_STAGE_BYTES + (p.b_res ? 0 : S * b_stage_bytes) + 1023) & ~1023);  // OUT_BUFS slabs (smem is 1024-aligned)
   const int SLAB_BYTES = BM * p.obox * 2;
   uint8_t* sRes = sOut + p.out_bytes;                  // res_bufs x res_slabs slabs
   float* sScale = reinterpret_cast<float*>(sRes + p.res_bufs * p.res_slabs * SLAB_BYTES);
@@ -296,8 +310,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) a[e] = __uint_as_float(v[cc][h * 8 + e]);
               fma8_f2(f, a, sc);  // f = acc * scale + shift, four packed fp32x2 FMAs
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = actf(f[e]);
+              actf(f);
               if (p.res_slabs) {
                 float rf[8];
                 unpack8(*reinterpret_cast<const uint4*>(rrow + phys), rf);
@@ -309,11 +322,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       };
-      // hardswish as z * sat(z/6 + 1/2): one FFMA.SAT + one FMUL instead of add / max / min / mul / mul
-      if (p.act == ACT_HSWISH) convert([](float z) { return z * __saturatef(fmaf(z, 1.f / 6.f, 0.5f)); });
-      else if (p.act == ACT_RELU) convert([](float z) { return fmaxf(z, 0.f); });
-      else if (p.act == ACT_NONE) convert([](float z) { return z; });
-      else convert([&](float z) { return apply_act(z, p.act); });
+      // hardswish as z * sat(z/6 + 1/2): one FFMA.SAT per element + one packed FMUL2 per pair instead of add / max / min / mul / mul
+      if (p.act == ACT_HSWISH) convert([](float (&z)[8]) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = __saturatef(fmaf(z[e], 1.f / 6.f, 0.5f));
+        mul8_f2(z, t);
+      });
+      else if (p.act == ACT_RELU) convert([](float (&z)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = fmaxf(z[e], 0.f);
+      });
+      else if (p.act == ACT_NONE) convert([](float (&)[8]) {});
+      else convert([&](float (&z)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = apply_act(z[e], p.act);
+      });
     };
     // ---- BatchNorm statistics of a staged slab (training): column sums of the bf16 values the TMA store writes --------------
     if (p.stat)
@@ -745,14 +769,9 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
 
   GemmKParams kp{};
   kp.M = g.M; kp.N = g.N; kp.K = g.K;
-  // MTGSEG_GEMM_BN128 (A/B): with a cheap A operand (K <= 256) cap the N tile at 128 columns: 2 x 128 TMEM columns per CTA
-  // instead of 512, so two CTAs (16 epilogue warps) share an SM; costs a re-read of the A tile from L2 per extra N tile
-  static const int bn128 = getenv("MTGSEG_GEMM_BN128") ? atoi(getenv("MTGSEG_GEMM_BN128")) : 0;
-  const int pad128 = ceil_div(g.N, 128) * 128 - g.N;
-  if (bn128 && !g.conv3x3 && g.N > 128 && g.K <= 256 && pad128 * 100 <= bn128 * g.N) {
-    kp.BN = 128;
-    kp.n_tiles = ceil_div(g.N, 128);
-  } else if (g.N <= 256) {
+  // (capping the N tile at 128 columns for K <= 256 so that two CTAs share an SM, 2 x 128 TMEM columns each, was measured and
+  // rejected: b7.expand 52 -> 44 us but b14-16.expand 60 -> 73 us, the A tile is then fetched eight times)
+  if (g.N <= 256) {
     kp.n_tiles = 1;
     kp.BN = static_cast<int>(align_up(g.N, 16));
   } else {
