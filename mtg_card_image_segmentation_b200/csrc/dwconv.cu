@@ -179,6 +179,17 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const float (&x)[8], const
   }
 }
 
+// acc[0..7] += x[0..7] * w[0..7] on packed bf16 operands: eight FHFMA.BF16 with half-register selectors
+__device__ __forceinline__ void fh8(float (&acc)[8], const uint4& x, const uint4& w) {
+  const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\t"
+        "mov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, xl, wl, %0;\n\tfma.rn.f32.bf16 %1, xh, wh, %1;\n\t}"
+        : "+f"(acc[2 * i]), "+f"(acc[2 * i + 1]) : "r"(xs[i]), "r"(ws[i]));
+}
+
 // TMA: phase 1 is ONE 4-D box load of the band's input rows (out-of-bounds rows / columns / channels are zero filled by
 // the TMA unit = the convolution padding) plus one 2-D box load of the weights, issued by thread 0 and awaited on an
 // mbarrier; no per-thread address arithmetic.  !TMA: the same tile gathered with 16-byte cp.async (kept for A/B).
@@ -267,18 +278,35 @@ __global__ void __launch_bounds__(256, 2) dwconv_smem_kernel(const __grid_consta
         for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
 #pragma unroll 1
       for (int ky = 0; ky < KS; ++ky) {
-        float wv[KS][8];
-#pragma unroll
-        for (int kx = 0; kx < KS; ++kx) unpack8(sw[(ky * KS + kx) * p.CVc + vl], wv[kx]);
         const uint4* row = sx + (static_cast<size_t>(ry * STRIDE + ky * DIL) * p.Wp + ox0 * STRIDE) * p.CVc + vl;
+        if constexpr (F2) {
+          // FHFMA.BF16 (bf16 x bf16 + fp32, see dwcol.cu): weights and activations are used as loaded, no unpack instructions;
+          // bit-identical to the fp32 FMA on widened operands
+          uint4 wq[KS];
 #pragma unroll
-        for (int xi = 0; xi < NI; ++xi) {
-          float xf[8];
-          unpack8(row[xi * p.CVc], xf);
+          for (int kx = 0; kx < KS; ++kx) wq[kx] = sw[(ky * KS + kx) * p.CVc + vl];
 #pragma unroll
-          for (int kx = 0; kx < KS; ++kx) {
-            const int t = xi - kx * DIL;  // compile-time after unrolling
-            if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) fma8<F2>(acc[t / STRIDE], xf, wv[kx]);
+          for (int xi = 0; xi < NI; ++xi) {
+            const uint4 xq = row[xi * p.CVc];
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+              const int t = xi - kx * DIL;  // compile-time after unrolling
+              if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) fh8(acc[t / STRIDE], xq, wq[kx]);
+            }
+          }
+        } else {
+          float wv[KS][8];
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) unpack8(sw[(ky * KS + kx) * p.CVc + vl], wv[kx]);
+#pragma unroll
+          for (int xi = 0; xi < NI; ++xi) {
+            float xf[8];
+            unpack8(row[xi * p.CVc], xf);
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+              const int t = xi - kx * DIL;  // compile-time after unrolling
+              if (t >= 0 && t % STRIDE == 0 && t / STRIDE < TW) fma8<false>(acc[t / STRIDE], xf, wv[kx]);
+            }
           }
         }
       }
@@ -507,7 +535,7 @@ int dw_phase() {
   return v;
 }
 
-// MTGSEG_DW_VARIANT (A/B switch): 0 (default) staged kernel, TMA box fill, packed fp32x2 FMAs; 4 = 0 with scalar FMAs; 3 staged kernel,
+// MTGSEG_DW_VARIANT (A/B switch): 0 (default) column-strip kernel or staged kernel per layer (use_col), TMA box fill, FHFMA.BF16; 4 = staged kernel with unpack + scalar fp32 FMAs; 3 staged kernel,
 // cp.async gather fill, scalar FMAs; 5 = 3 with packed FMAs (all four bit-identical; B=256 family time 1.57 / 1.58 / 2.03 / 2.03 ms); 2 legacy direct kernel, narrow strips; 1 legacy direct kernel, wide strips
 int dw_variant() {
   static int v = -1;
