@@ -766,6 +766,10 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
               "conv_gemm: channel counts must be multiples of 8 (K=%d N=%d)", g.K, g.N);
   MTG_REQUIRE(!(g.conv3x3 && g.a_scale), MTG_ERR_UNSUPPORTED, "conv_gemm: a_scale with conv3x3 is not supported");
   MTG_REQUIRE(!g.a_scale || g.hw > 0, MTG_ERR_ARG, "conv_gemm: a_scale needs hw");
+  if (g.conv3x3) {  // plain 3x3 on small feature maps: the haloed-tile kernel (conv3_tc.cu)
+    const int rc = launch_conv3x3_halo(g, st);
+    if (rc <= 0) return rc;
+  }
 
   GemmKParams kp{};
   kp.M = g.M; kp.N = g.N; kp.K = g.K;

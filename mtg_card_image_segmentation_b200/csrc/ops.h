@@ -26,6 +26,8 @@ struct ConvGemmArgs {
   double* stat = nullptr;  // training: [2][N] fp64, += per-channel sum / sum of squares of the stored outputs (zero it first)
 };
 int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st);
+// haloed-tile 3x3 (conv3_tc.cu): MTG_OK / error, or 1 when the shape is left to launch_conv_gemm's nine-shifted-boxes path
+int launch_conv3x3_halo(const ConvGemmArgs& g, cudaStream_t st);
 
 // ---- bandwidth-bound kernels (dwconv.cu, stem.cu, se.cu, tail.cu, metrics.cu) -------------------
 struct DwConvArgs {

@@ -49,6 +49,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp: the tcgen05 / TMA issue loops run in warp-uniform control flow and predicate only the issuing
+// instructions on this, so that descriptors and loop counters stay in uniform registers (inside an `if (lane == 0)` region
+// the compiler treats them as per-thread values and wraps every UTCHMMA in an ELECT / R2UR loop: ~130 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
