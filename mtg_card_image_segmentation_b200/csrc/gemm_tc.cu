@@ -249,8 +249,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // The whole warp walks the loop in warp-uniform control flow and one elected lane issues: stage indices and descriptors
+    // then live in uniform registers.  (Inside an `if (lane == 0)` region the compiler wraps every UTCHMMA in an ELECT / R2UR
+    // loop: measured ~130 cycles of issue per MMA, which bounded every tensor-heavy layer at ~35 % of the tensor pipe.)
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.BN);
+      const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB), sBres_u = ptx::smem_u32(sBres);
       uint32_t it = 0, tc = 0;
       if (p.b_res && static_cast<int>(blockIdx.x) < total_tiles) ptx::mbar_wait(bfull, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
@@ -265,13 +269,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tc_fence_after();
           const int kc = kb % p.kb_per_tap;
           const int ksteps = (kc == p.kb_per_tap - 1) ? p.ksteps_last : (BK / 16);
-          const uint64_t adesc = ptx::umma_desc_kmajor(ptx::smem_u32(sA + s * A_STAGE_BYTES), p.desc_hi);
-          const uint64_t bdesc = ptx::umma_desc_kmajor(ptx::smem_u32(p.b_res ? sBres + kb * b_stage_bytes : sB + s * b_stage_bytes), p.desc_hi);
-          for (int k = 0; k < ksteps; ++k)  // +32 B along K inside the swizzle row == +2 in the address field
-            ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          const uint64_t adesc = ptx::umma_desc_kmajor(sA_u + s * A_STAGE_BYTES, p.desc_hi);
+          const uint64_t bdesc = ptx::umma_desc_kmajor(p.b_res ? sBres_u + kb * b_stage_bytes : sB_u + s * b_stage_bytes, p.desc_hi);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // +32 B along K inside the swizzle row == +2 in the address field
+              if (k < ksteps) ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          }
+          __syncwarp();
         }
-        ptx::umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp < 10) {

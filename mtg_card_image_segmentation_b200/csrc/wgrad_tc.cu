@@ -98,15 +98,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // MN-major operands: LBO = distance between 64-channel boxes, SBO = distance between 8-pixel row groups
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BNp) | (1u << 15) | (1u << 16);
-      const uint32_t hi = static_cast<uint32_t>(1024 >> 4) | (1u << 14) | (2u << 29);
-      for (int i = 0; i < nseg; ++i) {
-        const int s = i % STAGES;
-        ptx::mbar_wait(&full[s], (i / STAGES) & 1);
-        ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * stage_bytes), sb = sa + a_bytes;
+    // whole warp in the loop, one elected lane issues (see ptx::elect_one)
+    // MN-major operands: LBO = distance between 64-channel boxes, SBO = distance between 8-pixel row groups
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BNp) | (1u << 15) | (1u << 16);
+    const uint32_t hi = static_cast<uint32_t>(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t smem_u = ptx::smem_u32(smem);
+    for (int i = 0; i < nseg; ++i) {
+      const int s = i % STAGES;
+      ptx::mbar_wait(&full[s], (i / STAGES) & 1);
+      ptx::tc_fence_after();
+      const uint32_t sa = smem_u + s * stage_bytes, sb = sa + a_bytes;
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < SEG / 16; ++k) {
           const uint64_t adesc = ptx::umma_desc_mnmajor(sa + k * 2048, BOX_BYTES, hi);
@@ -115,8 +117,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
         }
         ptx::umma_commit(&empty[s]);
       }
-      ptx::umma_commit(done);
+      __syncwarp();
     }
+    if (ptx::elect_one()) ptx::umma_commit(done);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;
