@@ -138,8 +138,10 @@ struct BnApplyP {
   float* running_mean; float* running_var; long long* num_batches_tracked;
   float* scale; float* shift; float* save_mean; float* save_rstd;
 };
-// grid (chunks, groups, B)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const Geo g) {
+// grid (chunks, groups, B).  kRows: rows (16-byte loads per operand) a thread has in flight; layers without a residual take 8
+// (one operand stream: 4 rows leave too few bytes in flight per SM to cover the HBM latency at 3 CTAs per SM)
+template <int kRows, bool kRes>
+__global__ void __launch_bounds__(256, kRes ? 2 : 3) bn_apply_kernel(const BnApplyP p, const Geo g) {
   __shared__ float red[256 * 8];
   __shared__ float s_sc[128], s_sh[128];
   pdl_trigger();
@@ -194,17 +196,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const G
       const size_t img = static_cast<size_t>(n) * g.HW * g.C + l.c0;
       // kRowsInFlight independent 16-byte loads per thread before the first use: the loop is latency bound otherwise (the store
       // in the body keeps the compiler from hoisting the next row's load)
-      for (int r = r0 + l.pl; r < r1; r += kRowsInFlight * g.PL) {
-        uint4 zq[kRowsInFlight], rq[kRowsInFlight];
+      for (int r = r0 + l.pl; r < r1; r += kRows * g.PL) {
+        uint4 zq[kRows], rq[kRes ? kRows : 1];
 #pragma unroll
-        for (int u = 0; u < kRowsInFlight; ++u) {
+        for (int u = 0; u < kRows; ++u) {
           const int rr = r + u * g.PL;
           const size_t off = img + static_cast<size_t>(rr < r1 ? rr : r) * g.C;
           zq[u] = ldg16(p.z + off);
-          if (p.residual) rq[u] = ldg16(p.residual + off);
+          if (kRes) rq[u] = ldg16(p.residual + off);
         }
 #pragma unroll
-        for (int u = 0; u < kRowsInFlight; ++u) {
+        for (int u = 0; u < kRows; ++u) {
           const int rr = r + u * g.PL;
           if (rr >= r1) break;
           const size_t off = img + static_cast<size_t>(rr) * g.C;
@@ -212,9 +214,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p, const G
           unpack8(zq[u], f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], sc[j], sh[j]), p.act);
-          if (p.residual) {
+          if (kRes) {
             float rf[8];
-            unpack8(rq[u], rf);
+            unpack8(rq[kRes ? u : 0], rf);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += rf[j];
           }
@@ -391,7 +393,8 @@ int launch_bn_train_fwd(const BnTrainFwdArgs& a, cudaStream_t st) {
               a.running_mean, a.running_var, a.num_batches_tracked, a.scale, a.shift, a.save_mean, a.save_rstd};
   ga = elementwise_geo(ga);
   grid.z = ceil_div(a.B, ga.ipc);
-  MTG_CUDA(launch_pdl(bn_apply_kernel, grid, dim3(256), 0, st, ap, ga));
+  if (a.residual) MTG_CUDA(launch_pdl(bn_apply_kernel<kRowsInFlight, true>, grid, dim3(256), 0, st, ap, ga));
+  else MTG_CUDA(launch_pdl(bn_apply_kernel<8, false>, grid, dim3(256), 0, st, ap, ga));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }

@@ -11,7 +11,7 @@ namespace {
 
 // kU8: the batch is raw uint8 HWC camera/dataset pixels; (v/255 - mean)/std (train/dataset.py:182-185) is applied on load,
 // so the host never materialises the 4x larger normalised fp32 NCHW tensor.  Zero padding lives in the normalised domain.
-template <bool kU8>
+template <bool kU8, bool kVec>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xu8, float3 nmul,
                                                    float3 nadd, const float* __restrict__ w,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
@@ -28,17 +28,69 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   // fp32x2 over output-channel pairs (FFMA2), the input value broadcast into both halves.
   const int Wp = (Wo + 1) >> 1;  // pixel pairs per output row
   const long long total = static_cast<long long>(B) * Ho * Wp;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  // (whole warps stay in the loop: the wide-load path shuffles between lanes; lanes past the end recompute the last pair
+  // and skip the store)
+  const long long total_w = (total + 31) / 32 * 32;
+  for (long long idx0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx0 < total_w;
+       idx0 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool live = idx0 < total;
+    const long long idx = live ? idx0 : total - 1;
     const int oxp = static_cast<int>(idx % Wp);
     const long long t = idx / Wp;
     const int oy = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
     const int ox = oxp * 2;
     const bool second = ox + 1 < Wo;
-    // gather the 45 taps first (predicated, no branches between them: all loads are in flight together)
+    // gather the 45 taps first (no branches between the loads: all are in flight together)
     float xin[3][3][5];
-    if (kU8) {
+    if (kVec) {
+      // W % 4 == 0: a thread's window is columns 4*oxp - 1 .. 4*oxp + 3.  The four aligned columns come as ONE 16-byte load
+      // (fp32) / three 4-byte words (uint8 RGB) per channel-row, the column to the left from the neighbouring lane (it holds
+      // the previous pixel pair of the same row whenever oxp > 0; lane 0 loads it itself).  9 wide loads instead of 45 scalar
+      // ones: the scalar version was bound by L1 wavefronts (each warp-wide scalar load touched 16 sectors for 128 useful bytes).
+      const int lane = threadIdx.x & 31;
+      const bool need_left = oxp > 0;
+      if (kU8) {
+        const uint8_t* xn = xu8 + static_cast<size_t>(n) * H * W * 3;
+        const float mul[3] = {nmul.x, nmul.y, nmul.z}, add[3] = {nadd.x, nadd.y, nadd.z};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy * 2 - 1 + ky;
+          const bool ok = iy >= 0 && iy < H;
+          const uint8_t* row = xn + (static_cast<size_t>(ok ? iy : 0) * W + 4 * oxp) * 3;
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+          uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2);
+          uint32_t left = __shfl_up_sync(0xffffffffu, w2, 1) >> 8;  // bytes 9..11 of the neighbour = its last pixel
+          if (lane == 0 && need_left) left = static_cast<uint32_t>(__ldg(row - 3)) | (static_cast<uint32_t>(__ldg(row - 2)) << 8) | (static_cast<uint32_t>(__ldg(row - 1)) << 16);
+          const uint32_t by[5][3] = {{left & 255u, (left >> 8) & 255u, (left >> 16) & 255u},
+                                     {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u},
+                                     {w0 >> 24, w1 & 255u, (w1 >> 8) & 255u},
+                                     {(w1 >> 16) & 255u, w1 >> 24, w2 & 255u},
+                                     {(w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24}};
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+              xin[ci][ky][c] = (ok && (c > 0 || need_left)) ? fmaf(static_cast<float>(by[c][ci]), mul[ci], add[ci]) : 0.f;
+        }
+      } else {
+        const float* xn = x + static_cast<size_t>(n) * 3 * H * W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - 1 + ky;
+            const bool ok = iy >= 0 && iy < H;
+            const float* row = xn + (static_cast<size_t>(ci) * H + (ok ? iy : 0)) * W + 4 * oxp;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+            float left = __shfl_up_sync(0xffffffffu, v.w, 1);
+            if (lane == 0 && need_left) left = __ldg(row - 1);
+            xin[ci][ky][0] = (ok && need_left) ? left : 0.f;
+            xin[ci][ky][1] = ok ? v.x : 0.f; xin[ci][ky][2] = ok ? v.y : 0.f;
+            xin[ci][ky][3] = ok ? v.z : 0.f; xin[ci][ky][4] = ok ? v.w : 0.f;
+          }
+      }
+    } else if (kU8) {
       const uint8_t* xn = xu8 + static_cast<size_t>(n) * H * W * 3;
       const float mul[3] = {nmul.x, nmul.y, nmul.z}, add[3] = {nadd.x, nadd.y, nadd.z};
 #pragma unroll
@@ -99,7 +151,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     auto emit = [&](auto actf) {
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        if (p == 1 && !second) break;
+        if (!live || (p == 1 && !second)) break;
         float o0[8], o1[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -132,8 +184,16 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
   // v/255 normalised: (v/255 - mean)/std = v * 1/(255 std) - mean/std
   const float3 nmul = make_float3(1.f / (255.f * a.std[0]), 1.f / (255.f * a.std[1]), 1.f / (255.f * a.std[2]));
   const float3 nadd = make_float3(-a.mean[0] / a.std[0], -a.mean[1] / a.std[1], -a.mean[2] / a.std[2]);
-  if (a.x_u8) MTG_CUDA(launch_pdl(stem_kernel<true>, dim3(static_cast<int>(blocks)), dim3(256), 0, st, nullptr, a.x_u8, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
-  else MTG_CUDA(launch_pdl(stem_kernel<false>, dim3(static_cast<int>(blocks)), dim3(256), 0, st, a.x, nullptr, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
+  // wide loads need 4-column alignment of every row (W % 4 == 0 and an aligned base pointer)
+  const bool vec = a.W % 4 == 0 && (a.x_u8 ? (reinterpret_cast<uintptr_t>(a.x_u8) & 3) == 0 : (reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+  const dim3 grid(static_cast<int>(blocks)), block(256);
+  if (a.x_u8) {
+    if (vec) MTG_CUDA(launch_pdl(stem_kernel<true, true>, grid, block, 0, st, nullptr, a.x_u8, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
+    else MTG_CUDA(launch_pdl(stem_kernel<true, false>, grid, block, 0, st, nullptr, a.x_u8, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
+  } else {
+    if (vec) MTG_CUDA(launch_pdl(stem_kernel<false, true>, grid, block, 0, st, a.x, nullptr, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
+    else MTG_CUDA(launch_pdl(stem_kernel<false, false>, grid, block, 0, st, a.x, nullptr, nmul, nadd, a.w, a.scale, a.shift, a.out, a.B, a.H, a.W, Ho, Wo, a.act));
+  }
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
