@@ -39,7 +39,8 @@ namespace {
 
 constexpr int BM = 128;           // UMMA M
 constexpr int MAX_STAGES = 8;
-constexpr int BAR_BYTES = 320;               // mbarriers + TMEM slot
+constexpr int BAR_BYTES = 384;               // mbarriers + TMEM slot
+constexpr int MAX_RES = 8;                   // residual ring depth (mode 1)
 constexpr int OUT_BUFS = 2;                  // double-buffered output staging
 constexpr int SS_BYTES = 2 * 256 * 4;        // scale / shift of the current N tile (+ as much again for the BatchNorm statistics)
 
@@ -59,7 +60,8 @@ struct GemmKParams {
   const float* a_scale;
   int hw;
   int res_slabs;  // 0 or ceil(BN/obox)
-  int res_bufs;   // 2: residual tile prefetched one tile ahead; 1: single buffer, reloaded after the epilogue has read it (long mainloops)
+  int res_bufs;   // 1: single buffer, reloaded after the epilogue has read it (long mainloops); 2: prefetched one tile ahead;
+                  // 4..8 (mode 1, small tiles): a ring deep enough to cover the HBM latency of the residual stream as well
   int epi_mode;   // 1: per-warp epilogue (pointwise path): the two sets of 4 epilogue warps take alternate tiles, every warp stages and
                   //    TMA-stores its own 32-row sub-slab, no CTA-wide barrier; 0: all 8 warps share one slab at a time (3x3 / fallback)
   int wbufs;      // staging buffers per epilogue warp in mode 1 (1 or 2)
@@ -133,10 +135,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* xform = bars + 2 * MAX_STAGES;
   uint64_t* tfull = bars + 3 * MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* resbar = tempty + 2;  // [2]: the residual tile is double buffered and prefetched one tile ahead
-  uint64_t* bfull = resbar + 2;   // resident weights have landed
-  uint64_t* res_free = bfull + 1; // [2] (mode 1): epilogue set s has finished reading the residual of its current tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 2);
+  uint64_t* resbar = tempty + 2;  // [MAX_RES]: residual tile landed (indexed by ring slot; by epilogue set with a single buffer)
+  uint64_t* bfull = resbar + MAX_RES;   // resident weights have landed
+  uint64_t* res_free = bfull + 1; // [MAX_RES] (mode 1): the epilogue set has finished reading the residual tile in this slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + MAX_RES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,10 +152,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull[b], 1);
       ptx::mbar_init(&tempty[b], p.epi_mode ? 128 : 256);
+    }
+    for (int b = 0; b < MAX_RES; ++b) {
+      ptx::mbar_init(&resbar[b], 1);
       ptx::mbar_init(&res_free[b], 128);
     }
-    ptx::mbar_init(&resbar[0], 1);
-    ptx::mbar_init(&resbar[1], 1);
     ptx::mbar_init(bfull, 1);
     ptx::fence_mbar_init();
   }
@@ -196,16 +199,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // one sequential consumer, so the usual (use count & 1) parity is unambiguous even when one buffer serves both sets.
       auto pump = [&](uint32_t upto) {  // issue pending residual loads of tiles with counter <= upto whose buffer is free
         while (rtile < total_tiles && tcr <= upto) {
-          const uint32_t rb = p.res_bufs == 2 ? (tcr & 1) : 0;
-          // the buffer was last read for tile tcr - res_bufs, by set (tcr - res_bufs) & 1, as that set's ((tcr - res_bufs) >> 1)-th tile
+          // ring slot and barrier of residual tile t: slot t % res_bufs (an even ring: slot parity == epilogue set, so every
+          // barrier has one sequential consumer); with a single buffer the barriers are indexed by the set instead
+          const uint32_t rb = p.res_bufs >= 2 ? tcr % p.res_bufs : 0;
+          const uint32_t bi = p.res_bufs >= 2 ? rb : (tcr & 1);
+          // the slot was last read for tile tcr - res_bufs (use number (tcr - res_bufs) / res_bufs of the slot; single buffer:
+          // by set (tcr - 1) & 1 as that set's ((tcr - 1) >> 1)-th tile)
           if (tcr >= static_cast<uint32_t>(p.res_bufs)) {
             const uint32_t prev = tcr - p.res_bufs;
-            if (!ptx::mbar_try_wait(&res_free[prev & 1], (prev >> 1) & 1)) return false;
+            const bool ok = p.res_bufs >= 2 ? ptx::mbar_try_wait(&res_free[rb], (prev / p.res_bufs) & 1)
+                                            : ptx::mbar_try_wait(&res_free[prev & 1], (prev >> 1) & 1);
+            if (!ok) return false;
           }
           const int mt = rtile / p.n_tiles, nt = rtile - mt * p.n_tiles;
-          ptx::mbar_arrive_expect_tx(&resbar[tcr & 1], r_slabs * r_slab_bytes);
+          ptx::mbar_arrive_expect_tx(&resbar[bi], r_slabs * r_slab_bytes);
           for (int sl = 0; sl < r_slabs; ++sl)
-            ptx::tma_load_2d(sRes + (rb * r_slabs + sl) * r_slab_bytes, &tmR, &resbar[tcr & 1], nt * p.BN + sl * p.obox, mt * BM);
+            ptx::tma_load_2d(sRes + (rb * r_slabs + sl) * r_slab_bytes, &tmR, &resbar[bi], nt * p.BN + sl * p.obox, mt * BM);
           ++tcr;
           rtile += gridDim.x;
         }
@@ -409,10 +418,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (static_cast<int>(tc & 1) != wset) continue;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         const uint32_t buf = tc & 1, aph = (tc >> 1) & 1;
-        const uint32_t rb = p.res_bufs == 2 ? (tc & 1) : 0;
+        const uint32_t rb = p.res_bufs >= 2 ? tc % p.res_bufs : 0;  // residual ring slot (see the producer)
+        const uint32_t rbi = p.res_bufs >= 2 ? rb : static_cast<uint32_t>(wset);
         ptx::mbar_wait(&tfull[buf], aph);
         ptx::tc_fence_after();
-        if (p.res_slabs) ptx::mbar_wait(&resbar[wset], (tc >> 1) & 1);  // per-set barrier: this set's (tc >> 1)-th residual tile
+        if (p.res_slabs) ptx::mbar_wait(&resbar[rbi], p.res_bufs >= 2 ? ((tc / p.res_bufs) & 1) : ((tc >> 1) & 1));
         const uint32_t taddr = tmem_base + buf * buf_stride + (static_cast<uint32_t>(q * 32) << 16);
         for (int sl = 0; sl < slabs; ++sl, ++wstore) {
           uint8_t* sbuf = wbuf + (p.wbufs == 2 ? (wstore & 1) : 0) * WSLAB;
@@ -436,7 +446,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty[buf]);
-        if (p.res_slabs) ptx::mbar_arrive(&res_free[wset]);
+        if (p.res_slabs) ptx::mbar_arrive(&res_free[rbi]);
       }
       if (p.stat) flush_stats(blockIdx.x % p.n_tiles);
       if (lane == 0) ptx::bulk_wait_all();  // smem must stay valid until the last store has read it
@@ -909,6 +919,14 @@ int launch_conv_gemm(const ConvGemmArgs& g, cudaStream_t st) {
   const size_t slab_bytes = static_cast<size_t>(BM) * kp.obox * 2;
   // a long mainloop (>= 6 k-blocks) hides the reload of a single residual buffer; the 48-96 KB saved become ring stages
   kp.res_bufs = (kp.res_slabs && kp.num_kb >= 6) ? 1 : 2;
+  // small residual tiles (narrow layers) in the per-warp epilogue mode: the residual stream needs as much prefetch depth as the
+  // A ring has, or every tile waits a full HBM round trip for its residual (b1.project: 3.3 TB/s with two buffers); up to
+  // 32 KB of ring, an even number of slots
+  if (kp.res_slabs && kp.epi_mode && kp.res_bufs == 2) {
+    int rbufs = static_cast<int>((32 * 1024) / (kp.res_slabs * slab_bytes)) & ~1;
+    if (rbufs > MAX_RES) rbufs = MAX_RES;
+    if (rbufs > 2) kp.res_bufs = rbufs;
+  }
   // ring depth for a given amount of output staging: enough stages that two co-resident CTAs keep >= ~64 KB of loads in
   // flight per SM (HBM latency x bandwidth); prefer two co-resident CTAs over a deeper ring when that is what it costs
   auto plan = [&](size_t out_bytes, int& stages_out, size_t& need_out) {
