@@ -63,7 +63,12 @@ def test_conv1x1(M, N, K, act, res, se):
     _check(f"conv1x1 M{M} N{N} K{K}", got, ref)
 
 
-@pytest.mark.parametrize("B,H,W,N,K", [(2, 20, 15, 128, 960), (3, 4, 3, 128, 960), (5, 20, 15, 128, 64), (1, 9, 7, 32, 72)])
+# plain 3x3 on maps up to 63 pixels wide = the haloed-tile kernel (csrc/conv3_tc.cu): an odd number of M tiles (the last pair
+# holds one tile), several N tiles with a ragged last one, the dgrad shape of the head conv (128 -> 960), a 40-wide map (three
+# rows per tile), K with a ragged last 64-channel slab; wider maps (W = 70) keep the nine-shifted-boxes path of gemm_tc.cu
+@pytest.mark.parametrize("B,H,W,N,K", [(2, 20, 15, 128, 960), (3, 4, 3, 128, 960), (5, 20, 15, 128, 64), (1, 9, 7, 32, 72),
+                                       (1, 20, 15, 128, 64), (2, 30, 40, 200, 136), (3, 20, 15, 960, 128), (2, 40, 30, 48, 40),
+                                       (2, 6, 70, 32, 64)])
 def test_conv3x3(B, H, W, N, K):
     g = torch.Generator().manual_seed(B * 1000 + H)
     x = _rand(B, H, W, K, gen=g).bfloat16().to(DEV)
