@@ -295,50 +295,69 @@ __global__ void __launch_bounds__(256) dw_wgrad_rows_kernel(const DwBwdP p, int 
 
 // ---------------------------------------------------------------------------------------------------------
 // stem wgrad: dW[o][ci][ky][kx] += sum dz[n,oy,ox,o] * x[n,ci,2oy-1+ky,2ox-1+kx]   (432 outputs)
-// CTA: 64 output pixels staged in smem (27 patch values + 16 gradients each); thread t < 432 owns one weight.
+// CTA = 9 warps, warp w owns (ci, ky) = (w / 3, w % 3): 3 kx x 16 o = 48 accumulators per lane in registers.  The lanes walk the
+// output pixels of a row (ox = lane + 32 s), rows (n, oy) are dealt to the CTAs grid-stride: per pixel a lane loads its 16
+// gradients (32 contiguous bytes) and two input values (the third tap is the neighbouring lane's, by shuffle) and issues 48 FMAs.
+// (The first version staged 64-pixel patches in shared memory and spent two shared-memory loads per FMA plus an index
+// decomposition per gathered element: 1.2 ms at B = 256 for 4.2 GFLOP.)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(448) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz,
-                                                         float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
-                                                         int pix_per_cta) {
+__global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz,
+                                                         float* __restrict__ dw, int B, int H, int W, int Ho, int Wo) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float sp[64][28];
-  __shared__ float sg[64][16];
-  // 32-bit pixel indices (the launcher checks B*Ho*Wo < 2^31): the staging loop decomposes one index per gathered element,
-  // and three 64-bit divisions per element made that arithmetic the whole kernel (233 us for 49 MB of input at B=32)
-  const int total = B * Ho * Wo;
-  const int p_begin = blockIdx.x * pix_per_cta, p_end = min(total, p_begin + pix_per_cta);
-  const int t = threadIdx.x;
-  const int o = t / 27, q = t % 27;  // weight (o, q) with q = ci*9 + ky*3 + kx
-  const int plane = Ho * Wo;
-  float acc = 0.f;
-  for (int p0 = p_begin; p0 < p_end; p0 += 64) {
-    for (int i = t; i < 64 * 27; i += blockDim.x) {
-      const int pp = i / 27, qq = i - pp * 27;
-      const int pix = p0 + pp;
-      float v = 0.f;
-      if (pix < p_end) {
-        const int n = pix / plane, rem = pix - n * plane;
-        const int oy = rem / Wo, ox = rem - oy * Wo;
-        const int ci = qq / 9, r9 = qq - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
-        const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<size_t>(n) * 3 + ci) * H + iy) * W + ix);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci = warp / 3, ky = warp - ci * 3;
+  float acc[3][16];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[k][o] = 0.f;
+  const int rows = B * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    const int iy = 2 * oy - 1 + ky;
+    if (iy < 0 || iy >= H) continue;  // zero padding row (warp-uniform)
+    const float* xr = x + ((static_cast<size_t>(n) * 3 + ci) * H + iy) * W;
+    const bf16* dr = dz + static_cast<size_t>(row) * Wo * 16;
+#pragma unroll 2
+    for (int ox0 = 0; ox0 < Wo; ox0 += 32) {
+      const int ox = ox0 + lane;
+      const bool live = ox < Wo;
+      const int c = 2 * ox;
+      const float x0 = (live && c < W) ? __ldg(xr + c) : 0.f;
+      const float x1 = (live && c + 1 < W) ? __ldg(xr + c + 1) : 0.f;
+      uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
+      if (live) {
+        g0 = ldg16(dr + static_cast<size_t>(ox) * 16);
+        g1 = ldg16(dr + static_cast<size_t>(ox) * 16 + 8);
       }
-      sp[pp][qq] = v;
+      float xm = __shfl_up_sync(0xffffffffu, x1, 1);  // column 2*ox - 1 is the previous pixel's column 2*(ox-1) + 1
+      if (lane == 0) xm = (live && ox > 0) ? __ldg(xr + c - 1) : 0.f;
+      float g[16];
+      {
+        float lo[8], hi[8];
+        unpack8(g0, lo);
+        unpack8(g1, hi);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { g[o] = lo[o]; g[8 + o] = hi[o]; }
+      }
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        acc[0][o] = fmaf(g[o], xm, acc[0][o]);
+        acc[1][o] = fmaf(g[o], x0, acc[1][o]);
+        acc[2][o] = fmaf(g[o], x1, acc[2][o]);
+      }
     }
-    for (int i = t; i < 64 * 16; i += blockDim.x) {
-      const int pp = i >> 4, oo = i & 15;
-      const int pix = p0 + pp;
-      sg[pp][oo] = pix < p_end ? __bfloat162float(dz[static_cast<size_t>(pix) * 16 + oo]) : 0.f;
-    }
-    __syncthreads();
-    if (t < 432) {
-#pragma unroll 8
-      for (int pp = 0; pp < 64; ++pp) acc = fmaf(sg[pp][o], sp[pp][q], acc);
-    }
-    __syncthreads();
   }
-  if (t < 432) atomicAdd(dw + o * 27 + q, acc);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      float v = acc[k][o];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) atomicAdd(dw + o * 27 + ci * 9 + ky * 3 + k, v);
+    }
 }
 
 }  // namespace
@@ -431,10 +450,9 @@ int launch_stem_wgrad(const float* x, const bf16* dz, float* dw, int B, int H, i
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo;
   MTG_REQUIRE(total < (1LL << 31) - 64 * 1024, MTG_ERR_UNSUPPORTED, "stem_wgrad: %lld output pixels exceed the 32-bit index range", total);
-  long long ctas = 148 * 4;
-  long long per = ((total + ctas - 1) / ctas + 63) / 64 * 64;
-  ctas = (total + per - 1) / per;
-  MTG_CUDA(launch_pdl(stem_wgrad_kernel, dim3(static_cast<unsigned>(ctas)), dim3(448), 0, st, x, dz, dw, B, H, W, Ho, Wo, static_cast<int>(per)));
+  int ctas = 148 * 2;  // two CTAs of 9 warps per SM
+  if (ctas > B * Ho) ctas = B * Ho;
+  MTG_CUDA(launch_pdl(stem_wgrad_kernel, dim3(static_cast<unsigned>(ctas)), dim3(288), 0, st, x, dz, dw, B, H, W, Ho, Wo));
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
