@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > $O/r2_bench_reference.js
 FWD="python bench.py --no-graph --steps 2 --warmup 1 --no-cpu --no-train --no-pose --no-eager --no-fp32"
 $FWD > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv $FWD > $O/ncu_fwd.log 2>&1
 FWD1="python bench.py --no-graph --steps 1 --warmup 1 --no-cpu --no-train --no-pose --no-eager --no-fp32"
-ncu --set full --clock-control none -k regex:"dwconv_smem_kernel|dwconv_half_kernel|conv_gemm_kernel" -c 46 -f -o /tmp/r2_fwd $FWD1 > $O/ncu_fwd_full.log 2>&1 \
+ncu --set full --clock-control none -k regex:"dwconv_smem_kernel|dwconv_half_kernel|dw_col_kernel|conv_gemm_kernel|conv3x3_halo_kernel" -c 46 -f -o /tmp/r2_fwd $FWD1 > $O/ncu_fwd_full.log 2>&1 \
   && ncu -i /tmp/r2_fwd.ncu-rep --page raw --csv > $O/r2_prof_fwd.csv
 ncu --set full --clock-control none -k regex:"stem_kernel|se_fused_kernel|gap_kernel|head_mix_kernel|upsample_out_kernel" -c 14 -f -o /tmp/r2_misc $FWD1 > $O/ncu_misc_full.log 2>&1 \
   && ncu -i /tmp/r2_misc.ncu-rep --page raw --csv > $O/r2_prof_misc.csv

@@ -17,8 +17,10 @@ import sys
 
 
 def kind_of(name):
-    if "dwconv" in name:
+    if "dwconv" in name or "dw_col_kernel" in name:
         return "dwconv"
+    if "conv3x3_halo_kernel" in name:
+        return "conv_gemm_3x3"
     m = re.search(r"conv_gemm_kernel<\s*(\d)\s*,\s*(\d)\s*>", name)
     if not m:
         return "?"
@@ -53,7 +55,7 @@ def main(src, layers_json, dst_md, dst_json):
         assert kind_of(name) == e["kernel"], (name, e)
         rd, wr = mbytes(r, "dram__bytes_read.sum"), mbytes(r, "dram__bytes_write.sum")
         rec = {
-            "layer": e["name"], "kernel": e["kernel"], "template": re.search(r"(\w+_kernel<[^>]*>)", name).group(1),
+            "layer": e["name"], "kernel": e["kernel"], "template": (re.search(r"(\w+_kernel<[^>]*>)", name) or re.search(r"(\w+_kernel)", name)).group(1),
             "grid": r[col["Grid Size"]], "block": r[col["Block Size"]],
             "ncu_us": val(r, "gpu__time_duration.sum"), "event_us": e["ms"] * 1e3,
             "dram_read_MB": rd, "dram_write_MB": wr, "traffic_MB": rd + wr, "algorithmic_MB": e["bytes"] / 1e6,
