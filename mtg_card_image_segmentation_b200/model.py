@@ -205,7 +205,8 @@ class CardSegmentationModel(nn.Module):
                 slots.append((self.get_submodule(prefix) if prefix else self, attr))
             self._slots = slots
             # the slots that are Parameters in the reference layout: their identity validates the cache
-            self._param_slots = [(m, a) for m, a in slots if a in m._parameters]
+            # (a model that was pruned BEFORE its first forward holds `<attr>_orig` instead: still a parameter slot)
+            self._param_slots = [(m, a) for m, a in slots if a in m._parameters or (a + "_orig") in m._parameters]
         return self._slots
 
     def _state_tensors(self):

@@ -236,6 +236,23 @@ def test_uint8_input_path_matches_normalised_fp32_path():
     assert (m_u8.long() == torch.argmax(a, 1)).all()
 
 
+def test_graphed_inference_follows_weight_updates():
+    """A captured inference graph reads the packed weight arena: replays after an in-place parameter update (optimizer step,
+    load_state_dict) must see the new weights without any eager call in between (stale packed weights)."""
+    from mtg_card_image_segmentation_b200.engine import GraphedInference
+    x = O.synthetic_cards(2, seed=5, height=64, width=48)[0].cuda()
+    model = _model(O.calibrate_running_stats(O.make_weights(33), x.cpu()))
+    with torch.no_grad():
+        gi = GraphedInference(model, torch.zeros_like(x), logits_dtype=torch.float32)
+        before = gi.run(x).clone()
+        bias = dict(model.named_parameters())["model.classifier.high_classifier.bias"]
+        bias.add_(torch.tensor([1.5, -0.5], device=bias.device))
+        after = gi.run(x).clone()
+        eager = model.engine().infer(model._state_tensors(), x, logits_dtype=torch.float32, precision="bf16")
+    assert float((after - before).abs().max()) > 0.4, "the replay did not see the updated classifier bias"
+    assert torch.equal(after, eager)
+
+
 def test_graphed_inference_mask_only_matches_predict():
     """engine.GraphedInference(logits_dtype=None, want_mask=True): the CUDA-graph replay the e2e bench leg uses must give the
     mask of model.predict bit for bit, for normalised fp32 NCHW batches and for raw uint8 HWC frames, across replays."""

@@ -313,6 +313,46 @@ def test_graphed_train_step_under_autocast_and_rebuild():
     assert int(model.state_dict()["model.backbone.0.1.num_batches_tracked"]) == 4
 
 
+def test_structured_pruning_flow():
+    """train/prune.py:76-93 (`PRUNING_STRUCTURED = True`): `prune.ln_structured(module, 'weight', amount=int(out_channels * 0.3),
+    n=2, dim=0)` on every Conv2d.  torch keeps the tensor shapes and masks whole output channels, so on the drop-in it is the
+    mask path again: evaluation with the masks active equals the oracle on the masked weights, whole filters are zero in the
+    effective weights, a training step leaves them without gradient, and prune.remove restores the 319-key layout."""
+    import torch.nn.utils.prune as prune
+    x, m = O.synthetic_cards(4, seed=10, height=64, width=48)
+    sd = O.calibrate_running_stats(O.make_weights(44), x)
+    xc, mc = x.cuda(), m.cuda()
+    model = _train_model(sd).eval()
+    pruned_filters = 0
+    for mod in model.model.modules():  # the loop of apply_structured_pruning
+        if isinstance(mod, torch.nn.Conv2d) and mod.out_channels > 1:
+            n = int(mod.out_channels * 0.3)
+            if n > 0:
+                prune.ln_structured(mod, name="weight", amount=n, n=2, dim=0)
+                pruned_filters += n
+    assert pruned_filters > 1000
+    masked_sd = {k: v.detach().cpu() for k, v in zip(model._ref_keys, model._state_tensors())}
+    dead = sum(int((masked_sd[k].flatten(1).abs().sum(1) == 0).sum()) for k in sd if sd[k].dim() == 4)
+    assert dead >= pruned_filters
+    with torch.no_grad():
+        got = model(xc).float().cpu()
+    ref = O.forward_bf16_emulated(masked_sd, x)
+    assert D.report("structured pruning (masks active) vs emulated oracle on masked weights", got, ref)[0] <= 2e-2
+    model.train()
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0)
+    crit = M.CombinedLoss()
+    opt.zero_grad(set_to_none=True)
+    loss = crit(model(xc), mc)
+    loss.backward()
+    opt.step()
+    assert float(loss.detach()) == float(loss.detach())
+    for mod in model.model.modules():
+        if hasattr(mod, "weight_mask"):
+            assert bool((mod.weight_orig.grad[mod.weight_mask == 0] == 0).all())
+            prune.remove(mod, "weight")
+    assert sorted(model.state_dict().keys()) == sorted(sd.keys())
+
+
 def test_pruning_flow_masks_active_then_removed():
     """train/prune.py:52-113,144-175 on the drop-in model: global magnitude pruning of the conv children, evaluation and fine-tuning
     with the masks ACTIVE (weight = weight_orig * weight_mask, maintained by torch's pruning hook), then prune.remove.  No call
