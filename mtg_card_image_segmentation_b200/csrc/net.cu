@@ -3,6 +3,8 @@
 // in the activation workspace, and enqueues the kernels of one inference forward on a stream.
 #include "net.h"
 
+#include <stdlib.h>
+
 #include <vector>
 
 namespace mtgseg {
@@ -54,6 +56,12 @@ void plan_convbn(ConvBnPlan& c, int& pi, Bump& arena, size_t w_elems, size_t w_e
 
 const BlockCfg* block_table() { return kBlocks; }
 
+// MTGSEG_PIXEL_PACK=0 (A/B): narrow 1x1 layers as plain [M][16] GEMMs
+static bool pixel_packing_enabled() {
+  static const bool on = [] { const char* e = getenv("MTGSEG_PIXEL_PACK"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 void LayerProfiler::begin(const char* name, const char* kernel, double bytes, double flops) {
   Rec r{};
   snprintf(r.name, sizeof(r.name), "%s", name);
@@ -92,6 +100,18 @@ int build_plan(const mtgseg_net_desc& d, NetPlan& P) {
       b.fc2_b_off = arena.take(c.cexp * sizeof(float));
     }
     plan_convbn(b.project, pi, arena, static_cast<size_t>(c.cout) * c.cexp, 2, c.cout, eps_bb, true, c.cexp);
+    // pixel packing of the narrow full-resolution projections (see ConvBnPlan::pp): 16 -> 16 as 64 -> 64 over four pixels
+    // (and 72 -> 24 with its 48-byte output / residual rows as 144 -> 48 over two pixels)
+    int want_pp = 1;
+    if (!c.se && c.cexp <= 16 && c.cout <= 16) want_pp = 64 / c.cexp;
+    else if (!c.se && c.cexp == 72 && c.cout == 24 && c.stride == 1) want_pp = 2;
+    if (want_pp > 1 && pixel_packing_enabled()) {
+      b.project.pp = want_pp;
+      const int pp = b.project.pp;
+      b.project.wpp_off = arena.take(static_cast<size_t>(pp) * c.cout * pp * c.cexp * 2);
+      b.project.scale_pp_off = arena.take(static_cast<size_t>(pp) * c.cout * sizeof(float));
+      b.project.shift_pp_off = arena.take(static_cast<size_t>(pp) * c.cout * sizeof(float));
+    }
   }
   plan_convbn(P.last, pi, arena, 960 * 160, 2, 960, eps_bb, true, 160);
   const int ic = d.inter_channels, nc = d.num_classes;
@@ -140,6 +160,14 @@ static int pack_weights_impl(const NetPlan& P, const void* const* params, void* 
     RC(launch_cast_bf16(f(b.project.w_idx), reinterpret_cast<bf16*>(base + b.project.w_off), static_cast<size_t>(c.cout) * c.cexp, st));
     RC(launch_pack_transpose_bf16(f(b.project.w_idx), reinterpret_cast<bf16*>(base + b.project.wt_off), c.cout, c.cexp, st));
     RC(fold(b.project));
+    if (b.project.pp > 1) {
+      const int pp = b.project.pp;
+      RC(launch_pack_blockdiag(f(b.project.w_idx), reinterpret_cast<bf16*>(base + b.project.wpp_off), c.cout, c.cexp, pp, st));
+      for (int q = 0; q < pp; ++q)
+        RC(launch_fold_bn(f(b.project.gamma), f(b.project.beta), f(b.project.mean), f(b.project.var), b.project.eps,
+                          reinterpret_cast<float*>(base + b.project.scale_pp_off) + q * c.cout,
+                          reinterpret_cast<float*>(base + b.project.shift_pp_off) + q * c.cout, c.cout, st));
+    }
   }
   RC(launch_cast_bf16(f(P.last.w_idx), reinterpret_cast<bf16*>(base + P.last.w_off), 960 * 160, st));
   RC(launch_pack_transpose_bf16(f(P.last.w_idx), reinterpret_cast<bf16*>(base + P.last.wt_off), 960, 160, st));
@@ -251,9 +279,15 @@ int run_infer(const NetPlan& P, const InferIO& io, uint8_t* ws, size_t ws_bytes,
       g.scale = wf(b.project.scale_off); g.shift = wf(b.project.shift_off); g.act = ACT_NONE;
       g.residual = (c.stride == 1 && c.cin == c.cout) ? inp : nullptr;
       g.a_scale = sescale; g.hw = H * W;
+      if (b.project.pp > 1 && g.M % b.project.pp == 0) {  // pp pixels per GEMM row, block-diagonal weights: same bytes, 128-byte rows
+        const int pp = b.project.pp;
+        g.M /= pp; g.K *= pp; g.N *= pp;
+        g.w = wb(b.project.wpp_off); g.scale = wf(b.project.scale_pp_off); g.shift = wf(b.project.shift_pp_off);
+      }
       snprintf(nm, sizeof(nm), "b%d.project %dx%d %d->%d", i + 1, H, W, c.cexp, c.cout);
-      PROF(sescale ? "conv_gemm_1x1_se" : "conv_gemm_1x1", 2.0 * g.M * (g.K + g.N * (g.residual ? 2 : 1)) + 2.0 * g.N * g.K,
-           2.0 * g.M * g.N * g.K, launch_conv_gemm(g, st));
+      const double pm = static_cast<double>(B) * H * W;  // algorithmic bytes / flops of the layer itself (not of the packed GEMM)
+      PROF(sescale ? "conv_gemm_1x1_se" : "conv_gemm_1x1", 2.0 * pm * (c.cexp + c.cout * (g.residual ? 2 : 1)) + 2.0 * c.cout * c.cexp,
+           2.0 * pm * c.cout * c.cexp, launch_conv_gemm(g, st));
     }
     t = o;
     if (i == 3) { low = o; Hl = H; Wl = W; }  // features[4] -> 'low' (tv:models/segmentation/lraspp.py:87-91)

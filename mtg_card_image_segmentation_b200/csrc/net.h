@@ -17,6 +17,11 @@ struct ConvBnPlan {
   size_t w_off = 0, scale_off = 0, shift_off = 0;  // offsets into the packed arena
   size_t wt_off = 0;  // dgrad operand (transposed / flipped weights), 1x1 and 3x3 convs only
   int cin = 0;        // input channels of the dense convs
+  // pixel packing (inference, narrow 1x1 layers): pp consecutive pixels form ONE GEMM row of pp * cin channels and the weights
+  // become block diagonal [pp * cout][pp * cin] (scale / shift replicated pp times), so that TMA moves 128-byte rows instead
+  // of 32-byte ones.  The activations are the same bytes: a [M][C] row-major matrix IS a [M / pp][pp * C] matrix.
+  int pp = 1;
+  size_t wpp_off = 0, scale_pp_off = 0, shift_pp_off = 0;
 };
 
 struct BlockPlan {

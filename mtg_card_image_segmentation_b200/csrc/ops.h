@@ -200,6 +200,8 @@ int launch_adamw_dev(const void* chunk_table, int n_chunks, const float* hyper, 
 // [N][K] fp32 -> [K][N] bf16 ; [O][I][3][3] fp32 -> [I][9 (flipped)][O] bf16   (dgrad operands)
 int launch_pack_transpose_bf16(const float* in, bf16* out, int N, int K, cudaStream_t st);
 int launch_pack_dgrad3x3(const float* in, bf16* out, int O, int I, cudaStream_t st);
+// in [N][K] fp32 -> out [pp * N][pp * K] bf16, block diagonal (pp copies of the matrix, zeros elsewhere)
+int launch_pack_blockdiag(const float* in, bf16* out, int N, int K, int pp, cudaStream_t st);
 
 // ---- weight packing (pack.cu) --------------------------------------------------------------------
 int launch_cast_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);

@@ -11,7 +11,7 @@
 namespace mtgseg {
 namespace {
 
-enum PackType : int { PK_CAST = 0, PK_COPY, PK_OTAPI, PK_DW, PK_STEM, PK_FOLD, PK_TRANSPOSE, PK_DGRAD3 };
+enum PackType : int { PK_CAST = 0, PK_COPY, PK_OTAPI, PK_DW, PK_STEM, PK_FOLD, PK_TRANSPOSE, PK_DGRAD3, PK_BLOCKDIAG };
 struct PackJob {
   int type, a, b, c;  // dims (meaning per type)
   float eps;
@@ -105,6 +105,16 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__
         out[i] = __float2bfloat16(in[(static_cast<size_t>(o) * I + ci) * 9 + (8 - t)]);
       }
     } break;
+    case PK_BLOCKDIAG: {  // in [N][K] -> out [pp * N][pp * K], pp copies on the diagonal
+      bf16* out = static_cast<bf16*>(j.out0);
+      const int N = j.a, K = j.b, pp = j.c;
+      const int KK = K * pp;
+      for (size_t i = start; i < j.n; i += stride) {
+        const int col = static_cast<int>(i % KK), row = static_cast<int>(i / KK);
+        const bool on = row / N == col / K;
+        out[i] = __float2bfloat16(on ? in[static_cast<size_t>(row % N) * K + col % K] : 0.f);
+      }
+    } break;
     default: break;
   }
 }
@@ -181,6 +191,16 @@ __global__ void dgrad3x3_kernel(const float* __restrict__ in, bf16* __restrict__
   }
 }
 
+__global__ void blockdiag_kernel(const float* __restrict__ in, bf16* __restrict__ out, int N, int K, int pp) {
+  const int KK = K * pp;
+  const size_t n = static_cast<size_t>(N) * pp * KK;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % KK), row = static_cast<int>(i / KK);
+    const bool on = row / N == col / K;
+    out[i] = __float2bfloat16(on ? in[static_cast<size_t>(row % N) * K + col % K] : 0.f);
+  }
+}
+
 inline int blocks_for(size_t n) {
   size_t b = (n + 255) / 256;
   if (b > 1024) b = 1024;
@@ -223,6 +243,13 @@ int launch_pack_transpose_bf16(const float* in, bf16* out, int N, int K, cudaStr
 int launch_pack_dgrad3x3(const float* in, bf16* out, int O, int I, cudaStream_t st) {
   if (record(PK_DGRAD3, O, I, 0, 0.f, static_cast<unsigned long long>(O) * I * 9, in, nullptr, nullptr, nullptr, out, nullptr)) return MTG_OK;
   dgrad3x3_kernel<<<blocks_for(static_cast<size_t>(O) * I * 9), 256, 0, st>>>(in, out, O, I);
+  MTG_LAUNCH_CHECK();
+  return MTG_OK;
+}
+int launch_pack_blockdiag(const float* in, bf16* out, int N, int K, int pp, cudaStream_t st) {
+  const unsigned long long n = static_cast<unsigned long long>(N) * pp * K * pp;
+  if (record(PK_BLOCKDIAG, N, K, pp, 0.f, n, in, nullptr, nullptr, nullptr, out, nullptr)) return MTG_OK;
+  blockdiag_kernel<<<blocks_for(n), 256, 0, st>>>(in, out, N, K, pp);
   MTG_LAUNCH_CHECK();
   return MTG_OK;
 }
