@@ -52,6 +52,18 @@ unsigned long long launch_count();
 // pdl_trigger() at their top so that THEIR successor can be scheduled early.  Works the same inside a CUDA-graph capture
 // (programmatic edges).  MTGSEG_PDL=0 launches everything with full serialisation (A/B).
 bool pdl_enabled();
+// Launches made by this thread while a PdlScope(false) is alive are fully serialised.  Programmatic dependent launch pays for
+// chains of SHORT kernels; with long kernels the early-launched dependents only take CTA slots from their predecessor while
+// they sit in griddepcontrol.wait (measured on the training step: B=32 4.97 -> 4.69 ms with it, B=256 22.53 -> 23.09 ms).
+class PdlScope {
+ public:
+  explicit PdlScope(bool allow);
+  ~PdlScope();
+  PdlScope(const PdlScope&) = delete;
+  PdlScope& operator=(const PdlScope&) = delete;
+ private:
+  bool prev_;
+};
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -15,10 +15,13 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static thread_local bool t_pdl_scope = true;
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("MTGSEG_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+  return on && t_pdl_scope;
 }
+PdlScope::PdlScope(bool allow) : prev_(t_pdl_scope) { t_pdl_scope = allow; }
+PdlScope::~PdlScope() { t_pdl_scope = prev_; }
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

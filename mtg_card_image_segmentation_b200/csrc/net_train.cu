@@ -186,10 +186,16 @@ size_t train_workspace_bytes(const NetPlan& P, int batch) {
   return T.bytes;
 }
 
+constexpr int kBigBatch = 128;  // per-GPU batch from which the step is throughput bound, not launch-chain bound
+
 int run_train_forward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
   TrainBufs T;
   layout(P, io.batch, ws, T);
-  // MTGSEG_BN_EPI=0 (A/B): statistics from a separate pass over z instead of the conv epilogues
+  // Large per-GPU batches: no programmatic dependent launch (see PdlScope; the two measured points put the break-even at ~105
+  // images).  MTGSEG_BN_EPI=0 (A/B): statistics from a separate pass over z instead of the conv epilogues (measured: the epilogue
+  // statistics win at B=32, 4.84 -> 4.69 ms; at B=256 the separate pass wins only WITH dependent launch, 23.09 -> 22.79 ms, and
+  // loses without it, 22.53 -> 22.81 ms).
+  PdlScope pdl_scope(io.batch < kBigBatch);
   static const bool epi_stats = [] { const char* e = getenv("MTGSEG_BN_EPI"); return !(e && e[0] == '0'); }();
   auto SD = [&](double* p) { return epi_stats ? p : nullptr; };
   MTG_REQUIRE(T.bytes <= ws_bytes, MTG_ERR_WORKSPACE, "forward_train: workspace too small: need %zu bytes, got %zu", T.bytes, ws_bytes);
@@ -318,6 +324,7 @@ SideStream* side_stream() {
 }
 
 int run_train_backward(const NetPlan& P, const TrainIO& io, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
+  PdlScope pdl_scope(io.batch < kBigBatch);  // see run_train_forward
   TrainBufs T;
   layout(P, io.batch, ws, T);
   MTG_REQUIRE(T.bytes <= ws_bytes, MTG_ERR_WORKSPACE, "backward: workspace too small: need %zu bytes, got %zu", T.bytes, ws_bytes);
