@@ -186,3 +186,31 @@ def test_graphed_train_step_rejects_what_it_cannot_capture():
     two = FusedAdamW([{"params": list(model.parameters())[:10]}, {"params": list(model.parameters())[10:]}], lr=1e-3)
     with pytest.raises(RuntimeError, match="one parameter group"):
         GraphedTrainStep(model.train(), M.CombinedLoss(), two, x, y)
+
+
+def test_state_slots_of_a_model_pruned_before_its_first_forward():
+    """train/prune.py prunes a freshly loaded model.  torch's pruning moves `weight` out of `module._parameters` (it becomes
+    `weight_orig` + `weight_mask` and a plain attribute recomputed by a hook): the 319 reference slots and the 178 parameter slots
+    must be recognised all the same, whether the slot table is built before or after the surgery, for unstructured and for
+    structured (`ln_structured`, train/prune.py:76-93) pruning, and `prune.remove` must restore the reference layout."""
+    import torch.nn.utils.prune as prune
+    for structured in (False, True):
+        model = M.create_model(2, pretrained=False)
+        ref_keys = list(model.state_dict().keys())
+        convs = [m for m in model.model.modules() if isinstance(m, torch.nn.Conv2d)]
+        if structured:
+            for m in convs:
+                n = int(m.out_channels * 0.3)
+                if m.out_channels > 1 and n > 0:
+                    prune.ln_structured(m, name="weight", amount=n, n=2, dim=0)
+        else:
+            prune.global_unstructured([(m, "weight") for m in convs], pruning_method=prune.L1Unstructured, amount=0.3)
+        tensors = model._state_tensors()  # first call AFTER the surgery
+        assert len(tensors) == 319 and len(model._param_slots) == 178
+        assert sum(t.requires_grad for t in tensors) == 178
+        masked = [m for m in convs if hasattr(m, "weight_mask")]
+        assert masked and all(bool((m.weight[m.weight_mask == 0] == 0).all()) for m in masked)
+        for m in masked:
+            prune.remove(m, "weight")
+        assert sorted(model.state_dict().keys()) == sorted(ref_keys)  # (prune.remove re-registers `weight` after `bias`: same keys, new order)
+        assert sum(t.requires_grad for t in model._state_tensors()) == 178
